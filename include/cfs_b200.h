@@ -1,0 +1,136 @@
+/*
+ * cfs_b200.h -- C ABI of libcfs_b200.so: the B200-native (sm_100a) Convex-Feasible-Set hot path.
+ *
+ * Drop-in boundary for JessicaLeu-code/MotionPlanning_5D_m.  The reference has no FFI layer of
+ * its own; the boundary is the MATLAB class contract used by its mains
+ *     self = CFS_FANUC(obs, sys_info, ROBOT); self = self.optimizer();     (main_FANUC.m:150-151,
+ *     RRTstar_CFS.m:194-195, Lib/functions/s_Solver.m:33-36)
+ * and every entry point below replaces the body of one reference function (cited per function).
+ * A MEX gateway (matlab/cfs_mex.cpp) or any FFI (ctypes: motionplanning_5d_m_b200/_lib.py) binds
+ * exactly these symbols.  See INTEGRATION.md.
+ *
+ * Conventions
+ *   - all arrays are column-major FP64 exactly as MATLAB stores them; "n x B" means problem b
+ *     occupies elements [n*b, n*(b+1)).
+ *   - caller owns every host buffer; the library owns all device memory behind cfs_ctx.
+ *   - return value: 0 = ok, <0 = CFS_E_* (message via cfs_last_error).  Per-problem outcomes go
+ *     to status[] and never to the return code.
+ *   - one cfs_ctx is bound to one CUDA device and one stream; it is not thread-safe, but any
+ *     number of contexts/processes may coexist (MATLAB parfor workers: s_Parallel_rrt.m:16).
+ *   - there is NO CPU fallback: every entry point fails with CFS_E_CUDA if no sm_100 device
+ *     is usable.
+ */
+#ifndef CFS_B200_H
+#define CFS_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct cfs_ctx cfs_ctx;
+
+/* robot_kind: selects the FK flavour / joint offset exactly as CFS_FANUC.m:49-54 selects dist_arm_all */
+enum { CFS_ROBOT_M16IB = 0, /* Lib/M16iB/dist_arm_3D_Heu_2.m */
+       CFS_ROBOT_M200I = 1, /* Lib/200i/dist_arm_3D_200i_2.m (joint 2 offset -pi/2, :11) */
+       CFS_ROBOT_2L = 2 };  /* Lib/2L/dist_arm_2L.m + CapPos2.m */
+
+enum { CFS_SOLVER_CFS = 0,     /* Lib/CFS_FANUC.m    */
+       CFS_SOLVER_PSGCFS = 1 };/* Lib/PSGCFS_FANUC.m */
+
+enum { CFS_GRAD_NUMJAC = 0,    /* Lib/functions/num_jac.m (class path, CFS_FANUC.m:118) */
+       CFS_GRAD_DERIVEST = 1 };/* derivest on dist_link_*(linkid) (script path, M16iB/main_CFS.m:234-237) */
+
+/* status[b] low byte */
+enum { CFS_STATUS_CONVERGED = 0,  /* ||x_-x_old|| < epsilon_O                 (EVAL.m:64-67)  */
+       CFS_STATUS_MAX_ITER = 1,   /* iter_O > MAX_O_ITER                      (EVAL.m:69-72)  */
+       CFS_STATUS_INFEASIBLE = 2, /* QP infeasible: quadprog returns [] and the reference's rollout throws (CFS_FANUC.m:85-92) */
+       CFS_STATUS_NUMERICAL = 3 };
+/* status[b] flag bits */
+#define CFS_FLAG_TOUCH 0x100 /* the |dis|<1e-4 "axes touch" branch was taken at some evaluated configuration
+                                (dist_arm_3D_Heu_2.m:22-24).  On M16iB the reference subtracts a 3x1 from a 6x1
+                                there and throws; this library evaluates the 200i/dist_link form points(1:3). */
+
+enum { CFS_E_ARG = -1, CFS_E_CUDA = -2, CFS_E_STATE = -3, CFS_E_NOMEM = -4, CFS_E_NUMERIC = -5 };
+
+/* ---- context ------------------------------------------------------------------------------------------ */
+int         cfs_create(cfs_ctx **out, int device_id);
+void        cfs_destroy(cfs_ctx *ctx);
+const char *cfs_last_error(const cfs_ctx *ctx); /* ctx may be NULL: returns the last creation error */
+const char *cfs_version(void);
+/* Run on a caller-owned CUDA stream (cudaStream_t passed as void*; e.g. torch.cuda.current_stream().cuda_stream) so that
+ * the caller's events bracket the library's kernels.  NULL restores the context's own stream. */
+int cfs_set_stream(cfs_ctx *ctx, void *cuda_stream);
+
+/* ---- problem data ------------------------------------------------------------------------------------- */
+/* robotproperty2.m:12-139 -> sys_info.robot.{DH (6x4), base (3), cap{i}.p (3x2 per link), delta_t}; T2L = robot.T
+ * (3x3, only for CFS_ROBOT_2L, else NULL).  n_joints = sys_info.njoint (links used = first n_joints rows). */
+int cfs_set_robot(cfs_ctx *ctx, int robot_kind, const double *DH /*6x4*/, int dh_rows, const double *base /*3*/,
+                  const double *cap_p /*3x2xn_joints*/, int n_joints, const double *T2L /*3x3 or NULL*/, double dt);
+/* obs{j}.l (3x2), obs{j}.D, obs{j}.epsilon   (main_FANUC.m:56-60) */
+int cfs_set_obstacles(cfs_ctx *ctx, const double *seg /*3x2xn_obs*/, const double *D, const double *eps, int n_obs);
+/* sys_info.{H, QQ, lim, MAX_input} (main_FANUC.m:106-127).  lim==NULL: no velocity rows (M16iB/main_CFS.m path);
+ * max_input==NULL: no bounds.  Factors QQ once on the device and builds the shared Gram operator. */
+int cfs_set_cost(cfs_ctx *ctx, int H, const double *QQ /*n x n, n=H*n_joints*/, const double *lim /*n_joints*/,
+                 const double *max_input /*n*/);
+
+/* ---- the hot path ------------------------------------------------------------------------------------- */
+/* CFS_FANUC.optimizer (Lib/CFS_FANUC.m:62-79) / PSGCFS_FANUC.optimizer (Lib/PSGCFS_FANUC.m:65-82) for B problems.
+ *   x0 = sys_info.xR(:,1), ff = sys_info.ff, caug = sys_info.caug, xref = sys_info.x_, noise = the normrnd draws of
+ *   PSGCFS_FANUC.m:109 (n x max_outer x B, iteration-major per problem; NULL = zeros), alpha = sys_info.alpha.
+ *   outputs: u = self.u, x = self.x_, cost_hist = self.eval.cost_all (NaN padded), e_u_hist = self.eval.e_u_all,
+ *   iters = self.iter_O-1, status as above.  e_u_hist may be NULL. */
+int cfs_solve_batch(cfs_ctx *ctx, int B, int solver, int grad, const double *x0 /*2nj x B*/, const double *ff /*n x B*/,
+                    const double *caug /*B*/, const double *xref /*2njH x B*/, const double *noise, double eps_outer,
+                    int max_outer, double alpha, double *u /*n x B*/, double *x /*2njH x B*/,
+                    double *cost_hist /*max_outer x B*/, double *e_u_hist /*max_outer x B or NULL*/, int *iters /*B*/,
+                    int *status /*B*/);
+/* Same, every pointer is a DEVICE pointer on ctx's device (inputs already resident in HBM); asynchronous on the
+ * context stream unless sync != 0. */
+int cfs_solve_batch_device(cfs_ctx *ctx, int B, int solver, int grad, const double *x0, const double *ff,
+                           const double *caug, const double *xref, const double *noise, double eps_outer,
+                           int max_outer, double alpha, double *u, double *x, double *cost_hist, double *e_u_hist,
+                           int *iters, int *status, int sync);
+
+/* dist_arm_all + gradient for N configurations against every obstacle
+ * (CFS_FANUC.m:115-118: dist_arm_3D_Heu_2 / dist_arm_3D_200i_2 / dist_arm_2L + num_jac, or derivest+dist_link_*).
+ *   dist (n_obs x N), linkid (n_obs x N, 1-based), grad (nj x n_obs x N), flags (N: CFS_FLAG_TOUCH or 0). */
+int cfs_dist_grad(cfs_ctx *ctx, int N, int grad_mode, const double *theta /*nj x N*/, double *dist, int *linkid,
+                  double *grad, int *flags);
+
+/* CFS_FANUC.get_con (Lib/CFS_FANUC.m:101-135) for ONE problem, dense and in the reference's row order
+ * (per obstacle j, step i: 1 obstacle row, nj rows +Baug_w, nj rows -Baug_w).  Ainq is m x n column-major,
+ * m = n_obs*H*(1+2nj) (or n_obs*H when no lim was set).  margin_is_D: 0 -> obs.epsilon (CFS), 1 -> obs.D (PSGCFS). */
+int cfs_get_con(cfs_ctx *ctx, int grad_mode, int margin_is_D, const double *x0, const double *xcur /*2njH*/,
+                const double *u /*n*/, double *Ainq, double *binq);
+
+/* RRT_FANUC.feasible (Lib/RRT_FANUC.m:146-181) for N candidate nodes: feasible[i]=1 iff every link distance to every
+ * obstacle is >= obs.D; dmin = min distance over links and obstacles. */
+int cfs_nodes_feasible(cfs_ctx *ctx, int N, const double *theta /*nj x N*/, unsigned char *feasible, double *dmin);
+/* RRT_FANUC.getRandNode nearest scan + steer (Lib/RRT_FANUC.m:116-129) for S samples against one tree:
+ * parent[s] = argmin_i ||(nodes(:,i)-sample(:,s)).*ratial|| (first minimum, 0-based), newnode = parent + (sample-parent)*step/||parent-sample||. */
+int cfs_nearest_steer(cfs_ctx *ctx, int n_nodes, const double *nodes /*nj x n_nodes*/, int S, const double *samples /*nj x S*/,
+                      const double *ratial /*nj*/, double step, int *parent /*S*/, double *newnode /*nj x S*/);
+
+/* ---- introspection (profiling / bench) ---------------------------------------------------------------- */
+typedef struct {
+  double ms_setup;        /* last cfs_set_cost: device factorisation time                                 */
+  double ms_total;        /* last cfs_solve_batch*: device time of the whole solve (CUDA events)          */
+  double ms_grad;         /* ... of the distance/gradient kernel launches                                 */
+  double ms_qp;           /* ... of the QP/rollout kernel launches                                        */
+  double ms_h2d, ms_d2h;  /* host-pointer entry only                                                      */
+  long long grad_waypoints; /* (problem, waypoint, obstacle) gradient evaluations done                    */
+  long long problem_iters;  /* sum over problems of outer iterations                                      */
+  long long qp_steps;       /* sum of dual active-set iterations                                          */
+  int launches;           /* kernels launched by the last solve                                           */
+  int max_active;         /* largest working set seen                                                     */
+} cfs_stats;
+int cfs_get_stats(const cfs_ctx *ctx, cfs_stats *out);
+/* level 1 (default): whole-solve time only; level 2: per-kernel CUDA events (ms_grad / ms_qp) */
+int cfs_set_timing(cfs_ctx *ctx, int level);
+/* FP64 FMA micro-benchmark (roofline denominator: MEASURED_PEAKS.json has no FP64 entry). Returns TFLOP/s. */
+int cfs_measure_fp64_peak(cfs_ctx *ctx, double *tflops, double *sm_clock_mhz_est);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

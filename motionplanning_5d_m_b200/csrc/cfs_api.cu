@@ -1,0 +1,746 @@
+// cfs_api.cu -- C ABI of libcfs_b200.so (include/cfs_b200.h): context, device buffers, stream orchestration.
+//
+// Host side of the hot path: replaces the bodies of CFS_FANUC.optimizer (Lib/CFS_FANUC.m:62-79) and
+// PSGCFS_FANUC.optimizer (Lib/PSGCFS_FANUC.m:65-82) by a fixed, sync-free sequence of kernel launches on one stream:
+//   set-up (once per cost):  Cholesky + primitive solve + Gram GEMM                       (k_setup.cu)
+//   per batch:               u0 = -QQ^{-1} FF (GEMM), v0 = P u0, init / first stop test   (k_qp.cu)
+//   per outer iteration:     K1 distance+gradient over the active list -> K3 QP/roll-out/stop (device work queue,
+//                            device-built next active list; the host never reads anything back until the end)
+// There is no CPU fallback: every entry point needs a CUDA device.
+#include "../../include/cfs_b200.h"
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "cfs_kernels.cuh"
+
+using namespace cfs;
+
+static std::string g_create_error;
+
+struct DevBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+};
+
+struct cfs_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;      // stream in use
+  cudaStream_t own_stream = nullptr;  // created by cfs_create
+  std::string err;
+  // tables
+  DevTables htab;
+  DevTables *dtab = nullptr;
+  DerivestTab *ddv = nullptr;
+  bool have_robot = false, have_obs = false, have_cost = false;
+  int nj = 0, nobs = 0;
+  // cost
+  int H = 0, n = 0;
+  bool has_lim = false, has_bounds = false;
+  double qq_norm_inf = 0.0;
+  double *dQQ = nullptr, *dG = nullptr, *dgn = nullptr, *dGI = nullptr, *dgnI = nullptr;
+  double *dlim = nullptr, *dumax = nullptr, *dworkL = nullptr, *dworkY = nullptr;
+  int *dinfo = nullptr;
+  bool have_GI = false;
+  // batch buffers
+  DevBuf x0, ff, caug, xref, noise, u, x, cost, eu, u0, v0, cost0, dist, grad, lid, iters, status, flags, listA, listB,
+      counters, slab, scratch_theta, scratch_out, qpsteps, fupper;
+  int slab_grid = 0, slab_ld = 0;
+  // timing
+  std::vector<cudaEvent_t> ev;
+  cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+  int timing_level = 1;
+  cfs_stats stats;
+};
+
+static int fail(cfs_ctx *c, int code, const char *fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (c)
+    c->err = buf;
+  else
+    g_create_error = buf;
+  return code;
+}
+
+#define CU(call)                                                                                     \
+  do {                                                                                               \
+    cudaError_t e_ = (call);                                                                         \
+    if (e_ != cudaSuccess)                                                                           \
+      return fail(ctx, CFS_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+static int ensure(cfs_ctx *ctx, DevBuf &b, size_t bytes) {
+  if (bytes <= b.cap) return 0;
+  if (b.p) cudaFree(b.p);
+  b.p = nullptr;
+  b.cap = 0;
+  cudaError_t e = cudaMalloc(&b.p, bytes);
+  if (e != cudaSuccess) return fail(ctx, CFS_E_NOMEM, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+  b.cap = bytes;
+  return 0;
+}
+template <class T>
+static T *ptr(DevBuf &b) {
+  return reinterpret_cast<T *>(b.p);
+}
+
+extern "C" const char *cfs_version(void) { return "cfs_b200 0.1 (sm_100a)"; }
+
+extern "C" const char *cfs_last_error(const cfs_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+extern "C" int cfs_create(cfs_ctx **out, int device_id) {
+  if (!out) return fail(nullptr, CFS_E_ARG, "cfs_create: out is NULL");
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(nullptr, CFS_E_CUDA, "cfs_create: no CUDA device (%s); libcfs_b200 has no CPU fallback",
+                cudaGetErrorString(e));
+  if (device_id < 0 || device_id >= ndev) return fail(nullptr, CFS_E_ARG, "cfs_create: device %d of %d", device_id, ndev);
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, device_id);
+  if (prop.major != 10)
+    return fail(nullptr, CFS_E_CUDA, "cfs_create: device %d is sm_%d%d; this library is built for sm_100a only", device_id,
+                prop.major, prop.minor);
+  cfs_ctx *ctx = new cfs_ctx();
+  ctx->device = device_id;
+  memset(&ctx->stats, 0, sizeof(ctx->stats));
+  memset(&ctx->htab, 0, sizeof(ctx->htab));
+  if (cudaSetDevice(device_id) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaMalloc(&ctx->dtab, sizeof(DevTables)) != cudaSuccess || cudaMalloc(&ctx->ddv, sizeof(DerivestTab)) != cudaSuccess ||
+      cudaMalloc(&ctx->dinfo, sizeof(int)) != cudaSuccess || cudaEventCreate(&ctx->ev_a) != cudaSuccess ||
+      cudaEventCreate(&ctx->ev_b) != cudaSuccess) {
+    fail(nullptr, CFS_E_CUDA, "cfs_create: %s", cudaGetErrorString(cudaGetLastError()));
+    delete ctx;
+    return CFS_E_CUDA;
+  }
+  // DERIVEST constants (derivest.m:203,238,282,431,493-525), FP64 on the host once
+  DerivestTab dv;
+  memset(&dv, 0, sizeof(dv));
+  {
+    const double sr = 2.0000001, srinv = 1.0 / sr;
+    for (int k = 0; k < DV_NDEL; ++k) dv.delta[k] = 100.0 * pow(sr, (double)(-k));
+    // fdarule = [1 0]/fdamat(sr,1,2), fdamat(i,j)=c(j)*srinv^((i-1)(2j-1)), c=[1 1/6]
+    double A[2][3] = {{1.0, srinv, 1.0}, {1.0 / 6.0, (1.0 / 6.0) * pow(srinv, 3), 0.0}};
+    if (fabs(A[1][0]) > fabs(A[0][0]))
+      for (int k = 0; k < 3; ++k) std::swap(A[0][k], A[1][k]);
+    const double f = A[1][0] / A[0][0];
+    A[1][1] -= f * A[0][1];
+    A[1][2] -= f * A[0][2];
+    dv.fdarule[1] = A[1][2] / A[1][1];
+    dv.fdarule[0] = (A[0][2] - A[0][1] * dv.fdarule[1]) / A[0][0];
+    const double ex[2] = {4, 6};
+    for (int i = 0; i < 4; ++i) {
+      dv.rmat[i][0] = 1.0;
+      for (int j = 0; j < 2; ++j) dv.rmat[i][1 + j] = (i == 0) ? 1.0 : pow(srinv, i * ex[j]);
+    }
+    for (int j = 0; j < 3; ++j) {  // economy QR by twice-iterated modified Gram-Schmidt
+      double v[4];
+      for (int i = 0; i < 4; ++i) v[i] = dv.rmat[i][j];
+      for (int k = 0; k < 3; ++k) dv.rr[k][j] = 0;
+      for (int pass = 0; pass < 2; ++pass)
+        for (int k = 0; k < j; ++k) {
+          double dot = 0;
+          for (int i = 0; i < 4; ++i) dot += dv.q[i][k] * v[i];
+          dv.rr[k][j] += dot;
+          for (int i = 0; i < 4; ++i) v[i] -= dot * dv.q[i][k];
+        }
+      double nn = 0;
+      for (int i = 0; i < 4; ++i) nn += v[i] * v[i];
+      nn = sqrt(nn);
+      dv.rr[j][j] = nn;
+      for (int i = 0; i < 4; ++i) dv.q[i][j] = v[i] / nn;
+    }
+    double rinv[3][3] = {{0}};
+    for (int c = 0; c < 3; ++c)
+      for (int i = 2; i >= 0; --i) {
+        double s = (i == c) ? 1.0 : 0.0;
+        for (int k = i + 1; k < 3; ++k) s -= dv.rr[i][k] * rinv[k][c];
+        rinv[i][c] = s / dv.rr[i][i];
+      }
+    const double cov11 = rinv[0][0] * rinv[0][0] + rinv[0][1] * rinv[0][1] + rinv[0][2] * rinv[0][2];
+    dv.errfac = 12.7062047361747 * sqrt(cov11);
+  }
+  cudaMemcpy(ctx->ddv, &dv, sizeof(dv), cudaMemcpyHostToDevice);
+  ctx->own_stream = ctx->stream;
+  *out = ctx;
+  return 0;
+}
+
+extern "C" int cfs_set_stream(cfs_ctx *ctx, void *cuda_stream) {
+  if (!ctx) return CFS_E_ARG;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  ctx->stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
+  return 0;
+}
+
+static void free_buf(DevBuf &b) {
+  if (b.p) cudaFree(b.p);
+  b.p = nullptr;
+  b.cap = 0;
+}
+
+extern "C" void cfs_destroy(cfs_ctx *ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  DevBuf *bufs[] = {&ctx->x0, &ctx->ff, &ctx->caug, &ctx->xref, &ctx->noise, &ctx->u, &ctx->x, &ctx->cost, &ctx->eu,
+                    &ctx->u0, &ctx->v0, &ctx->cost0, &ctx->dist, &ctx->grad, &ctx->lid, &ctx->iters, &ctx->status,
+                    &ctx->flags, &ctx->listA, &ctx->listB, &ctx->counters, &ctx->slab, &ctx->scratch_theta,
+                    &ctx->scratch_out, &ctx->qpsteps, &ctx->fupper};
+  for (DevBuf *b : bufs) free_buf(*b);
+  double *ds[] = {ctx->dQQ, ctx->dG, ctx->dgn, ctx->dGI, ctx->dgnI, ctx->dlim, ctx->dumax, ctx->dworkL, ctx->dworkY};
+  for (double *d : ds)
+    if (d) cudaFree(d);
+  if (ctx->dtab) cudaFree(ctx->dtab);
+  if (ctx->ddv) cudaFree(ctx->ddv);
+  if (ctx->dinfo) cudaFree(ctx->dinfo);
+  for (cudaEvent_t e : ctx->ev) cudaEventDestroy(e);
+  if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);
+  if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+  delete ctx;
+}
+
+static int upload_tables(cfs_ctx *ctx) {
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaMemcpyAsync(ctx->dtab, &ctx->htab, sizeof(DevTables), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+extern "C" int cfs_set_robot(cfs_ctx *ctx, int robot_kind, const double *DH, int dh_rows, const double *base,
+                             const double *cap_p, int n_joints, const double *T2L, double dt) {
+  if (!ctx) return CFS_E_ARG;
+  if (!DH || !base || !cap_p) return fail(ctx, CFS_E_ARG, "cfs_set_robot: NULL argument");
+  if (n_joints < 2 || n_joints > CFS_MAXL || dh_rows < n_joints)
+    return fail(ctx, CFS_E_ARG, "cfs_set_robot: n_joints=%d (2..%d), dh_rows=%d", n_joints, CFS_MAXL, dh_rows);
+  if (robot_kind < CFS_ROBOT_M16IB || robot_kind > CFS_ROBOT_2L) return fail(ctx, CFS_E_ARG, "cfs_set_robot: kind %d", robot_kind);
+  if (robot_kind == CFS_ROBOT_2L && !T2L) return fail(ctx, CFS_E_ARG, "cfs_set_robot: 2L needs robot.T");
+  if (!(dt > 0)) return fail(ctx, CFS_E_ARG, "cfs_set_robot: dt must be positive");
+  DevTables &t = ctx->htab;
+  for (int i = 0; i < CFS_MAXL; ++i) memset(&t.link[i], 0, sizeof(LinkTab));
+  for (int i = 0; i < n_joints; ++i) {
+    LinkTab &L = t.link[i];
+    const double d = DH[i + dh_rows * 1], a = DH[i + dh_rows * 2], al = DH[i + dh_rows * 3];
+    if (robot_kind == CFS_ROBOT_2L) {  // CapPos2.m:21-27: R = Rz(theta), T = robot.T(:,i+1)
+      L.ca = 1.0;
+      L.sa = 0.0;
+      L.a = 0.0;
+      L.tx = T2L[0 + 3 * (i + 1 < 3 ? i + 1 : 2)];
+      L.ty = T2L[1 + 3 * (i + 1 < 3 ? i + 1 : 2)];
+      L.dz = T2L[2 + 3 * (i + 1 < 3 ? i + 1 : 2)];
+    } else {  // CapPos.m:13-16
+      L.ca = cos(al);
+      L.sa = sin(al);
+      L.a = a;
+      L.tx = 0.0;
+      L.ty = 0.0;
+      L.dz = d;
+    }
+    L.th_off = (robot_kind == CFS_ROBOT_M200I && i == 1) ? -(3.14159265358979323846 / 2) : 0.0;  // dist_arm_3D_200i_2.m:11
+    for (int k = 0; k < 2; ++k)
+      for (int c = 0; c < 3; ++c) L.cap[k][c] = cap_p[c + 3 * k + 6 * i];
+  }
+  for (int c = 0; c < 3; ++c) t.base[c] = base[c];
+  t.dt = dt;
+  t.kind = robot_kind;
+  t.nj = n_joints;
+  ctx->nj = n_joints;
+  ctx->have_robot = true;
+  ctx->have_cost = false;  // n depends on nj
+  return upload_tables(ctx);
+}
+
+extern "C" int cfs_set_obstacles(cfs_ctx *ctx, const double *seg, const double *D, const double *eps, int n_obs) {
+  if (!ctx) return CFS_E_ARG;
+  if (n_obs < 0 || n_obs > CFS_MAX_OBS) return fail(ctx, CFS_E_ARG, "cfs_set_obstacles: n_obs=%d (0..%d)", n_obs, CFS_MAX_OBS);
+  if (n_obs > 0 && !seg) return fail(ctx, CFS_E_ARG, "cfs_set_obstacles: NULL seg");
+  DevTables &t = ctx->htab;
+  for (int j = 0; j < n_obs; ++j) {
+    ObsTab &o = t.obs[j];
+    double D2 = 0.0;
+    for (int c = 0; c < 3; ++c) {
+      o.s[c] = seg[c + 6 * j];
+      o.d2[c] = seg[3 + c + 6 * j] - seg[c + 6 * j];  // distLinSeg.m:26
+    }
+    for (int c = 0; c < 3; ++c) D2 += o.d2[c] * o.d2[c];  // distLinSeg.m:30
+    o.D2 = D2;
+    o.D = D ? D[j] : 0.0;
+    o.eps = eps ? eps[j] : 0.0;
+    o.pad_ = 0.0;
+  }
+  t.nobs = n_obs;
+  ctx->nobs = n_obs;
+  ctx->have_obs = true;
+  return upload_tables(ctx);
+}
+
+extern "C" int cfs_set_cost(cfs_ctx *ctx, int H, const double *QQ, const double *lim, const double *max_input) {
+  if (!ctx) return CFS_E_ARG;
+  if (!ctx->have_robot) return fail(ctx, CFS_E_STATE, "cfs_set_cost: call cfs_set_robot first");
+  if (H < 1 || !QQ) return fail(ctx, CFS_E_ARG, "cfs_set_cost: H=%d", H);
+  CU(cudaSetDevice(ctx->device));
+  const int nj = ctx->nj, n = H * nj, np = 3 * n;
+  double *ds[] = {ctx->dQQ, ctx->dG, ctx->dgn, ctx->dGI, ctx->dgnI, ctx->dlim, ctx->dumax, ctx->dworkL, ctx->dworkY};
+  for (double *d : ds)
+    if (d) cudaFree(d);
+  ctx->dQQ = ctx->dG = ctx->dgn = ctx->dGI = ctx->dgnI = ctx->dlim = ctx->dumax = ctx->dworkL = ctx->dworkY = nullptr;
+  ctx->have_cost = false;
+  ctx->have_GI = false;
+  CU(cudaMalloc(&ctx->dQQ, sizeof(double) * n * n));
+  CU(cudaMalloc(&ctx->dG, sizeof(double) * (size_t)np * np));
+  CU(cudaMalloc(&ctx->dgn, sizeof(double) * np));
+  CU(cudaMalloc(&ctx->dworkL, sizeof(double) * n * n));
+  CU(cudaMalloc(&ctx->dworkY, sizeof(double) * (size_t)n * np));
+  CU(cudaMalloc(&ctx->dlim, sizeof(double) * CFS_MAXL));
+  CU(cudaMalloc(&ctx->dumax, sizeof(double) * n));
+  // symmetrise on the host: quadprog uses (QQ+QQ')/2 semantics for the quadratic form
+  std::vector<double> q((size_t)n * n);
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j < n; ++j) q[i + (size_t)n * j] = 0.5 * (QQ[i + (size_t)n * j] + QQ[j + (size_t)n * i]);
+  ctx->qq_norm_inf = 0.0;
+  for (int i = 0; i < n; ++i) {
+    double rs = 0.0;
+    for (int j = 0; j < n; ++j) rs += fabs(q[i + (size_t)n * j]);
+    if (rs > ctx->qq_norm_inf) ctx->qq_norm_inf = rs;
+  }
+  CU(cudaMemcpyAsync(ctx->dQQ, q.data(), sizeof(double) * n * n, cudaMemcpyHostToDevice, ctx->stream));
+  double limb[CFS_MAXL] = {0};
+  if (lim)
+    for (int k = 0; k < nj; ++k) limb[k] = lim[k];
+  CU(cudaMemcpyAsync(ctx->dlim, limb, sizeof(limb), cudaMemcpyHostToDevice, ctx->stream));
+  if (max_input) CU(cudaMemcpyAsync(ctx->dumax, max_input, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
+  ctx->has_lim = lim != nullptr;
+  ctx->has_bounds = max_input != nullptr;
+  CU(cudaEventRecord(ctx->ev_a, ctx->stream));
+  CU(setup_gram(n, H, nj, ctx->htab.dt, ctx->dQQ, ctx->dworkL, ctx->dworkY, ctx->dG, ctx->dgn, ctx->dinfo, ctx->stream));
+  CU(cudaEventRecord(ctx->ev_b, ctx->stream));
+  int info = 0;
+  CU(cudaMemcpyAsync(&info, ctx->dinfo, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, ctx->ev_a, ctx->ev_b);
+  ctx->stats.ms_setup = ms;
+  if (info != 0) return fail(ctx, CFS_E_NUMERIC, "cfs_set_cost: QQ is not positive definite (pivot %d)", info);
+  ctx->H = H;
+  ctx->n = n;
+  ctx->have_cost = true;
+  return 0;
+}
+
+static int ensure_GI(cfs_ctx *ctx) {  // identity-metric Gram operator for the PSGCFS projection
+  if (ctx->have_GI) return 0;
+  const int n = ctx->n, np = 3 * n;
+  CU(cudaMalloc(&ctx->dGI, sizeof(double) * (size_t)np * np));
+  CU(cudaMalloc(&ctx->dgnI, sizeof(double) * np));
+  CU(setup_gram(n, ctx->H, ctx->nj, ctx->htab.dt, nullptr, ctx->dworkL, ctx->dworkY, ctx->dGI, ctx->dgnI, ctx->dinfo,
+                ctx->stream));
+  ctx->have_GI = true;
+  return 0;
+}
+
+static int check_ready(cfs_ctx *ctx, bool need_cost) {
+  if (!ctx->have_robot) return fail(ctx, CFS_E_STATE, "robot not set (cfs_set_robot)");
+  if (!ctx->have_obs) return fail(ctx, CFS_E_STATE, "obstacles not set (cfs_set_obstacles)");
+  if (need_cost && !ctx->have_cost) return fail(ctx, CFS_E_STATE, "cost not set (cfs_set_cost)");
+  return 0;
+}
+
+// ---- the solve, device pointers --------------------------------------------------------------------------------------
+static int solve_device(cfs_ctx *ctx, int B, int solver, int grad, const double *x0, const double *ff,
+                        const double *caug, const double *xref, const double *noise, double eps_outer, int max_outer,
+                        double alpha, double *u, double *x, double *cost_hist, double *e_u_hist, int *iters, int *status) {
+  const int nj = ctx->nj, H = ctx->H, n = ctx->n, np = 3 * n, O = ctx->nobs, OH = O * H;
+  cudaStream_t st = ctx->stream;
+  if (solver == CFS_SOLVER_PSGCFS) return fail(ctx, CFS_E_ARG, "PSGCFS solver path not built yet");
+  int rc;
+  if ((rc = ensure(ctx, ctx->u0, sizeof(double) * (size_t)n * B))) return rc;
+  if ((rc = ensure(ctx, ctx->v0, sizeof(double) * (size_t)np * B))) return rc;
+  if ((rc = ensure(ctx, ctx->cost0, sizeof(double) * B))) return rc;
+  if ((rc = ensure(ctx, ctx->fupper, sizeof(double) * B))) return rc;
+  if ((rc = ensure(ctx, ctx->dist, sizeof(double) * (size_t)(OH > 0 ? OH : 1) * B))) return rc;
+  if ((rc = ensure(ctx, ctx->grad, sizeof(double) * (size_t)(OH > 0 ? OH : 1) * nj * B))) return rc;
+  if ((rc = ensure(ctx, ctx->flags, sizeof(int) * B))) return rc;
+  if ((rc = ensure(ctx, ctx->listA, sizeof(int) * B))) return rc;
+  if ((rc = ensure(ctx, ctx->listB, sizeof(int) * B))) return rc;
+  if ((rc = ensure(ctx, ctx->counters, sizeof(int) * 8))) return rc;
+  if ((rc = ensure(ctx, ctx->qpsteps, sizeof(long long) * 2))) return rc;
+
+  SolveArgs a;
+  memset(&a, 0, sizeof(a));
+  a.tab = ctx->dtab;
+  a.B = B; a.H = H; a.nj = nj; a.n = n; a.nobs = O; a.nprim = np;
+  a.solver = solver;
+  a.max_outer = max_outer;
+  a.eps_outer = eps_outer;
+  a.alpha = alpha;
+  a.has_lim = ctx->has_lim;
+  a.has_bounds = ctx->has_bounds;
+  a.margin_is_D = 0;
+  a.G = ctx->dG;
+  a.gdiag = ctx->dgn;
+  a.QQ = ctx->dQQ;
+  a.lim = ctx->dlim;
+  a.max_input = ctx->dumax;
+  a.x0 = x0; a.ff = ff; a.caug = caug; a.xref = xref; a.noise = noise;
+  a.u0 = ptr<double>(ctx->u0); a.v0 = ptr<double>(ctx->v0); a.cost0 = ptr<double>(ctx->cost0);
+  a.fupper = ptr<double>(ctx->fupper);
+  a.qq_norm_inf = ctx->qq_norm_inf;
+  a.u = u; a.x = x;
+  a.dist = ptr<double>(ctx->dist); a.grad = ptr<double>(ctx->grad);
+  a.cost_hist = cost_hist; a.e_u_hist = e_u_hist; a.iters = iters; a.status = status;
+  a.flags = ptr<int>(ctx->flags);
+  int *cnt = ptr<int>(ctx->counters);  // [0]=count A, [1]=count B, [2]=work counter, [3]=max_active
+  a.qp_steps = ptr<long long>(ctx->qpsteps);
+  a.max_active = cnt + 3;
+  a.slab_ld = n;
+
+  int grid = qp_max_grid(a, ctx->device);
+  {
+    int sms = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+    if (grid > 8 * sms) grid = 8 * sms;
+  }
+  if (grid > B) grid = B;
+  if (grid < 1) grid = 1;
+  if ((rc = ensure(ctx, ctx->slab, sizeof(double) * (size_t)n * n * grid))) return rc;
+  a.slab = ptr<double>(ctx->slab);
+
+  const bool detail = ctx->timing_level >= 2;
+  const size_t need_ev = detail ? (size_t)3 * max_outer + 2 : 0;
+  while (ctx->ev.size() < need_ev) {
+    cudaEvent_t e;
+    CU(cudaEventCreate(&e));
+    ctx->ev.push_back(e);
+  }
+  int launches = 0;
+  CU(cudaEventRecord(ctx->ev_a, st));
+  CU(cudaMemsetAsync(cnt, 0, sizeof(int) * 8, st));
+  CU(cudaMemsetAsync(ctx->qpsteps.p, 0, sizeof(long long) * 2, st));
+  a.list_cur = ptr<int>(ctx->listA); a.count_cur = cnt + 0;
+  a.list_next = ptr<int>(ctx->listB); a.count_next = cnt + 1;
+  a.work_counter = cnt + 2;
+  CU(launch_solve_init(a, st)); ++launches;
+  // u0 = -QQ^{-1} FF : the control block of G is QQ^{-1}
+  CU(launch_dgemm(n, B, n, -1.0, ctx->dG + (size_t)2 * n * np + 2 * n, np, false, ff, n, a.u0, n, st)); ++launches;
+  CU(launch_v0(a, st)); ++launches;
+
+  GradArgs g;
+  memset(&g, 0, sizeof(g));
+  g.tab = ctx->dtab; g.dv = ctx->ddv;
+  g.x = x; g.ld_prob = 2 * n; g.ld_i = 2 * nj;
+  g.nslots = B; g.H = H; g.nj = nj; g.nobs = O;
+  g.o_prob = OH; g.o_obs = H; g.o_i = 1;
+  g.dist = a.dist; g.linkid = nullptr; g.grad = a.grad; g.flags = a.flags;
+
+  for (int it = 1; it <= max_outer; ++it) {
+    a.outer_iter = it;
+    g.list = a.list_cur;
+    g.count = a.count_cur;
+    if (detail) CU(cudaEventRecord(ctx->ev[3 * (it - 1)], st));
+    if (O > 0) {
+      CU(grad == CFS_GRAD_DERIVEST ? launch_grad_derivest(g, st) : launch_grad_numjac(g, st)); ++launches;
+    }
+    if (detail) CU(cudaEventRecord(ctx->ev[3 * (it - 1) + 1], st));
+    CU(launch_qp(a, grid, st)); ++launches;
+    if (detail) CU(cudaEventRecord(ctx->ev[3 * (it - 1) + 2], st));
+    // swap lists; reset the consumed counter and the work queue
+    std::swap(a.list_cur, a.list_next);
+    std::swap(a.count_cur, a.count_next);
+    CU(cudaMemsetAsync(a.count_next, 0, sizeof(int), st));
+    CU(cudaMemsetAsync(a.work_counter, 0, sizeof(int), st));
+  }
+  CU(launch_finalize(a, st)); ++launches;
+  CU(cudaEventRecord(ctx->ev_b, st));
+  ctx->stats.launches = launches;
+  return 0;
+}
+
+static int collect_stats(cfs_ctx *ctx, int B, int max_outer, const int *d_iters, const int *d_status) {
+  cudaStream_t st = ctx->stream;
+  long long steps[2] = {0, 0};
+  int cnt[8] = {0};
+  std::vector<int> it(B), stt(B);
+  CU(cudaMemcpyAsync(stt.data(), d_status, sizeof(int) * B, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(steps, ctx->qpsteps.p, sizeof(steps), cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(cnt, ctx->counters.p, sizeof(cnt), cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(it.data(), d_iters, sizeof(int) * B, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, ctx->ev_a, ctx->ev_b);
+  ctx->stats.ms_total = ms;
+  ctx->stats.qp_steps = steps[0];
+  ctx->stats.max_active = cnt[3];
+  long long pit = 0, gev = 0;
+  for (int b = 0; b < B; ++b) {
+    pit += it[b];
+    gev += it[b] + (((stt[b] & 0xFF) >= 2) ? 1 : 0);  // a failed QP still consumed one gradient pass
+  }
+  ctx->stats.problem_iters = pit;
+  ctx->stats.grad_waypoints = gev * ctx->H * ctx->nobs;
+  ctx->stats.ms_grad = ctx->stats.ms_qp = 0;
+  if (ctx->timing_level >= 2) {
+    for (int k = 0; k < max_outer; ++k) {
+      float a = 0, b = 0;
+      cudaEventElapsedTime(&a, ctx->ev[3 * k], ctx->ev[3 * k + 1]);
+      cudaEventElapsedTime(&b, ctx->ev[3 * k + 1], ctx->ev[3 * k + 2]);
+      ctx->stats.ms_grad += a;
+      ctx->stats.ms_qp += b;
+    }
+  }
+  return 0;
+}
+
+static int check_solve_args(cfs_ctx *ctx, int B, int solver, int grad, const void *x0, const void *ff, const void *caug,
+                            const void *xref, int max_outer, const void *u, const void *x, const void *cost_hist,
+                            const void *iters, const void *status) {
+  if (!ctx) return CFS_E_ARG;
+  int rc = check_ready(ctx, true);
+  if (rc) return rc;
+  if (B < 0 || max_outer < 0) return fail(ctx, CFS_E_ARG, "cfs_solve_batch: B=%d max_outer=%d", B, max_outer);
+  if (solver != CFS_SOLVER_CFS && solver != CFS_SOLVER_PSGCFS) return fail(ctx, CFS_E_ARG, "cfs_solve_batch: solver=%d", solver);
+  if (grad != CFS_GRAD_NUMJAC && grad != CFS_GRAD_DERIVEST) return fail(ctx, CFS_E_ARG, "cfs_solve_batch: grad=%d", grad);
+  if (B > 0 && (!x0 || !ff || !caug || !xref || !u || !x || !cost_hist || !iters || !status))
+    return fail(ctx, CFS_E_ARG, "cfs_solve_batch: NULL buffer");
+  return 0;
+}
+
+extern "C" int cfs_solve_batch_device(cfs_ctx *ctx, int B, int solver, int grad, const double *x0, const double *ff,
+                                      const double *caug, const double *xref, const double *noise, double eps_outer,
+                                      int max_outer, double alpha, double *u, double *x, double *cost_hist,
+                                      double *e_u_hist, int *iters, int *status, int sync) {
+  int rc = check_solve_args(ctx, B, solver, grad, x0, ff, caug, xref, max_outer, u, x, cost_hist, iters, status);
+  if (rc) return rc;
+  if (B == 0) return 0;
+  CU(cudaSetDevice(ctx->device));
+  rc = solve_device(ctx, B, solver, grad, x0, ff, caug, xref, noise, eps_outer, max_outer, alpha, u, x, cost_hist,
+                    e_u_hist, iters, status);
+  if (rc) return rc;
+  if (sync) return collect_stats(ctx, B, max_outer, iters, status);
+  return 0;
+}
+
+extern "C" int cfs_solve_batch(cfs_ctx *ctx, int B, int solver, int grad, const double *x0, const double *ff,
+                               const double *caug, const double *xref, const double *noise, double eps_outer,
+                               int max_outer, double alpha, double *u, double *x, double *cost_hist, double *e_u_hist,
+                               int *iters, int *status) {
+  int rc = check_solve_args(ctx, B, solver, grad, x0, ff, caug, xref, max_outer, u, x, cost_hist, iters, status);
+  if (rc) return rc;
+  if (B == 0) return 0;
+  CU(cudaSetDevice(ctx->device));
+  const int nj = ctx->nj, n = ctx->n, K = max_outer > 0 ? max_outer : 1;
+  cudaStream_t st = ctx->stream;
+  if ((rc = ensure(ctx, ctx->x0, sizeof(double) * 2 * nj * B))) return rc;
+  if ((rc = ensure(ctx, ctx->ff, sizeof(double) * (size_t)n * B))) return rc;
+  if ((rc = ensure(ctx, ctx->caug, sizeof(double) * B))) return rc;
+  if ((rc = ensure(ctx, ctx->xref, sizeof(double) * (size_t)2 * n * B))) return rc;
+  if ((rc = ensure(ctx, ctx->u, sizeof(double) * (size_t)n * B))) return rc;
+  if ((rc = ensure(ctx, ctx->x, sizeof(double) * (size_t)2 * n * B))) return rc;
+  if ((rc = ensure(ctx, ctx->cost, sizeof(double) * (size_t)K * B))) return rc;
+  if ((rc = ensure(ctx, ctx->eu, sizeof(double) * (size_t)K * B))) return rc;
+  if ((rc = ensure(ctx, ctx->iters, sizeof(int) * B))) return rc;
+  if ((rc = ensure(ctx, ctx->status, sizeof(int) * B))) return rc;
+  if (noise && (rc = ensure(ctx, ctx->noise, sizeof(double) * (size_t)n * K * B))) return rc;
+  cudaEvent_t h0, h1, h2, h3;
+  CU(cudaEventCreate(&h0)); CU(cudaEventCreate(&h1)); CU(cudaEventCreate(&h2)); CU(cudaEventCreate(&h3));
+  CU(cudaEventRecord(h0, st));
+  CU(cudaMemcpyAsync(ctx->x0.p, x0, sizeof(double) * 2 * nj * B, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(ctx->ff.p, ff, sizeof(double) * (size_t)n * B, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(ctx->caug.p, caug, sizeof(double) * B, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(ctx->xref.p, xref, sizeof(double) * (size_t)2 * n * B, cudaMemcpyHostToDevice, st));
+  if (noise) CU(cudaMemcpyAsync(ctx->noise.p, noise, sizeof(double) * (size_t)n * K * B, cudaMemcpyHostToDevice, st));
+  CU(cudaEventRecord(h1, st));
+  rc = solve_device(ctx, B, solver, grad, ptr<double>(ctx->x0), ptr<double>(ctx->ff), ptr<double>(ctx->caug),
+                    ptr<double>(ctx->xref), noise ? ptr<double>(ctx->noise) : nullptr, eps_outer, max_outer, alpha,
+                    ptr<double>(ctx->u), ptr<double>(ctx->x), ptr<double>(ctx->cost), ptr<double>(ctx->eu),
+                    ptr<int>(ctx->iters), ptr<int>(ctx->status));
+  if (rc) return rc;
+  CU(cudaEventRecord(h2, st));
+  CU(cudaMemcpyAsync(u, ctx->u.p, sizeof(double) * (size_t)n * B, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(x, ctx->x.p, sizeof(double) * (size_t)2 * n * B, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(cost_hist, ctx->cost.p, sizeof(double) * (size_t)max_outer * B, cudaMemcpyDeviceToHost, st));
+  if (e_u_hist) CU(cudaMemcpyAsync(e_u_hist, ctx->eu.p, sizeof(double) * (size_t)max_outer * B, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(iters, ctx->iters.p, sizeof(int) * B, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(status, ctx->status.p, sizeof(int) * B, cudaMemcpyDeviceToHost, st));
+  CU(cudaEventRecord(h3, st));
+  rc = collect_stats(ctx, B, max_outer, ptr<int>(ctx->iters), ptr<int>(ctx->status));
+  float a = 0, b = 0;
+  cudaEventElapsedTime(&a, h0, h1);
+  cudaEventElapsedTime(&b, h2, h3);
+  ctx->stats.ms_h2d = a;
+  ctx->stats.ms_d2h = b;
+  cudaEventDestroy(h0); cudaEventDestroy(h1); cudaEventDestroy(h2); cudaEventDestroy(h3);
+  return rc;
+}
+
+// ---- direct kernels -------------------------------------------------------------------------------------------------
+extern "C" int cfs_dist_grad(cfs_ctx *ctx, int N, int grad_mode, const double *theta, double *dist, int *linkid,
+                             double *grad, int *flags) {
+  if (!ctx) return CFS_E_ARG;
+  int rc = check_ready(ctx, false);
+  if (rc) return rc;
+  if (N < 0 || (N > 0 && (!theta || !dist || !grad))) return fail(ctx, CFS_E_ARG, "cfs_dist_grad: bad argument");
+  if (N == 0 || ctx->nobs == 0) return 0;
+  CU(cudaSetDevice(ctx->device));
+  const int nj = ctx->nj, O = ctx->nobs;
+  cudaStream_t st = ctx->stream;
+  if ((rc = ensure(ctx, ctx->scratch_theta, sizeof(double) * (size_t)nj * N))) return rc;
+  const size_t bytes_out = (sizeof(double) * (1 + nj) + sizeof(int)) * (size_t)O * N + sizeof(int) * (size_t)N + 64;
+  if ((rc = ensure(ctx, ctx->scratch_out, bytes_out))) return rc;
+  double *d_dist = ptr<double>(ctx->scratch_out);
+  double *d_grad = d_dist + (size_t)O * N;
+  int *d_lid = reinterpret_cast<int *>(d_grad + (size_t)O * N * nj);
+  int *d_flags = d_lid + (size_t)O * N;
+  CU(cudaMemcpyAsync(ctx->scratch_theta.p, theta, sizeof(double) * (size_t)nj * N, cudaMemcpyHostToDevice, st));
+  CU(cudaMemsetAsync(d_flags, 0, sizeof(int) * N, st));
+  GradArgs g;
+  memset(&g, 0, sizeof(g));
+  g.tab = ctx->dtab; g.dv = ctx->ddv;
+  g.x = ptr<double>(ctx->scratch_theta);
+  // one "problem" per configuration so that flags are per configuration: prob = i
+  g.ld_prob = nj; g.ld_i = 0; g.nslots = N; g.H = 1; g.nj = nj; g.nobs = O;
+  g.o_prob = O; g.o_obs = 1; g.o_i = 0;  // dist (n_obs x N): dist[j + O*prob]
+  g.dist = d_dist; g.linkid = d_lid; g.grad = d_grad; g.flags = d_flags;
+  CU(grad_mode == CFS_GRAD_DERIVEST ? launch_grad_derivest(g, st) : launch_grad_numjac(g, st));
+  CU(cudaMemcpyAsync(dist, d_dist, sizeof(double) * (size_t)O * N, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(grad, d_grad, sizeof(double) * (size_t)O * N * nj, cudaMemcpyDeviceToHost, st));
+  if (linkid) CU(cudaMemcpyAsync(linkid, d_lid, sizeof(int) * (size_t)O * N, cudaMemcpyDeviceToHost, st));
+  if (flags) CU(cudaMemcpyAsync(flags, d_flags, sizeof(int) * (size_t)N, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  return 0;
+}
+
+extern "C" int cfs_get_con(cfs_ctx *ctx, int grad_mode, int margin_is_D, const double *x0, const double *xcur,
+                           const double *u, double *Ainq, double *binq) {
+  if (!ctx) return CFS_E_ARG;
+  int rc = check_ready(ctx, true);
+  if (rc) return rc;
+  if (!x0 || !xcur || !u || !Ainq || !binq) return fail(ctx, CFS_E_ARG, "cfs_get_con: NULL argument");
+  CU(cudaSetDevice(ctx->device));
+  const int nj = ctx->nj, H = ctx->H, n = ctx->n, O = ctx->nobs, OH = O * H;
+  const int m = OH * (ctx->has_lim ? 1 + 2 * nj : 1);
+  if (m == 0) return 0;
+  cudaStream_t st = ctx->stream;
+  const size_t in_d = (size_t)2 * nj + 2 * n + n;
+  if ((rc = ensure(ctx, ctx->scratch_theta, sizeof(double) * in_d))) return rc;
+  const size_t out_d = (size_t)OH + (size_t)OH * nj + (size_t)m * n + m;
+  if ((rc = ensure(ctx, ctx->scratch_out, sizeof(double) * out_d + sizeof(int) * 4))) return rc;
+  double *d_x0 = ptr<double>(ctx->scratch_theta), *d_x = d_x0 + 2 * nj, *d_u = d_x + 2 * n;
+  double *d_dist = ptr<double>(ctx->scratch_out), *d_grad = d_dist + OH, *d_A = d_grad + (size_t)OH * nj,
+         *d_b = d_A + (size_t)m * n;
+  int *d_flags = reinterpret_cast<int *>(d_b + m);
+  CU(cudaMemcpyAsync(d_x0, x0, sizeof(double) * 2 * nj, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(d_x, xcur, sizeof(double) * 2 * n, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(d_u, u, sizeof(double) * n, cudaMemcpyHostToDevice, st));
+  CU(cudaMemsetAsync(d_flags, 0, sizeof(int) * 4, st));
+  GradArgs g;
+  memset(&g, 0, sizeof(g));
+  g.tab = ctx->dtab; g.dv = ctx->ddv;
+  g.x = d_x; g.ld_prob = 2 * n; g.ld_i = 2 * nj; g.nslots = 1; g.H = H; g.nj = nj; g.nobs = O;
+  g.o_prob = OH; g.o_obs = H; g.o_i = 1;
+  g.dist = d_dist; g.linkid = nullptr; g.grad = d_grad; g.flags = d_flags;
+  CU(grad_mode == CFS_GRAD_DERIVEST ? launch_grad_derivest(g, st) : launch_grad_numjac(g, st));
+  CU(launch_get_con_rows(ctx->dtab, H, nj, O, ctx->has_lim, margin_is_D, d_x0, d_u, ctx->dlim, d_dist, d_grad, d_A, d_b,
+                         m, st));
+  CU(cudaMemcpyAsync(Ainq, d_A, sizeof(double) * (size_t)m * n, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(binq, d_b, sizeof(double) * m, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  return 0;
+}
+
+extern "C" int cfs_nodes_feasible(cfs_ctx *ctx, int N, const double *theta, unsigned char *feasible, double *dmin) {
+  if (!ctx) return CFS_E_ARG;
+  int rc = check_ready(ctx, false);
+  if (rc) return rc;
+  if (N < 0 || (N > 0 && (!theta || !feasible))) return fail(ctx, CFS_E_ARG, "cfs_nodes_feasible: bad argument");
+  if (N == 0) return 0;
+  CU(cudaSetDevice(ctx->device));
+  const int nj = ctx->nj;
+  cudaStream_t st = ctx->stream;
+  if ((rc = ensure(ctx, ctx->scratch_theta, sizeof(double) * (size_t)nj * N))) return rc;
+  if ((rc = ensure(ctx, ctx->scratch_out, (sizeof(double) + 1) * (size_t)N + 64))) return rc;
+  double *d_dmin = ptr<double>(ctx->scratch_out);
+  unsigned char *d_feas = reinterpret_cast<unsigned char *>(d_dmin + N);
+  CU(cudaMemcpyAsync(ctx->scratch_theta.p, theta, sizeof(double) * (size_t)nj * N, cudaMemcpyHostToDevice, st));
+  CU(launch_nodes_feasible(ctx->dtab, nj, ctx->nobs, N, ptr<double>(ctx->scratch_theta), d_feas, d_dmin, st));
+  CU(cudaMemcpyAsync(feasible, d_feas, (size_t)N, cudaMemcpyDeviceToHost, st));
+  if (dmin) CU(cudaMemcpyAsync(dmin, d_dmin, sizeof(double) * (size_t)N, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  return 0;
+}
+
+extern "C" int cfs_nearest_steer(cfs_ctx *ctx, int n_nodes, const double *nodes, int S, const double *samples,
+                                 const double *ratial, double step, int *parent, double *newnode) {
+  if (!ctx) return CFS_E_ARG;
+  if (!ctx->have_robot) return fail(ctx, CFS_E_STATE, "robot not set (cfs_set_robot)");
+  if (n_nodes < 1 || S < 0 || !nodes || (S > 0 && (!samples || !ratial || !parent || !newnode)))
+    return fail(ctx, CFS_E_ARG, "cfs_nearest_steer: bad argument");
+  if (S == 0) return 0;
+  CU(cudaSetDevice(ctx->device));
+  const int nj = ctx->nj;
+  cudaStream_t st = ctx->stream;
+  int rc;
+  const size_t in_d = (size_t)nj * n_nodes + (size_t)nj * S + CFS_MAXL;
+  if ((rc = ensure(ctx, ctx->scratch_theta, sizeof(double) * in_d))) return rc;
+  if ((rc = ensure(ctx, ctx->scratch_out, sizeof(double) * (size_t)nj * S + sizeof(int) * (size_t)S + 64))) return rc;
+  double *d_nodes = ptr<double>(ctx->scratch_theta), *d_s = d_nodes + (size_t)nj * n_nodes, *d_r = d_s + (size_t)nj * S;
+  double *d_new = ptr<double>(ctx->scratch_out);
+  int *d_par = reinterpret_cast<int *>(d_new + (size_t)nj * S);
+  CU(cudaMemcpyAsync(d_nodes, nodes, sizeof(double) * (size_t)nj * n_nodes, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(d_s, samples, sizeof(double) * (size_t)nj * S, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(d_r, ratial, sizeof(double) * nj, cudaMemcpyHostToDevice, st));
+  CU(launch_nearest_steer(nj, n_nodes, d_nodes, S, d_s, d_r, step, d_par, d_new, st));
+  CU(cudaMemcpyAsync(parent, d_par, sizeof(int) * (size_t)S, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(newnode, d_new, sizeof(double) * (size_t)nj * S, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  return 0;
+}
+
+extern "C" int cfs_get_stats(const cfs_ctx *ctx, cfs_stats *out) {
+  if (!ctx || !out) return CFS_E_ARG;
+  *out = ctx->stats;
+  return 0;
+}
+
+extern "C" int cfs_set_timing(cfs_ctx *ctx, int level) {
+  if (!ctx) return CFS_E_ARG;
+  ctx->timing_level = level;
+  return 0;
+}
+
+extern "C" int cfs_measure_fp64_peak(cfs_ctx *ctx, double *tflops, double *sm_clock_mhz_est) {
+  if (!ctx || !tflops) return CFS_E_ARG;
+  CU(cudaSetDevice(ctx->device));
+  int sms = 0;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+  int rc;
+  if ((rc = ensure(ctx, ctx->scratch_out, 64))) return rc;
+  const int iters = 1 << 16, block = 256, grid = sms * 8;
+  cudaStream_t st = ctx->stream;
+  CU(launch_fp64_peak(ptr<double>(ctx->scratch_out), 1 << 12, grid, block, st));  // warm-up
+  double best = 0;
+  for (int rep = 0; rep < 5; ++rep) {
+    CU(cudaEventRecord(ctx->ev_a, st));
+    CU(launch_fp64_peak(ptr<double>(ctx->scratch_out), iters, grid, block, st));
+    CU(cudaEventRecord(ctx->ev_b, st));
+    CU(cudaStreamSynchronize(st));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ctx->ev_a, ctx->ev_b);
+    const double fl = 2.0 * 8.0 * (double)iters * block * (double)grid;
+    const double tf = fl / (ms * 1e-3) / 1e12;
+    if (tf > best) best = tf;
+  }
+  *tflops = best;
+  if (sm_clock_mhz_est) *sm_clock_mhz_est = best * 1e12 / (2.0 * 64.0 * sms) / 1e6;  // 64 FP64 FMA lanes per SM
+  return 0;
+}

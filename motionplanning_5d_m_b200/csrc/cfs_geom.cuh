@@ -1,0 +1,161 @@
+// cfs_geom.cuh -- device-side forward kinematics and capsule-axis distances, FP64, all in registers.
+//
+// Replaces (reference file:line):
+//   Lib/functions/CapPos.m:8-23          chain  M{i+1}=M{i}*[R T;0 0 0 1], endpoints pos{i}.p
+//   Lib/2L/CapPos2.m:16-29               planar chain with constant translations robot.T(:,i)
+//   Lib/functions/distLinSeg.m:23-101    Lumelsky segment-segment distance
+//   Lib/M16iB/dist_arm_3D_Heu_2.m:20-29, Lib/200i/dist_arm_3D_200i_2.m:21-29, Lib/2L/dist_arm_2L.m:13-22
+//                                        min over links + "negative when the axes touch" rule
+#pragma once
+#include "cfs_types.cuh"
+
+namespace cfs {
+
+// ---- TMA bulk staging of the robot/obstacle tables -----------------------------------------------------
+// One elected thread arms an mbarrier with the byte count and issues cp.async.bulk (SASS: UBLKCP);
+// every thread then waits on the barrier phase.  The tables are < 4 KB, so this is about latency, not
+// bandwidth: one bulk transaction instead of ~100 scattered LDGs per thread.
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ void tma_stage(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *mbar) {
+  const uint32_t bar = smem_u32(mbar);
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(gmem_src), "r"(bytes), "r"(bar)
+        : "memory");
+  }
+  // phase 0 wait
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(0u)
+        : "memory");
+  }
+}
+
+__device__ __forceinline__ uint32_t tab_bytes(int nobs) {
+  return static_cast<uint32_t>(CFS_TAB_HEADER_BYTES + sizeof(ObsTab) * nobs);
+}
+
+// ---- one chain step: Mn = M * [R T; 0 0 0 1]   (CapPos.m:13-17) ------------------------------------------
+// M is 3x4 row-major in registers (bottom row is [0 0 0 1] throughout).  R(3,1) == 0 structurally.
+struct Xf {
+  double m[12];
+};
+
+__device__ __forceinline__ void link_RT(const LinkTab &L, double c, double s, double R[9], double T[3]) {
+  R[0] = c;   R[1] = -s * L.ca;  R[2] = s * L.sa;
+  R[3] = s;   R[4] = c * L.ca;   R[5] = -c * L.sa;
+  R[6] = 0.0; R[7] = L.sa;       R[8] = L.ca;
+  T[0] = L.a * c + L.tx;
+  T[1] = L.a * s + L.ty;
+  T[2] = L.dz;
+}
+
+__device__ __forceinline__ void xf_first(const LinkTab &L, double c, double s, Xf &M) {
+  double R[9], T[3];
+  link_RT(L, c, s, R, T);  // eye(4) * X == X exactly
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    M.m[4 * a + 0] = R[3 * a + 0];
+    M.m[4 * a + 1] = R[3 * a + 1];
+    M.m[4 * a + 2] = R[3 * a + 2];
+    M.m[4 * a + 3] = T[a];
+  }
+}
+
+__device__ __forceinline__ void xf_step(const Xf &M, const LinkTab &L, double c, double s, Xf &Mn) {
+  double R[9], T[3];
+  link_RT(L, c, s, R, T);
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    const double m0 = M.m[4 * a], m1 = M.m[4 * a + 1], m2 = M.m[4 * a + 2], m3 = M.m[4 * a + 3];
+    Mn.m[4 * a + 0] = m0 * R[0] + m1 * R[3];  // + m2*0
+    Mn.m[4 * a + 1] = (m0 * R[1] + m1 * R[4]) + m2 * R[7];
+    Mn.m[4 * a + 2] = (m0 * R[2] + m1 * R[5]) + m2 * R[8];
+    Mn.m[4 * a + 3] = ((m0 * T[0] + m1 * T[1]) + m2 * T[2]) + m3;
+  }
+}
+
+// pos{i}.p(:,k) = M(1:3,1:3)*cap.p(:,k) + M(1:3,4) + base   (CapPos.m:18-20); p[0..2]=start, p[3..5]=end
+__device__ __forceinline__ void link_endpoints(const Xf &M, const LinkTab &L, const double base[3], double p[6]) {
+#pragma unroll
+  for (int k = 0; k < 2; ++k)
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+      p[3 * k + a] = (((M.m[4 * a] * L.cap[k][0] + M.m[4 * a + 1] * L.cap[k][1]) + M.m[4 * a + 2] * L.cap[k][2]) +
+                      M.m[4 * a + 3]) + base[a];
+}
+
+__device__ __forceinline__ double fixbound(double v) {  // distLinSeg.m:93-101
+  return v < 0.0 ? 0.0 : (v > 1.0 ? 1.0 : v);
+}
+
+// distLinSeg(link start, link end, obs start, obs end) followed by the touch rule of dist_arm_*:
+//   if |dis| < 1e-4: dis = -norm(P1 - link_end)       (dist_arm_3D_200i_2.m:22-24, dist_link_Heu.m:19-21)
+// The branch-deciding quantity den = D1*D2 - R^2 is formed with explicit round-to-nearest mul/sub (no FMA
+// contraction) so that the parallel-lines test (distLinSeg.m:55) sees the same value as MATLAB's arithmetic.
+__device__ __forceinline__ double link_obs_dist(const double p[6], const ObsTab &o, int &touched) {
+  const double d1x = p[3] - p[0], d1y = p[4] - p[1], d1z = p[5] - p[2];
+  const double d12x = o.s[0] - p[0], d12y = o.s[1] - p[1], d12z = o.s[2] - p[2];
+  const double d2x = o.d2[0], d2y = o.d2[1], d2z = o.d2[2];
+  const double D1 = (d1x * d1x + d1y * d1y) + d1z * d1z;
+  const double D2 = o.D2;
+  const double S1 = (d1x * d12x + d1y * d12y) + d1z * d12z;
+  const double S2 = (d2x * d12x + d2y * d12y) + d2z * d12z;
+  const double R = (d1x * d2x + d1y * d2y) + d1z * d2z;
+  const double den = __dsub_rn(__dmul_rn(D1, D2), __dmul_rn(R, R));
+  double t, u;
+  if (D1 == 0.0 || D2 == 0.0) {
+    if (D1 != 0.0) {
+      u = 0.0;
+      t = fixbound(S1 / D1);
+    } else if (D2 != 0.0) {
+      t = 0.0;
+      u = fixbound(-S2 / D2);
+    } else {
+      t = 0.0;
+      u = 0.0;
+    }
+  } else if (den == 0.0) {
+    t = 0.0;
+    u = -S2 / D2;
+    const double uf = fixbound(u);
+    if (uf != u) {
+      t = fixbound((uf * R + S1) / D1);
+      u = uf;
+    }
+  } else {
+    t = fixbound((S1 * D2 - S2 * R) / den);
+    u = (t * R - S2) / D2;
+    const double uf = fixbound(u);
+    if (uf != u) {
+      t = fixbound((uf * R + S1) / D1);
+      u = uf;
+    }
+  }
+  const double vx = (d1x * t - d2x * u) - d12x, vy = (d1y * t - d2y * u) - d12y, vz = (d1z * t - d2z * u) - d12z;
+  double dis = sqrt((vx * vx + vy * vy) + vz * vz);
+  if (fabs(dis) < CFS_TOUCH_TOL) {
+    const double wx = (p[0] + d1x * t) - p[3], wy = (p[1] + d1y * t) - p[4], wz = (p[2] + d1z * t) - p[5];
+    dis = -sqrt((wx * wx + wy * wy) + wz * wz);
+    touched = 1;
+  }
+  return dis;
+}
+
+}  // namespace cfs

@@ -1,0 +1,97 @@
+// cfs_kernels.cuh -- launch wrappers shared between the translation units of libcfs_b200.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "cfs_types.cuh"
+
+namespace cfs {
+
+// ---- K1 / K1d : distance + gradient ---------------------------------------------------------------------
+// Work item = (slot, i): configuration theta = x[prob*ld_prob + i*ld_i + k], k < nj, prob = list ? list[slot] : slot.
+// Outputs for obstacle j:   dist[prob*o_prob + j*o_obs + i*o_i], linkid (same index), grad[(same index)*nj + k].
+struct GradArgs {
+  const DevTables *tab;
+  const DerivestTab *dv;     // K1d only
+  const double *x;
+  long long ld_prob, ld_i;
+  const int *list;           // active problem list or nullptr
+  const int *count;          // device-side number of active slots or nullptr (=> nslots)
+  int nslots;                // upper bound on slots
+  int H;                     // configurations per problem
+  int nj, nobs;
+  long long o_prob, o_obs, o_i;
+  double *dist;
+  int *linkid;
+  double *grad;
+  int *flags;                // per problem: OR of CFS_FLAG_TOUCH (atomicOr)
+};
+cudaError_t launch_grad_numjac(const GradArgs &a, cudaStream_t s);
+cudaError_t launch_grad_derivest(const GradArgs &a, cudaStream_t s);
+
+// ---- K6 : RRT node feasibility and nearest/steer ----------------------------------------------------------
+cudaError_t launch_nodes_feasible(const DevTables *tab, int nj, int nobs, int N, const double *theta,
+                                  unsigned char *feasible, double *dmin, cudaStream_t s);
+cudaError_t launch_nearest_steer(int nj, int n_nodes, const double *nodes, int S, const double *samples,
+                                 const double *ratial, double step, int *parent, double *newnode, cudaStream_t s);
+
+// ---- set-up: shared Gram operator G = P QQ^{-1} P' ----------------------------------------------------------
+// P = [B_theta; B_omega; I] (3n x n): the primitives every constraint row of CFS_FANUC.get_con is built from.
+// hessian_is_identity: PSGCFS projection (PSGCFS_FANUC.m:117) -> G = P P'.
+cudaError_t setup_gram(int n, int H, int nj, double dt, const double *QQ /*device n x n or nullptr*/, double *work_L /*n*n*/,
+                       double *work_Y /*n*3n*/, double *G /*3n x 3n*/, double *gdiag /*3n*/, int *info /*device*/,
+                       cudaStream_t s);
+
+// C = alpha * op(A) * B  (column-major, A is M x K with lda (or K x M if transA), B is K x N, C is M x N)
+cudaError_t launch_dgemm(int M, int N, int K, double alpha, const double *A, int lda, bool transA, const double *B,
+                         int ldb, double *C, int ldc, cudaStream_t s);
+
+// ---- per-batch init + the QP / rollout kernel ----------------------------------------------------------------
+struct SolveArgs {
+  const DevTables *tab;
+  int B, H, nj, n, nobs, nprim;  // nprim = 3n
+  int solver;                    // 0 CFS, 1 PSGCFS
+  int max_outer;
+  double eps_outer, alpha;
+  int has_lim, has_bounds, margin_is_D;
+  const double *G, *gdiag;       // Gram operator used by the QP (QQ metric for CFS, identity metric for PSGCFS)
+  const double *QQ;              // n x n (PSGCFS gradient / cost)
+  const double *lim, *max_input;
+  // per problem inputs
+  const double *x0, *ff, *caug, *xref, *noise;
+  // per problem state
+  double *u0;     // n x B   unconstrained minimiser (CFS) / PSG point (PSGCFS)
+  double *v0;     // 3n x B  P*u0
+  double *cost0;  // B       cost at u0 (CFS)
+  double *fupper; // B       upper bound of the cost over the box |u| <= MAX_input (infeasibility certificate)
+  double qq_norm_inf;
+  double *u, *x;  // current iterate
+  double *dist, *grad;  // K1 outputs: [prob][obs][i], [prob][obs][i][nj]
+  double *cost_hist, *e_u_hist;
+  int *iters, *status, *flags;
+  // scheduling
+  int *list_cur, *list_next;  // active problem lists
+  int *count_cur, *count_next;
+  int *work_counter;          // persistent-CTA work queue
+  double *slab;               // per-CTA workspace for the working-set inverse, slab_ld*slab_ld doubles each
+  int slab_ld;
+  int outer_iter;             // 1-based iteration being executed
+  long long *qp_steps;        // device counter
+  int *max_active;            // device max
+};
+cudaError_t launch_solve_init(const SolveArgs &a, cudaStream_t s);
+cudaError_t launch_v0(const SolveArgs &a, cudaStream_t s);
+cudaError_t launch_psg_point(const SolveArgs &a, cudaStream_t s);
+cudaError_t launch_qp(const SolveArgs &a, int grid, cudaStream_t s);
+size_t qp_smem_bytes(const SolveArgs &a);
+int qp_max_grid(const SolveArgs &a, int device);
+cudaError_t launch_finalize(const SolveArgs &a, cudaStream_t s);
+
+// ---- dense get_con rows (one problem) -------------------------------------------------------------------------
+cudaError_t launch_get_con_rows(const DevTables *tab, int H, int nj, int nobs, int has_lim, int margin_is_D,
+                                const double *x0, const double *u, const double *lim, const double *dist,
+                                const double *grad, double *Ainq, double *binq, int m, cudaStream_t s);
+
+// ---- FP64 peak micro-benchmark ----------------------------------------------------------------------------------
+cudaError_t launch_fp64_peak(double *sink, int iters, int grid, int block, cudaStream_t s);
+
+}  // namespace cfs

@@ -1,0 +1,459 @@
+// k_grad.cu -- K1 (num_jac), K1d (DERIVEST) distance/gradient kernels and K6 (RRT node checks), sm_100a.
+//
+// K1  replaces CFS_FANUC.get_con's inner loop body, Lib/CFS_FANUC.m:113-118:
+//        [distance,linkid] = dist_arm_all(theta,...);  Diff = num_jac(f,theta)
+//     One thread per (problem, waypoint).  The 11 evaluations of num_jac (Lib/functions/num_jac.m:2,10-16)
+//     are restructured, without changing any evaluated value, around two facts:
+//       * num_jac never resets xp(i) after column i (num_jac.m:13-14), so column k is evaluated with joints
+//         1..k-1 at theta-eps/2.  The kinematic prefix M_1^- ... M_{k-1}^- is therefore a running product
+//         shared by every later column, and the distances of links < k are the ones the "minus" evaluation
+//         of their own column already produced.
+//       * only links >= k move when joint k is perturbed.
+//     => 15 sincos + 35 link transforms/distances per waypoint instead of 55 + 55, all in registers;
+//     the per-thread sin/cos cache lives in shared memory (conflict-free [value][thread] layout).
+// K1d replaces the script path M16iB/main_CFS.m:231-237: derivest(@(x) dist_link_Heu(...,linkid), theta(s)).
+// K6  replaces RRT_FANUC.feasible (Lib/RRT_FANUC.m:146-181) and the nearest/steer scan (:116-129).
+#include "cfs_geom.cuh"
+#include "cfs_kernels.cuh"
+
+namespace cfs {
+
+#define GRAD_THREADS 128
+
+__device__ __forceinline__ double min_first(double cur, double cand) { return cand < cur ? cand : cur; }
+
+// ============================================================================================================
+// K1: num_jac
+// ============================================================================================================
+template <int NJ, int OC>
+__global__ void __launch_bounds__(GRAD_THREADS) k_grad_numjac(GradArgs a) {
+  __shared__ alignas(128) DevTables tab;
+  __shared__ alignas(8) uint64_t mbar;
+  // sin/cos cache: [6 kinds][NJ][thread]; kinds: c0,s0 (theta), cp,sp (theta+eps/2), cm,sm (theta-eps/2)
+  __shared__ double sc[6][NJ][GRAD_THREADS];
+
+  const int count = a.count ? *a.count : a.nslots;
+  const long long total = (long long)count * a.H;
+  if ((long long)blockIdx.x * blockDim.x >= total) return;  // whole CTA idle
+  tma_stage(&tab, a.tab, tab_bytes(a.nobs), &mbar);
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const int tid = threadIdx.x;
+  const int slot = (int)(t / a.H), i = (int)(t % a.H);
+  const int prob = a.list ? a.list[slot] : slot;
+  const double *thp = a.x + prob * a.ld_prob + i * a.ld_i;
+
+  const double hh = CFS_NUMJAC_EPS / 2;  // num_jac.m:11,13
+#pragma unroll
+  for (int k = 0; k < NJ; ++k) {
+    const double th = thp[k];
+    const double off = tab.link[k].th_off;
+    double s, c;
+    sincos(th + off, &s, &c);
+    sc[0][k][tid] = c;
+    sc[1][k][tid] = s;
+    sincos((th + hh) + off, &s, &c);
+    sc[2][k][tid] = c;
+    sc[3][k][tid] = s;
+    sincos((th - hh) + off, &s, &c);
+    sc[4][k][tid] = c;
+    sc[5][k][tid] = s;
+  }
+  int touched = 0;
+  const int nobs = a.nobs;
+
+  for (int j0 = 0; j0 < nobs; j0 += OC) {
+    double dbase[OC], dpre[OC];
+    int lid[OC];
+#pragma unroll
+    for (int jj = 0; jj < OC; ++jj) {
+      dbase[jj] = INFINITY;
+      dpre[jj] = INFINITY;
+      lid[jj] = 0;
+    }
+    Xf M, Mn, Pm;
+    double p[6];
+    // ---- y = f(x): base evaluation, gives distance and linkid (CFS_FANUC.m:115) ----
+#pragma unroll 1
+    for (int l = 0; l < NJ; ++l) {
+      if (l == 0) {
+        xf_first(tab.link[0], sc[0][0][tid], sc[1][0][tid], M);
+      } else {
+        xf_step(M, tab.link[l], sc[0][l][tid], sc[1][l][tid], Mn);
+        M = Mn;
+      }
+      link_endpoints(M, tab.link[l], tab.base, p);
+#pragma unroll
+      for (int jj = 0; jj < OC; ++jj)
+        if (j0 + jj < nobs) {
+          const double d = link_obs_dist(p, tab.obs[j0 + jj], touched);
+          if (d < dbase[jj]) {  // strict <: first minimal link (dist_arm_3D_Heu_2.m:25-28)
+            dbase[jj] = d;
+            lid[jj] = l + 1;
+          }
+        }
+    }
+    // ---- columns of num_jac ----
+#pragma unroll 1
+    for (int k = 0; k < NJ; ++k) {
+      double dpl[OC], dmi[OC], dk[OC];
+      // yhi = f(xp), xp(k) = x(k)+eps/2, joints < k at x-eps/2
+      if (k == 0)
+        xf_first(tab.link[0], sc[2][0][tid], sc[3][0][tid], M);
+      else
+        xf_step(Pm, tab.link[k], sc[2][k][tid], sc[3][k][tid], M);
+      link_endpoints(M, tab.link[k], tab.base, p);
+#pragma unroll
+      for (int jj = 0; jj < OC; ++jj)
+        dpl[jj] = (j0 + jj < nobs) ? min_first(dpre[jj], link_obs_dist(p, tab.obs[j0 + jj], touched)) : 0.0;
+#pragma unroll 1
+      for (int l = k + 1; l < NJ; ++l) {
+        xf_step(M, tab.link[l], sc[0][l][tid], sc[1][l][tid], Mn);
+        M = Mn;
+        link_endpoints(M, tab.link[l], tab.base, p);
+#pragma unroll
+        for (int jj = 0; jj < OC; ++jj)
+          if (j0 + jj < nobs) dpl[jj] = min_first(dpl[jj], link_obs_dist(p, tab.obs[j0 + jj], touched));
+      }
+      // ylo = f(xp), xp(k) = x(k)-eps/2
+      if (k == 0)
+        xf_first(tab.link[0], sc[4][0][tid], sc[5][0][tid], M);
+      else
+        xf_step(Pm, tab.link[k], sc[4][k][tid], sc[5][k][tid], M);
+      Pm = M;  // running prefix M_1^- ... M_k^-
+      link_endpoints(M, tab.link[k], tab.base, p);
+#pragma unroll
+      for (int jj = 0; jj < OC; ++jj) {
+        dk[jj] = (j0 + jj < nobs) ? link_obs_dist(p, tab.obs[j0 + jj], touched) : 0.0;
+        dmi[jj] = min_first(dpre[jj], dk[jj]);
+      }
+#pragma unroll 1
+      for (int l = k + 1; l < NJ; ++l) {
+        xf_step(M, tab.link[l], sc[0][l][tid], sc[1][l][tid], Mn);
+        M = Mn;
+        link_endpoints(M, tab.link[l], tab.base, p);
+#pragma unroll
+        for (int jj = 0; jj < OC; ++jj)
+          if (j0 + jj < nobs) dmi[jj] = min_first(dmi[jj], link_obs_dist(p, tab.obs[j0 + jj], touched));
+      }
+#pragma unroll
+      for (int jj = 0; jj < OC; ++jj)
+        if (j0 + jj < nobs) {
+          const long long o = prob * a.o_prob + (long long)(j0 + jj) * a.o_obs + i * a.o_i;
+          a.grad[o * NJ + k] = (dpl[jj] - dmi[jj]) / CFS_NUMJAC_EPS;  // num_jac.m:15
+          dpre[jj] = min_first(dpre[jj], dk[jj]);
+        }
+    }
+#pragma unroll
+    for (int jj = 0; jj < OC; ++jj)
+      if (j0 + jj < nobs) {
+        const long long o = prob * a.o_prob + (long long)(j0 + jj) * a.o_obs + i * a.o_i;
+        a.dist[o] = dbase[jj];
+        if (a.linkid) a.linkid[o] = lid[jj];
+      }
+  }
+  if (touched && a.flags) atomicOr(&a.flags[prob], 0x100);
+}
+
+template <int NJ>
+static cudaError_t launch_numjac_nj(const GradArgs &a, cudaStream_t s) {
+  const long long total = (long long)a.nslots * a.H;
+  if (total <= 0) return cudaSuccess;
+  const int grid = (int)((total + GRAD_THREADS - 1) / GRAD_THREADS);
+  if (a.nobs <= 1)
+    k_grad_numjac<NJ, 1><<<grid, GRAD_THREADS, 0, s>>>(a);
+  else
+    k_grad_numjac<NJ, 2><<<grid, GRAD_THREADS, 0, s>>>(a);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_grad_numjac(const GradArgs &a, cudaStream_t s) {
+  switch (a.nj) {
+    case 2: return launch_numjac_nj<2>(a, s);
+    case 3: return launch_numjac_nj<3>(a, s);
+    case 4: return launch_numjac_nj<4>(a, s);
+    case 5: return launch_numjac_nj<5>(a, s);
+    case 6: return launch_numjac_nj<6>(a, s);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+// ============================================================================================================
+// K1d: DERIVEST gradients of dist_link(linkid)
+//   one thread per (problem, waypoint, obstacle, joint s)
+// ============================================================================================================
+template <int NJ>
+__global__ void __launch_bounds__(GRAD_THREADS) k_grad_derivest(GradArgs a) {
+  __shared__ alignas(128) DevTables tab;
+  __shared__ alignas(128) DerivestTab dv;
+  __shared__ alignas(8) uint64_t mbar;
+  __shared__ double fdel_s[DV_NDEL][GRAD_THREADS];
+
+  const int count = a.count ? *a.count : a.nslots;
+  const long long total = (long long)count * a.H * a.nobs * NJ;
+  if ((long long)blockIdx.x * blockDim.x >= total) return;
+  tma_stage(&tab, a.tab, tab_bytes(a.nobs), &mbar);
+  for (int w = threadIdx.x; w < (int)(sizeof(DerivestTab) / sizeof(double)); w += blockDim.x)
+    reinterpret_cast<double *>(&dv)[w] = reinterpret_cast<const double *>(a.dv)[w];
+  __syncthreads();
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const int tid = threadIdx.x;
+  const int s = (int)(t % NJ);
+  long long rest = t / NJ;
+  const int j = (int)(rest % a.nobs);
+  rest /= a.nobs;
+  const int i = (int)(rest % a.H);
+  const int slot = (int)(rest / a.H);
+  const int prob = a.list ? a.list[slot] : slot;
+  const double *thp = a.x + prob * a.ld_prob + i * a.ld_i;
+  const ObsTab &ob = tab.obs[j];
+
+  double th[NJ], c0[NJ], s0[NJ];
+#pragma unroll
+  for (int k = 0; k < NJ; ++k) {
+    th[k] = thp[k];
+    sincos(th[k] + tab.link[k].th_off, &s0[k], &c0[k]);
+  }
+  int touched = 0;
+  // base evaluation: distance, linkid (M16iB/main_CFS.m:229) and the kinematic prefix of joint s
+  Xf M, Mn, Ps;
+  double p[6];
+  double dbase = INFINITY;
+  int lid = 0;
+#pragma unroll
+  for (int l = 0; l < NJ; ++l) {
+    if (l == s) Ps = M;  // product of links < s (unused when s == 0)
+    if (l == 0) {
+      xf_first(tab.link[0], c0[0], s0[0], M);
+    } else {
+      xf_step(M, tab.link[l], c0[l], s0[l], Mn);
+      M = Mn;
+    }
+    link_endpoints(M, tab.link[l], tab.base, p);
+    const double d = link_obs_dist(p, ob, touched);
+    if (d < dbase) {
+      dbase = d;
+      lid = l + 1;
+    }
+  }
+  const long long o = prob * a.o_prob + (long long)j * a.o_obs + i * a.o_i;
+  if (s == 0) {
+    a.dist[o] = dbase;
+    if (a.linkid) a.linkid[o] = lid;
+  }
+  double der = 0.0;
+  if (s < lid) {  // dist_link(linkid) does not depend on joints > linkid: every f_del is exactly 0 there
+    double ths = 0.0, offs = 0.0;
+#pragma unroll
+    for (int k = 0; k < NJ; ++k)
+      if (k == s) {
+        ths = th[k];
+        offs = tab.link[k].th_off;
+      }
+    const double h = ths > 0.02 ? ths : 0.02;  // par.NominalStep = max(x0,0.02)  derivest.m:229
+#pragma unroll 1
+    for (int kk = 0; kk < DV_NDEL; ++kk) {
+      double f[2];
+#pragma unroll 1
+      for (int sg = 0; sg < 2; ++sg) {
+        const double xs = sg == 0 ? ths + h * dv.delta[kk] : ths - h * dv.delta[kk];  // derivest.m:369-370
+        double sn, cs;
+        sincos(xs + offs, &sn, &cs);
+        if (s == 0)
+          xf_first(tab.link[0], cs, sn, M);
+        else
+          xf_step(Ps, tab.link[s], cs, sn, M);
+#pragma unroll
+        for (int l = 1; l < NJ; ++l)
+          if (l > s && l < lid) {
+            xf_step(M, tab.link[l], c0[l], s0[l], Mn);
+            M = Mn;
+          }
+        link_endpoints(M, tab.link[lid - 1], tab.base, p);
+        f[sg] = link_obs_dist(p, ob, touched);
+      }
+      fdel_s[kk][tid] = (f[0] - f[1]) / 2;  // odd transformation, derivest.m:376
+    }
+    // der_init (derivest.m:415-418)
+    double dinit[DV_NE];
+#pragma unroll
+    for (int e = 0; e < DV_NE; ++e)
+      dinit[e] = (fdel_s[e][tid] * dv.fdarule[0] + fdel_s[e + 1][tid] * dv.fdarule[1]) / (h * dv.delta[e]);
+    // rombextrap (derivest.m:512-526)
+    double dr[DV_NEST], er[DV_NEST];
+#pragma unroll
+    for (int c = 0; c < DV_NEST; ++c) {
+      double qtr[3], coef[3];
+#pragma unroll
+      for (int cc = 0; cc < 3; ++cc) {
+        double acc = 0.0;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) acc += dv.q[r][cc] * dinit[r + c];
+        qtr[cc] = acc;
+      }
+      coef[2] = qtr[2] / dv.rr[2][2];
+      coef[1] = (qtr[1] - dv.rr[1][2] * coef[2]) / dv.rr[1][1];
+      coef[0] = ((qtr[0] - dv.rr[0][1] * coef[1]) - dv.rr[0][2] * coef[2]) / dv.rr[0][0];
+      dr[c] = coef[0];
+      double ss = 0.0;
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const double res =
+            dinit[r + c] - ((dv.rmat[r][0] * coef[0] + dv.rmat[r][1] * coef[1]) + dv.rmat[r][2] * coef[2]);
+        ss += res * res;
+      }
+      er[c] = sqrt(ss) * dv.errfac;
+    }
+    // sort ascending (stable), drop ranks {1,2,nest-1,nest}, take the minimum error (derivest.m:442-462).
+    // Done by rank counting: no data-dependent indexing, everything stays in registers.
+    double best_err = INFINITY;
+    int best_rank = DV_NEST;
+    bool have = false;
+#pragma unroll
+    for (int c = 0; c < DV_NEST; ++c) {
+      int rank = 0;
+#pragma unroll
+      for (int e = 0; e < DV_NEST; ++e) {
+        const bool lt = dr[e] < dr[c] || (isnan(dr[c]) && !isnan(dr[e]));
+        const bool eq = (dr[e] == dr[c]) || (isnan(dr[c]) && isnan(dr[e]));
+        rank += (lt || (eq && e < c)) ? 1 : 0;
+      }
+      if (rank >= 2 && rank < DV_NEST - 2) {
+        // min() returns the first minimum in sorted order -> smallest rank on ties
+        if (!have || er[c] < best_err || (er[c] == best_err && rank < best_rank)) {
+          best_err = er[c];
+          best_rank = rank;
+          der = dr[c];
+          have = true;
+        }
+      }
+    }
+  }
+  a.grad[o * NJ + s] = der;
+  if (touched && a.flags) atomicOr(&a.flags[prob], 0x100);
+}
+
+cudaError_t launch_grad_derivest(const GradArgs &a, cudaStream_t s) {
+  const long long total = (long long)a.nslots * a.H * a.nobs * a.nj;
+  if (total <= 0) return cudaSuccess;
+  const int grid = (int)((total + GRAD_THREADS - 1) / GRAD_THREADS);
+  switch (a.nj) {
+    case 2: k_grad_derivest<2><<<grid, GRAD_THREADS, 0, s>>>(a); break;
+    case 3: k_grad_derivest<3><<<grid, GRAD_THREADS, 0, s>>>(a); break;
+    case 4: k_grad_derivest<4><<<grid, GRAD_THREADS, 0, s>>>(a); break;
+    case 5: k_grad_derivest<5><<<grid, GRAD_THREADS, 0, s>>>(a); break;
+    case 6: k_grad_derivest<6><<<grid, GRAD_THREADS, 0, s>>>(a); break;
+    default: return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
+}
+
+// ============================================================================================================
+// K6: RRT node feasibility (RRT_FANUC.m:146-181) and nearest/steer (RRT_FANUC.m:116-129)
+// ============================================================================================================
+__global__ void __launch_bounds__(GRAD_THREADS) k_nodes_feasible(const DevTables *gtab, int nj, int nobs, int N,
+                                                                const double *theta, unsigned char *feasible,
+                                                                double *dmin) {
+  __shared__ alignas(128) DevTables tab;
+  __shared__ alignas(8) uint64_t mbar;
+  tma_stage(&tab, gtab, tab_bytes(nobs), &mbar);
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= N) return;
+  Xf M, Mn;
+  double p[6];
+  int touched = 0;
+  bool feas = true;
+  double dm = INFINITY;
+  for (int l = 0; l < nj; ++l) {
+    double s, c;
+    sincos(theta[(long long)t * nj + l] + tab.link[l].th_off, &s, &c);
+    if (l == 0) {
+      xf_first(tab.link[0], c, s, M);
+    } else {
+      xf_step(M, tab.link[l], c, s, Mn);
+      M = Mn;
+    }
+    link_endpoints(M, tab.link[l], tab.base, p);
+    for (int j = 0; j < nobs; ++j) {
+      const double d = link_obs_dist(p, tab.obs[j], touched);
+      dm = d < dm ? d : dm;
+      if (d < tab.obs[j].D) feas = false;  // RRT_FANUC.m:172
+    }
+  }
+  feasible[t] = feas ? 1 : 0;
+  if (dmin) dmin[t] = dm;
+}
+
+cudaError_t launch_nodes_feasible(const DevTables *tab, int nj, int nobs, int N, const double *theta,
+                                  unsigned char *feasible, double *dmin, cudaStream_t s) {
+  if (N <= 0) return cudaSuccess;
+  k_nodes_feasible<<<(N + GRAD_THREADS - 1) / GRAD_THREADS, GRAD_THREADS, 0, s>>>(tab, nj, nobs, N, theta, feasible,
+                                                                                   dmin);
+  return cudaGetLastError();
+}
+
+__global__ void k_nearest_steer(int nj, int n_nodes, const double *nodes, int S, const double *samples,
+                                const double *ratial, double step, int *parent, double *newnode) {
+  const int sidx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (sidx >= S) return;
+  double smp[CFS_MAXL], rat[CFS_MAXL];
+  for (int k = 0; k < nj; ++k) {
+    smp[k] = samples[(long long)sidx * nj + k];
+    rat[k] = ratial[k];
+  }
+  int best = 0;
+  double bestd = 0.0;
+  for (int i = 0; i < n_nodes; ++i) {
+    double ss = 0.0;
+    for (int k = 0; k < nj; ++k) {
+      const double v = (nodes[(long long)i * nj + k] - smp[k]) * rat[k];
+      ss += v * v;
+    }
+    const double d = sqrt(ss);
+    if (i == 0 || d < bestd) {  // RRT_FANUC.m:119-126 : strict <, first minimum wins
+      bestd = d;
+      best = i;
+    }
+  }
+  parent[sidx] = best;
+  double ss = 0.0;
+  for (int k = 0; k < nj; ++k) {
+    const double v = nodes[(long long)best * nj + k] - smp[k];
+    ss += v * v;
+  }
+  const double nrm = sqrt(ss);
+  for (int k = 0; k < nj; ++k) {  // RRT_FANUC.m:129
+    const double pk = nodes[(long long)best * nj + k];
+    newnode[(long long)sidx * nj + k] = pk + (smp[k] - pk) * step / nrm;
+  }
+}
+
+cudaError_t launch_nearest_steer(int nj, int n_nodes, const double *nodes, int S, const double *samples,
+                                 const double *ratial, double step, int *parent, double *newnode, cudaStream_t s) {
+  if (S <= 0) return cudaSuccess;
+  k_nearest_steer<<<(S + 127) / 128, 128, 0, s>>>(nj, n_nodes, nodes, S, samples, ratial, step, parent, newnode);
+  return cudaGetLastError();
+}
+
+// ============================================================================================================
+// FP64 FMA peak micro-benchmark (roofline denominator)
+// ============================================================================================================
+__global__ void k_fp64_peak(double *sink, int iters) {
+  double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6,
+         a7 = a0 + 7;
+  const double b = 1.0000001, c = 1e-9;
+  for (int i = 0; i < iters; ++i) {
+    a0 = fma(a0, b, c); a1 = fma(a1, b, c); a2 = fma(a2, b, c); a3 = fma(a3, b, c);
+    a4 = fma(a4, b, c); a5 = fma(a5, b, c); a6 = fma(a6, b, c); a7 = fma(a7, b, c);
+  }
+  const double r = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+  if (r == 123.456) sink[0] = r;
+}
+
+cudaError_t launch_fp64_peak(double *sink, int iters, int grid, int block, cudaStream_t s) {
+  k_fp64_peak<<<grid, block, 0, s>>>(sink, iters);
+  return cudaGetLastError();
+}
+
+}  // namespace cfs

@@ -1,0 +1,677 @@
+// k_qp.cu -- K2+K3+K4: constraint assembly, batched strictly-convex QP, roll-out, cost and stop rule (sm_100a).
+//
+// Replaces, per outer iteration and per problem (reference file:line):
+//   Lib/CFS_FANUC.m:119-129   get_con row assembly  (l=-Diff'*Bj(1:njoint,:), s=I-Diff'*Bj*u, velocity rows)
+//   Lib/CFS_FANUC.m:85        quadprog(QQ,ff,Ainq,binq,[],[],-MAX_input,MAX_input)
+//   Lib/PSGCFS_FANUC.m:120    quadprog(I,-u_,Ainq,binq)                       (projection, identity metric)
+//   Lib/CFS_FANUC.m:90-94     roll-out xR(:,i)=A*xR(:,i-1)+B*u_i
+//   Lib/EVAL.m:51-73          get_cost, store_result, stop_outer
+//
+// Design (B200-first, not a translation of quadprog):
+//   * one persistent CTA per SM slot pulls problems from a device work queue (no host round trip, no tail of idle SMs);
+//   * the QP is solved by a dual active-set method (Goldfarb-Idnani) written entirely in "primitive space":
+//     v = P u (3n values: joint displacements B_theta u, joint velocities B_omega u, controls u) lives in shared
+//     memory; every constraint reads <= nj entries of v, and every metric inner product the method needs is a small
+//     bilinear form over the batch-shared Gram matrix G = P QQ^{-1} P' (k_setup.cu) held in L2.  No n x n
+//     per-problem factorisation, no dense Ainq (550 x 250 per problem in the reference) is ever formed;
+//   * the only per-problem matrix is the inverse of the working-set Gram matrix (q x q, q = #active rows, typically
+//     < 8), updated by rank-1 bordering on add / drop;
+//   * the optimal cost comes from duality: f(u) = f(u0) + 1/2 sum_w lambda_w * (violation of row w at u0).
+#include "cfs_kernels.cuh"
+
+namespace cfs {
+
+#define QP_THREADS 128
+#define QP_DEP_TOL 1e-8
+#define QP_WARPS (QP_THREADS / 32)
+
+struct QpView {  // decoded shared-memory layout
+  double *v;       // np
+  double *ocoef;   // OH*nj   (-g)
+  double *orhs;    // OH
+  double *onrm;    // OH      sqrt(c QQ^-1 c')
+  double *lam;     // n+1
+  double *r;       // n+1
+  double *g;       // n+1
+  double *red;     // 4*QP_WARPS
+  int *act;        // n+1
+  int *ctl;        // 8 ints of control words
+  unsigned char *inact;  // m
+};
+
+__host__ __device__ inline size_t qp_smem_layout(int n, int nj, int OH, int m, size_t *off /*[11]*/) {
+  size_t o = 0;
+  const int np = 3 * n;
+  off[0] = o; o += sizeof(double) * np;
+  off[1] = o; o += sizeof(double) * (size_t)OH * nj;
+  off[2] = o; o += sizeof(double) * OH;
+  off[3] = o; o += sizeof(double) * OH;
+  off[4] = o; o += sizeof(double) * (n + 2);
+  off[5] = o; o += sizeof(double) * (n + 2);
+  off[6] = o; o += sizeof(double) * (n + 2);
+  off[7] = o; o += sizeof(double) * 4 * QP_WARPS;
+  off[8] = o; o += sizeof(int) * (n + 2);
+  off[9] = o; o += sizeof(int) * 8;
+  off[10] = o; o += (size_t)((m + 15) / 16) * 16;
+  return (o + 15) / 16 * 16;
+}
+
+size_t qp_smem_bytes(const SolveArgs &a) {
+  size_t off[11];
+  const int OH = a.nobs * a.H;
+  return qp_smem_layout(a.n, a.nj, OH, OH + 4 * a.n, off);
+}
+
+// ---- constraint descriptors --------------------------------------------------------------------------------
+// cid in [0,OH): obstacle row (j,i), cid = j*H+i, terms k<nj on theta primitive (i,k) with coefficient ocoef[cid*nj+k]
+// cid in [OH,OH+2n): velocity row of omega primitive idx=(cid-OH)>>1, sign bit (0: +row <= lim-w0, 1: -row <= lim+w0)
+// cid in [OH+2n,OH+4n): bound row of control idx, sign bit likewise (CFS_FANUC.m:85 lb/ub)
+struct Desc {
+  int nterm;
+  int row0;     // first primitive row; terms are consecutive rows
+  double coef;  // single-term coefficient (+-1) when nterm == 1
+  const double *cv;  // coefficient vector when nterm > 1
+};
+
+__device__ __forceinline__ Desc decode(int cid, int OH, int H, int n, int nj, const double *ocoef) {
+  Desc d;
+  if (cid < OH) {
+    const int i = cid % H;
+    d.nterm = nj;
+    d.row0 = i * nj;
+    d.coef = 0.0;
+    d.cv = ocoef + (size_t)cid * nj;
+  } else {
+    const int e = cid - OH;  // [0,2n): omega primitives n.., [2n,4n): control primitives 2n..
+    d.nterm = 1;
+    d.row0 = n + (e >> 1);
+    d.coef = (e & 1) ? -1.0 : 1.0;
+    d.cv = nullptr;
+  }
+  return d;
+}
+
+__device__ __forceinline__ double gram(const Desc &a, const Desc &b, const double *__restrict__ G, int np) {
+  double s = 0.0;
+  for (int k = 0; k < a.nterm; ++k) {
+    const double ca = a.cv ? a.cv[k] : a.coef;
+    const double *Gr = G + (size_t)(a.row0 + k) * np + b.row0;
+    double t = 0.0;
+    for (int l = 0; l < b.nterm; ++l) t += (b.cv ? b.cv[l] : b.coef) * Gr[l];
+    s += ca * t;
+  }
+  return s;
+}
+
+// (P QQ^-1 c_a')[pi]
+__device__ __forceinline__ double gcol(const Desc &a, int pi, const double *__restrict__ G, int np) {
+  if (a.nterm == 1) return a.coef * G[(size_t)a.row0 * np + pi];
+  double s = 0.0;
+  for (int k = 0; k < a.nterm; ++k) s += a.cv[k] * G[(size_t)(a.row0 + k) * np + pi];
+  return s;
+}
+
+struct Limits {
+  const double *lim, *umax;
+  double w0[CFS_MAXL];
+  int has_lim, has_bounds;
+};
+
+// slack = rhs - c u, evaluated from the primitive values v
+__device__ __forceinline__ double slack_of(int cid, int OH, int H, int n, int nj, const QpView &s, const Limits &L) {
+  if (cid < OH) {
+    const int i = cid % H;
+    const double *c = s.ocoef + (size_t)cid * nj;
+    const double *vv = s.v + i * nj;
+    double val = 0.0;
+    for (int k = 0; k < nj; ++k) val += c[k] * vv[k];
+    return s.orhs[cid] - val;
+  }
+  const int e = cid - OH;
+  const int idx = e >> 1, neg = e & 1;
+  if (e < 2 * n) {  // CFS_FANUC.m:126-129 : +-Baug_w u <= lim -+ Aaug_w x0
+    const int k = idx % nj;
+    const double vv = s.v[n + idx];
+    return neg ? (L.lim[k] + L.w0[k]) + vv : (L.lim[k] - L.w0[k]) - vv;
+  }
+  const int c = idx - n;
+  const double vv = s.v[2 * n + c];
+  return neg ? L.umax[c] + vv : L.umax[c] - vv;
+}
+
+__device__ __forceinline__ double rhs_scale(int cid, int OH, int n, int nj, const QpView &s, const Limits &L) {
+  if (cid < OH) return fabs(s.orhs[cid]);
+  const int e = cid - OH, idx = e >> 1;
+  if (e < 2 * n) return L.lim[idx % nj];
+  return L.umax[idx - n];
+}
+
+// ---- block reductions (QP_THREADS threads) --------------------------------------------------------------------
+__device__ __forceinline__ void block_argmin(double &val, int &idx, double *red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double ov = __shfl_down_sync(0xffffffffu, val, o);
+    const int oi = __shfl_down_sync(0xffffffffu, idx, o);
+    if (ov < val || (ov == val && oi >= 0 && (idx < 0 || oi < idx))) {
+      val = ov;
+      idx = oi;
+    }
+  }
+  const int w = threadIdx.x >> 5;
+  __syncthreads();  // protect red from the previous use
+  if ((threadIdx.x & 31) == 0) {
+    red[2 * w] = val;
+    reinterpret_cast<int *>(red + 2 * w + 1)[0] = idx;
+  }
+  __syncthreads();
+  val = red[0];
+  idx = reinterpret_cast<int *>(red + 1)[0];
+#pragma unroll
+  for (int ww = 1; ww < QP_WARPS; ++ww) {
+    const double ov = red[2 * ww];
+    const int oi = reinterpret_cast<int *>(red + 2 * ww + 1)[0];
+    if (ov < val || (ov == val && oi >= 0 && (idx < 0 || oi < idx))) {
+      val = ov;
+      idx = oi;
+    }
+  }
+}
+
+__device__ __forceinline__ double block_sum(double val, double *red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) val += __shfl_down_sync(0xffffffffu, val, o);
+  const int w = threadIdx.x >> 5;
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[w] = val;
+  __syncthreads();
+  double s = red[0];
+#pragma unroll
+  for (int ww = 1; ww < QP_WARPS; ++ww) s += red[ww];
+  return s;
+}
+
+// ============================================================================================================
+// The kernel
+// ============================================================================================================
+__global__ void __launch_bounds__(QP_THREADS) k_qp(SolveArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int n = a.n, nj = a.nj, H = a.H, np = 3 * n, OH = a.nobs * H, m = OH + 4 * n;
+  const int tid = threadIdx.x;
+  size_t off[11];
+  qp_smem_layout(n, nj, OH, m, off);
+  QpView s;
+  s.v = reinterpret_cast<double *>(smem_raw + off[0]);
+  s.ocoef = reinterpret_cast<double *>(smem_raw + off[1]);
+  s.orhs = reinterpret_cast<double *>(smem_raw + off[2]);
+  s.onrm = reinterpret_cast<double *>(smem_raw + off[3]);
+  s.lam = reinterpret_cast<double *>(smem_raw + off[4]);
+  s.r = reinterpret_cast<double *>(smem_raw + off[5]);
+  s.g = reinterpret_cast<double *>(smem_raw + off[6]);
+  s.red = reinterpret_cast<double *>(smem_raw + off[7]);
+  s.act = reinterpret_cast<int *>(smem_raw + off[8]);
+  s.ctl = reinterpret_cast<int *>(smem_raw + off[9]);
+  s.inact = smem_raw + off[10];
+
+  const double *__restrict__ G = a.G;
+  const double *__restrict__ gnorm = a.gdiag;  // sqrt(diag(G))
+  const double dt = a.tab->dt;
+  const int ld = a.slab_ld;
+  double *Minv = a.slab + (size_t)blockIdx.x * ld * ld;  // working-set inverse, column-major
+  const int count = *a.count_cur;
+  const int has_vel = a.has_lim, has_bnd = a.has_bounds;
+  long long steps_total = 0;
+  int qmax_seen = 0;
+
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) s.ctl[0] = atomicAdd(a.work_counter, 1);
+    __syncthreads();
+    const int slot = s.ctl[0];
+    if (slot >= count) break;
+    const int b = a.list_cur[slot];
+    const double *x0 = a.x0 + (size_t)b * 2 * nj;
+    double *ub = a.u + (size_t)b * n;
+    double *xb = a.x + (size_t)b * 2 * n;
+    const double *v0 = a.v0 + (size_t)b * np;
+
+    Limits L;
+    L.lim = a.lim;
+    L.umax = a.max_input;
+    L.has_lim = has_vel;
+    L.has_bounds = has_bnd;
+#pragma unroll
+    for (int k = 0; k < CFS_MAXL; ++k) L.w0[k] = (k < nj) ? x0[nj + k] : 0.0;
+
+    // ---- prologue: v = v0; disp = B_theta u_cur; obstacle rows ------------------------------------------------
+    for (int pi = tid; pi < np; pi += QP_THREADS) s.v[pi] = v0[pi];
+    for (int e = tid; e < m; e += QP_THREADS) s.inact[e] = 0;
+    // disp(i,k) = sum_{j<=i} (0.5 dt^2 + (i-j) dt dt) u(j,k)   ( = Bj(1:njoint,:)*u of CFS_FANUC.m:120 ) -> s.g
+    for (int e = tid; e < n; e += QP_THREADS) {
+      const int i = e / nj, k = e % nj;
+      double acc = 0.0;
+      for (int j = 0; j <= i; ++j) acc += (0.5 * dt * dt + ((i - j) * dt) * dt) * ub[j * nj + k];
+      s.g[e] = acc;
+    }
+    __syncthreads();
+    for (int cid = tid; cid < OH; cid += QP_THREADS) {
+      const int j = cid / H, i = cid % H;
+      const double *gr = a.grad + ((size_t)b * OH + cid) * nj;
+      const double dist = a.dist[(size_t)b * OH + cid];
+      const double margin = a.margin_is_D ? a.tab->obs[j].D : a.tab->obs[j].eps;
+      double gu = 0.0;
+      for (int k = 0; k < nj; ++k) {
+        s.ocoef[cid * nj + k] = -gr[k];                 // l = -Diff'*Bj(1:njoint,:)   (CFS_FANUC.m:121)
+        gu += gr[k] * s.g[i * nj + k];
+      }
+      s.orhs[cid] = (dist - margin) - gu;               // s = I - Diff'*Bj*u          (CFS_FANUC.m:117,120)
+    }
+    __syncthreads();
+    for (int cid = tid; cid < OH; cid += QP_THREADS) {
+      const Desc d = decode(cid, OH, H, n, nj, s.ocoef);
+      const double sg = gram(d, d, G, np);
+      s.onrm[cid] = sg > 0.0 ? sqrt(sg) : 0.0;
+    }
+    __syncthreads();
+
+    // ---- dual active-set iterations --------------------------------------------------------------------------
+    int q = 0, status = -1, steps = 0;
+    double fval = a.cost0[b];
+    const double fupper = (has_bnd && a.fupper) ? a.fupper[b] : INFINITY;
+    const int max_steps = 20 * (m + n) + 100;
+    while (status < 0) {
+      // (1) most violated inactive row, normalised by its QQ^-1 norm
+      double best = 0.0;
+      int bidx = -1;
+      for (int cid = tid; cid < m; cid += QP_THREADS) {
+        if (cid >= OH) {
+          const int e = cid - OH;
+          if (e < 2 * n ? !has_vel : !has_bnd) continue;
+        }
+        if (s.inact[cid]) continue;
+        const double nr = cid < OH ? s.onrm[cid] : gnorm[n + ((cid - OH) >> 1)];
+        if (!(nr > 0.0)) continue;
+        const double sl = slack_of(cid, OH, H, n, nj, s, L);
+        const double tol = 1e-11 * (1.0 + rhs_scale(cid, OH, n, nj, s, L));
+        if (sl < -tol) {
+          const double val = sl / nr;
+          if (val < best || bidx < 0) {
+            best = val;
+            bidx = cid;
+          }
+        }
+      }
+      block_argmin(best, bidx, s.red);
+      if (bidx < 0) {
+        status = 0;
+        break;
+      }
+      const int p = bidx;
+      const Desc dp = decode(p, OH, H, n, nj, s.ocoef);
+      double lam_p = 0.0;
+      // (2) bring row p into the working set
+      for (;;) {
+        if (++steps > max_steps) {
+          status = 3;
+          break;
+        }
+        // g_w = c_w QQ^-1 c_p'
+        for (int w = tid; w < q; w += QP_THREADS) s.g[w] = gram(decode(s.act[w], OH, H, n, nj, s.ocoef), dp, G, np);
+        const double sigma = gram(dp, dp, G, np);
+        __syncthreads();
+        // r = Minv g
+        double part = 0.0;
+        for (int w = tid; w < q; w += QP_THREADS) {
+          double acc = 0.0;
+          for (int c = 0; c < q; ++c) acc += Minv[w + (size_t)ld * c] * s.g[c];
+          s.r[w] = acc;
+          part += s.g[w] * acc;
+        }
+        const double delta = sigma - block_sum(part, s.red);  // z'n+ in Goldfarb-Idnani's notation
+        // t1: largest dual step keeping the multipliers non-negative
+        double t1 = INFINITY;
+        int l = -1;
+        for (int w = tid; w < q; w += QP_THREADS)
+          if (s.r[w] > 0.0) {
+            const double t = s.lam[w] / s.r[w];
+            if (t < t1 || l < 0) {
+              t1 = t;
+              l = w;
+            }
+          }
+        block_argmin(t1, l, s.red);
+        if (l < 0) t1 = INFINITY;
+        if (!(delta == delta) || !(sigma == sigma)) {
+          status = 3;
+          break;
+        }
+        // Row p is treated as linearly dependent on the working set when its QQ^-1-orthogonal remainder is below
+        // 1e-8 of its norm^2: in Gram form delta carries cancellation noise ~eps*cond(S_W)*sigma, and a step of
+        // length -sp/delta along such a direction only manufactures astronomically large multipliers.
+        const bool dependent = !(delta > QP_DEP_TOL * sigma);
+        const double sp = slack_of(p, OH, H, n, nj, s, L);
+        double t2 = INFINITY;
+        if (!dependent) {
+          t2 = -sp / delta;
+          if (t2 < 0.0) t2 = 0.0;
+        }
+        if (l < 0 && dependent) {
+          status = 2;  // infeasible
+          break;
+        }
+        const bool full = (t2 <= t1);
+        const double t = full ? t2 : t1;
+        // dual objective (Goldfarb-Idnani: f += t z'n+ (t/2 + u+_{q+1})); weak duality: if it exceeds an upper bound of
+        // the primal objective over the box |u| <= MAX_input the QP has no feasible point.
+        if (!dependent) fval += t * delta * (0.5 * t + lam_p);
+        if (fval > fupper) {
+          status = 2;
+          break;
+        }
+        // multipliers
+        for (int w = tid; w < q; w += QP_THREADS) s.lam[w] -= t * s.r[w];
+        lam_p += t;
+        // primal move in primitive space: v += -t * (G c_p' - sum_w r_w G c_w')
+        if (!dependent && t > 0.0) {
+          for (int pi = tid; pi < np; pi += QP_THREADS) {
+            double acc = gcol(dp, pi, G, np);
+            for (int w = 0; w < q; ++w) acc -= s.r[w] * gcol(decode(s.act[w], OH, H, n, nj, s.ocoef), pi, G, np);
+            s.v[pi] -= t * acc;
+          }
+        }
+        __syncthreads();
+        if (full) {
+          // add p: bordered inverse  [[M + r r'/d, -r/d], [-r'/d, 1/d]]
+          const double id = 1.0 / delta;
+          for (int e = tid; e < (q + 1) * (q + 1); e += QP_THREADS) {
+            const int r_ = e % (q + 1), c_ = e / (q + 1);
+            double val;
+            if (r_ < q && c_ < q)
+              val = Minv[r_ + (size_t)ld * c_] + s.r[r_] * s.r[c_] * id;
+            else if (r_ == q && c_ == q)
+              val = id;
+            else
+              val = -s.r[r_ < q ? r_ : c_] * id;
+            Minv[r_ + (size_t)ld * c_] = val;
+          }
+          if (tid == 0) {
+            s.act[q] = p;
+            s.lam[q] = lam_p;
+            s.inact[p] = 1;
+          }
+          ++q;
+          if (q > qmax_seen) qmax_seen = q;
+          __syncthreads();
+          break;
+        }
+        // drop working-set member l: M <- M - M(:,l) M(l,:)/M(l,l), then move the last member into slot l
+        {
+          const int last = q - 1;
+          for (int w = tid; w < q; w += QP_THREADS) s.g[w] = Minv[w + (size_t)ld * l];
+          __syncthreads();
+          const double ip = 1.0 / s.g[l];
+          for (int e = tid; e < q * q; e += QP_THREADS) {
+            const int r_ = e % q, c_ = e / q;
+            Minv[r_ + (size_t)ld * c_] -= s.g[r_] * s.g[c_] * ip;
+          }
+          __syncthreads();
+          if (l != last) {
+            for (int w = tid; w < q; w += QP_THREADS) Minv[w + (size_t)ld * l] = Minv[w + (size_t)ld * last];
+            __syncthreads();
+            for (int w = tid; w < q; w += QP_THREADS) Minv[l + (size_t)ld * w] = Minv[last + (size_t)ld * w];
+          }
+          if (tid == 0) {
+            s.inact[s.act[l]] = 0;
+            s.act[l] = s.act[last];
+            s.lam[l] = s.lam[last];
+          }
+          --q;
+          __syncthreads();
+        }
+      }
+    }
+    steps_total += steps;
+
+    // ---- epilogue ------------------------------------------------------------------------------------------------
+    const int it = a.outer_iter;  // 1-based
+    if (status == 0) {
+      // u = control block of v; e_u = ||u_old - u||   (EVAL.m:58)
+      double pe = 0.0;
+      for (int c = tid; c < n; c += QP_THREADS) {
+        const double un = s.v[2 * n + c];
+        const double dlt = ub[c] - un;
+        pe += dlt * dlt;
+        ub[c] = un;
+      }
+      const double e_u = sqrt(block_sum(pe, s.red));
+      // cost by duality: f(u) = f(u0) + 1/2 sum_w lam_w * (c_w u0 - rhs_w)
+      double pc = 0.0;
+      for (int w = tid; w < q; w += QP_THREADS) {
+        const int cid = s.act[w];
+        double val0;  // c_w u0 - rhs_w = -slack at u0
+        if (cid < OH) {
+          const int i = cid % H;
+          double val = 0.0;
+          for (int k = 0; k < nj; ++k) val += s.ocoef[cid * nj + k] * v0[i * nj + k];
+          val0 = val - s.orhs[cid];
+        } else {
+          const int e = cid - OH, idx = e >> 1, neg = e & 1;
+          if (e < 2 * n) {
+            const int k = idx % nj;
+            val0 = neg ? -v0[n + idx] - (L.lim[k] + L.w0[k]) : v0[n + idx] - (L.lim[k] - L.w0[k]);
+          } else {
+            const int c = idx - n;
+            val0 = neg ? -v0[2 * n + c] - L.umax[c] : v0[2 * n + c] - L.umax[c];
+          }
+        }
+        pc += s.lam[w] * val0;
+      }
+      const double cost = a.cost0[b] + 0.5 * block_sum(pc, s.red);
+      // roll-out (CFS_FANUC.m:90-94) by nj threads, accumulating ||x_new - x_old||^2 (EVAL.m:64)
+      double px = 0.0;
+      if (tid < nj) {
+        double th = x0[tid], om = x0[nj + tid];
+        for (int i = 0; i < H; ++i) {
+          const double uk = s.v[2 * n + i * nj + tid];
+          const double thn = (th + dt * om) + (0.5 * dt * dt) * uk;
+          const double omn = om + dt * uk;
+          th = thn;
+          om = omn;
+          double *xs = xb + (size_t)i * 2 * nj;
+          const double d1 = th - xs[tid], d2 = om - xs[nj + tid];
+          px += d1 * d1 + d2 * d2;
+          xs[tid] = th;
+          xs[nj + tid] = om;
+        }
+      }
+      const double dx = sqrt(block_sum(px, s.red));
+      if (tid == 0) {
+        a.cost_hist[(size_t)b * a.max_outer + (it - 1)] = cost;
+        if (a.e_u_hist) a.e_u_hist[(size_t)b * a.max_outer + (it - 1)] = e_u;
+        a.iters[b] = it;
+        if (dx < a.eps_outer) {
+          a.status[b] = 0;  // converged (EVAL.m:64-67)
+        } else if (it + 1 > a.max_outer) {
+          a.status[b] = 1;  // MAX_ITER (EVAL.m:69-72)
+        } else {
+          a.list_next[atomicAdd(a.count_next, 1)] = b;
+        }
+      }
+    } else if (tid == 0) {
+      a.status[b] = status;  // 2 infeasible / 3 numerical: u, x keep the previous iterate
+    }
+  }
+  if (tid == 0) {
+    if (steps_total) atomicAdd(reinterpret_cast<unsigned long long *>(a.qp_steps), (unsigned long long)steps_total);
+    if (qmax_seen) atomicMax(a.max_active, qmax_seen);
+  }
+}
+
+int qp_max_grid(const SolveArgs &a, int device) {
+  int sms = 0, per = 0;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  const size_t smem = qp_smem_bytes(a);
+  cudaFuncSetAttribute(k_qp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_qp, QP_THREADS, smem);
+  if (per < 1) per = 1;
+  return sms * per;
+}
+
+cudaError_t launch_qp(const SolveArgs &a, int grid, cudaStream_t st) {
+  const size_t smem = qp_smem_bytes(a);
+  k_qp<<<grid, QP_THREADS, smem, st>>>(a);
+  return cudaGetLastError();
+}
+
+// ============================================================================================================
+// Batch initialisation
+// ============================================================================================================
+// one CTA per problem: u=0, x_=sys_info.x_ (CFS_FANUC.m:55-56), histories NaN, first stop_outer test with
+// x_old = ones (EVAL.m:47,61-73), initial active list.
+__global__ void __launch_bounds__(128) k_solve_init(SolveArgs a) {
+  __shared__ double red[QP_WARPS];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const int n = a.n, N = 2 * n;
+  double part = 0.0;
+  for (int e = tid; e < N; e += blockDim.x) {
+    const double xv = a.xref[(size_t)b * N + e];
+    a.x[(size_t)b * N + e] = xv;
+    part += (xv - 1.0) * (xv - 1.0);
+  }
+  for (int e = tid; e < n; e += blockDim.x) a.u[(size_t)b * n + e] = 0.0;
+  for (int e = tid; e < a.max_outer; e += blockDim.x) {
+    a.cost_hist[(size_t)b * a.max_outer + e] = __longlong_as_double(0x7ff8000000000000LL);
+    if (a.e_u_hist) a.e_u_hist[(size_t)b * a.max_outer + e] = __longlong_as_double(0x7ff8000000000000LL);
+  }
+  const double nrm = sqrt(block_sum(part, red));
+  if (tid == 0) {
+    a.iters[b] = 0;
+    a.flags[b] = 0;
+    if (nrm < a.eps_outer) {
+      a.status[b] = 0;
+    } else if (1 > a.max_outer) {
+      a.status[b] = 1;
+    } else {
+      a.status[b] = -1;
+      a.list_cur[atomicAdd(a.count_cur, 1)] = b;
+    }
+  }
+}
+
+cudaError_t launch_solve_init(const SolveArgs &a, cudaStream_t s) {
+  if (a.B <= 0) return cudaSuccess;
+  k_solve_init<<<a.B, 128, 0, s>>>(a);
+  return cudaGetLastError();
+}
+
+// v0 = P u0 and cost0 = caug + 1/2 ff'u0 (value of EVAL.get_cost at the unconstrained minimiser), one CTA per problem
+__global__ void __launch_bounds__(128) k_v0(SolveArgs a) {
+  __shared__ double red[QP_WARPS];
+  extern __shared__ double u0s[];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const int n = a.n, nj = a.nj, np = 3 * n;
+  const double dt = a.tab->dt;
+  double part = 0.0;
+  for (int e = tid; e < n; e += blockDim.x) {
+    const double uv = a.u0[(size_t)b * n + e];
+    u0s[e] = uv;
+    part += a.ff[(size_t)b * n + e] * uv;
+  }
+  const double fu = block_sum(part, red);
+  if (tid == 0) a.cost0[b] = a.caug[b] + 0.5 * fu;
+  if (a.fupper) {  // sup over the box |u|<=MAX_input of EVAL.get_cost: 1/2 ||QQ||_inf sum umax^2 + sum |ff| umax + caug
+    double pb = 0.0;
+    if (a.has_bounds)
+      for (int e = tid; e < n; e += blockDim.x) {
+        const double um = a.max_input[e];
+        pb += 0.5 * a.qq_norm_inf * um * um + fabs(a.ff[(size_t)b * n + e]) * um;
+      }
+    const double sb = block_sum(pb, red);
+    if (tid == 0) a.fupper[b] = a.has_bounds ? (fabs(a.caug[b]) + sb) * (1.0 + 1e-6) + 1e-6 : INFINITY;
+  }
+  for (int pi = tid; pi < np; pi += blockDim.x) {
+    double acc;
+    if (pi < n) {
+      const int i = pi / nj, k = pi % nj;
+      acc = 0.0;
+      for (int j = 0; j <= i; ++j) acc += (0.5 * dt * dt + ((i - j) * dt) * dt) * u0s[j * nj + k];
+    } else if (pi < 2 * n) {
+      const int qq = pi - n, i = qq / nj, k = qq % nj;
+      acc = 0.0;
+      for (int j = 0; j <= i; ++j) acc += dt * u0s[j * nj + k];
+    } else {
+      acc = u0s[pi - 2 * n];
+    }
+    a.v0[(size_t)b * np + pi] = acc;
+  }
+}
+
+cudaError_t launch_v0(const SolveArgs &a, cudaStream_t s) {
+  if (a.B <= 0) return cudaSuccess;
+  k_v0<<<a.B, 128, sizeof(double) * a.n, s>>>(a);
+  return cudaGetLastError();
+}
+
+// problems still marked running (-1) after the last launched iteration cannot exist; flags are merged into status here
+__global__ void k_finalize(SolveArgs a) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= a.B) return;
+  int st = a.status[b];
+  if (st < 0) st = 1;
+  a.status[b] = st | (a.flags[b] & 0x100);
+}
+
+cudaError_t launch_finalize(const SolveArgs &a, cudaStream_t s) {
+  if (a.B <= 0) return cudaSuccess;
+  k_finalize<<<(a.B + 127) / 128, 128, 0, s>>>(a);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_psg_point(const SolveArgs &, cudaStream_t) { return cudaErrorNotSupported; }
+
+// ============================================================================================================
+// Dense get_con rows for one problem, in the reference's order (CFS_FANUC.m:110-131); parity/debug entry.
+// ============================================================================================================
+__global__ void k_get_con_rows(const DevTables *tab, int H, int nj, int nobs, int has_lim, int margin_is_D,
+                               const double *x0, const double *u, const double *lim, const double *dist,
+                               const double *grad, double *Ainq, double *binq, int m) {
+  const int n = H * nj;
+  const int per = has_lim ? 1 + 2 * nj : 1;
+  const double dt = tab->dt;
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (long long)m * n) return;
+  const int row = (int)(e % m), col = (int)(e / m);
+  const int blk = row / per, sub = row % per;
+  const int j = blk / H, i = blk % H;
+  const int jj = col / nj, k = col % nj;
+  double val = 0.0;
+  if (sub == 0) {
+    const double g = grad[((size_t)j * H + i) * nj + k];
+    if (jj <= i) val = -(g * (0.5 * dt * dt + ((i - jj) * dt) * dt));
+    if (col == 0) {
+      double gu = 0.0;
+      for (int c = 0; c < n; ++c) {
+        const int j2 = c / nj, k2 = c % nj;
+        if (j2 <= i) gu += (grad[((size_t)j * H + i) * nj + k2] * (0.5 * dt * dt + ((i - j2) * dt) * dt)) * u[c];
+      }
+      const double margin = margin_is_D ? tab->obs[j].D : tab->obs[j].eps;
+      binq[row] = (dist[(size_t)j * H + i] - margin) - gu;
+    }
+  } else {
+    const int kk = (sub - 1) % nj, neg = (sub - 1) / nj;
+    if (kk == k && jj <= i) val = neg ? -dt : dt;
+    if (col == 0) binq[row] = neg ? lim[kk] + x0[nj + kk] : lim[kk] - x0[nj + kk];
+  }
+  Ainq[row + (size_t)m * col] = val;
+}
+
+cudaError_t launch_get_con_rows(const DevTables *tab, int H, int nj, int nobs, int has_lim, int margin_is_D,
+                                const double *x0, const double *u, const double *lim, const double *dist,
+                                const double *grad, double *Ainq, double *binq, int m, cudaStream_t s) {
+  const long long total = (long long)m * H * nj;
+  if (total <= 0) return cudaSuccess;
+  k_get_con_rows<<<(int)((total + 255) / 256), 256, 0, s>>>(tab, H, nj, nobs, has_lim, margin_is_D, x0, u, lim, dist,
+                                                              grad, Ainq, binq, m);
+  return cudaGetLastError();
+}
+
+}  // namespace cfs

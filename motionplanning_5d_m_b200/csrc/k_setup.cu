@@ -1,0 +1,161 @@
+// k_setup.cu -- one-off device set-up per (H, weights): the shared Gram operator of the QP.
+//
+// Every inequality row CFS_FANUC.get_con (Lib/CFS_FANUC.m:119-129) and the quadprog bounds (:85) produce is a
+// combination of at most nj rows of P = [B_theta; B_omega; I] (3n x n), where B_theta/B_omega are the position /
+// velocity rows of sys_info.Baug (main_FANUC.m:84-86; closed form (0.5+(i-j))dt^2 and dt for j<=i).
+// With QQ = L L' shared by the whole batch, G = P QQ^{-1} P' = Y'Y, Y = L^{-1} P', is computed ONCE here; the
+// per-problem dual active-set solver (k_qp.cu) then never touches an n-vector: every inner product
+// c_a QQ^{-1} c_b' it needs is a <=nj x nj bilinear form over entries of G (4.5 MB at n=250: L2 resident).
+#include "cfs_kernels.cuh"
+
+namespace cfs {
+
+// ---- right-looking Cholesky of an n x n matrix held in global memory (column-major, lower), one CTA ----------
+__global__ void __launch_bounds__(1024) k_chol(int n, double *A, int *info) {
+  __shared__ double piv;
+  __shared__ int bad;
+  if (threadIdx.x == 0) bad = 0;
+  __syncthreads();
+  for (int j = 0; j < n; ++j) {
+    if (threadIdx.x == 0) {
+      const double d = A[j + (size_t)n * j];
+      if (!(d > 0.0)) bad = j + 1;
+      piv = sqrt(d);
+    }
+    __syncthreads();
+    if (bad) break;
+    const double d = piv;
+    for (int i = j + threadIdx.x; i < n; i += blockDim.x) A[i + (size_t)n * j] = (i == j) ? d : A[i + (size_t)n * j] / d;
+    __syncthreads();
+    // trailing update: A[i][c] -= L[i][j]*L[c][j] for j < c <= i
+    const int m = n - j - 1;
+    for (int e = threadIdx.x; e < m * m; e += blockDim.x) {
+      const int c = j + 1 + e / m, i = j + 1 + e % m;
+      if (i >= c) A[i + (size_t)n * c] -= A[i + (size_t)n * j] * A[c + (size_t)n * j];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *info = bad;
+}
+
+// b_pi = P'(:,pi): column pi of P' = row pi of P, as a function of the control index (j,k)
+__device__ __forceinline__ double p_entry(int pi, int col, int n, int nj, double dt) {
+  const int j = col / nj, k = col % nj;  // control u_{j,k}, j = 0..H-1
+  if (pi < n) {                          // theta primitive (i,kk): (0.5 + (i-j)) dt^2 for j <= i
+    const int i = pi / nj, kk = pi % nj;
+    return (kk == k && j <= i) ? (0.5 * dt * dt + ((i - j) * dt) * dt) : 0.0;
+  } else if (pi < 2 * n) {               // omega primitive: dt for j <= i
+    const int q = pi - n, i = q / nj, kk = q % nj;
+    return (kk == k && j <= i) ? dt : 0.0;
+  }
+  return (pi - 2 * n == col) ? 1.0 : 0.0;  // the control itself (bounds)
+}
+
+// Yt[pi + 3n*i] = (L^{-1} P')(i, pi): one thread per primitive pi, forward substitution, pi is the fast index so
+// every load of Yt is coalesced and every load of L is a warp-uniform broadcast.
+__global__ void k_trsm_primitives(int n, int nj, double dt, const double *L /*or nullptr = identity*/, double *Yt) {
+  const int np = 3 * n;
+  const int pi = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pi >= np) return;
+  for (int i = 0; i < n; ++i) {
+    double s = p_entry(pi, i, n, nj, dt);
+    if (L) {
+      const double *Li = L + i;  // L[i + n*k]
+#pragma unroll 4
+      for (int k = 0; k < i; ++k) s -= Li[(size_t)n * k] * Yt[pi + (size_t)np * k];
+      s /= Li[(size_t)n * i];
+    }
+    Yt[pi + (size_t)np * i] = s;
+  }
+}
+
+// ---- small tiled FP64 GEMM with arbitrary strides: C[m + ldc*nn] = alpha * sum_k A(m,k) B(k,nn) ----------------
+#define GT 64
+#define GK 16
+__global__ void __launch_bounds__(256) k_dgemm(int M, int N, int K, double alpha, const double *A, long long sAm,
+                                               long long sAk, const double *B, long long sBk, long long sBn, double *C,
+                                               int ldc) {
+  __shared__ double As[GK][GT + 1];
+  __shared__ double Bs[GK][GT + 1];
+  const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
+  const int m0 = blockIdx.x * GT, n0 = blockIdx.y * GT;
+  double acc[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
+  for (int k0 = 0; k0 < K; k0 += GK) {
+    for (int e = threadIdx.x; e < GT * GK; e += 256) {
+      const int mm = e % GT, kk = e / GT;
+      const int gm = m0 + mm, gk = k0 + kk;
+      As[kk][mm] = (gm < M && gk < K) ? A[gm * sAm + gk * sAk] : 0.0;
+      const int gn = n0 + mm;
+      Bs[kk][mm] = (gn < N && gk < K) ? B[gk * sBk + gn * sBn] : 0.0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < GK; ++kk) {
+      double av[4], bv[4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) av[a] = As[kk][tx + 16 * a];
+#pragma unroll
+      for (int b = 0; b < 4; ++b) bv[b] = Bs[kk][ty + 16 * b];
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = fma(av[a], bv[b], acc[a][b]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int gm = m0 + tx + 16 * a, gn = n0 + ty + 16 * b;
+      if (gm < M && gn < N) C[gm + (size_t)ldc * gn] = alpha * acc[a][b];
+    }
+}
+
+cudaError_t launch_dgemm(int M, int N, int K, double alpha, const double *A, int lda, bool transA, const double *B,
+                         int ldb, double *C, int ldc, cudaStream_t s) {
+  if (M <= 0 || N <= 0) return cudaSuccess;
+  dim3 grid((M + GT - 1) / GT, (N + GT - 1) / GT);
+  const long long sAm = transA ? lda : 1, sAk = transA ? 1 : lda;
+  k_dgemm<<<grid, 256, 0, s>>>(M, N, K, alpha, A, sAm, sAk, B, 1, ldb, C, ldc);
+  return cudaGetLastError();
+}
+
+__global__ void k_diag(int np, const double *G, double *gdiag) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < np) gdiag[i] = sqrt(G[i + (size_t)np * i]);  // QQ^-1 norm of each primitive row
+}
+
+__global__ void k_copy(size_t cnt, const double *src, double *dst) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += (size_t)gridDim.x * blockDim.x)
+    dst[i] = src[i];
+}
+
+cudaError_t setup_gram(int n, int H, int nj, double dt, const double *QQ, double *work_L, double *work_Y, double *G,
+                       double *gdiag, int *info, cudaStream_t s) {
+  (void)H;
+  const int np = 3 * n;
+  cudaError_t e;
+  if (QQ) {
+    k_copy<<<64, 256, 0, s>>>((size_t)n * n, QQ, work_L);
+    k_chol<<<1, 1024, 0, s>>>(n, work_L, info);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  } else {
+    e = cudaMemsetAsync(info, 0, sizeof(int), s);
+    if (e != cudaSuccess) return e;
+  }
+  k_trsm_primitives<<<(np + 63) / 64, 64, 0, s>>>(n, nj, dt, QQ ? work_L : nullptr, work_Y);
+  if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  // G = Yt * Yt'  (np x np, K = n):  A(m,k) = Yt[m + np*k], B(k,nn) = Yt[nn + np*k]
+  dim3 grid((np + GT - 1) / GT, (np + GT - 1) / GT);
+  k_dgemm<<<grid, 256, 0, s>>>(np, np, n, 1.0, work_Y, 1, np, work_Y, np, 1, G, np);
+  if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  k_diag<<<(np + 127) / 128, 128, 0, s>>>(np, G, gdiag);
+  return cudaGetLastError();
+}
+
+}  // namespace cfs

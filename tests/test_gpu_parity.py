@@ -1,0 +1,173 @@
+"""-m gpu : the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs.
+
+Tolerances (BASELINE.json north_star): trajectories within 1e-6 rad, costs within 1e-6 relative, collision-distance
+signs / link ids / iteration counts / status identical.
+"""
+import numpy as np
+import pytest
+
+import motionplanning_5d_m_b200 as M
+from motionplanning_5d_m_b200 import _lib
+from tests import common
+
+pytestmark = pytest.mark.gpu
+
+
+def _set(ctx, ROBOT, robot, obs, s=None, bounds=True):
+    r = dict(robot)
+    r["name"] = ROBOT
+    ctx.set_robot(r, len(s["lim"]) if s is not None else (2 if ROBOT == "2L" else 5))
+    ctx.set_obstacles(obs)
+    if s is not None:
+        ctx.set_cost(s["H"], s["QQ"], s.get("lim"), s["MAX_input"] if bounds else None)
+
+
+@pytest.mark.parametrize("ROBOT", ["M16iB", "M200i"])
+def test_dist_and_numjac_parity(ctx, oracle, ROBOT):
+    O = oracle
+    rng = np.random.default_rng(7)
+    robot = M.robotproperty2(ROBOT)
+    obs = [{"l": np.array([[3.906, 3.906], [8.313, 8.313], [0.001, 1.938]]), "D": 0.2, "epsilon": 0.2},
+           {"l": np.array([[3.406, 3.406], [7.813, 7.813], [0.800, 1.538]]), "D": 0.2, "epsilon": 0.2},
+           {"l": np.array([[3.7, 3.1], [8.9, 8.2], [0.2, 0.9]]), "D": 0.1, "epsilon": 0.3}]
+    _set(ctx, ROBOT, robot, obs)
+    th = common.sampling_box(rng, 1500)
+    dist, lid, g, flags = ctx.dist_grad(th)
+    r = O.robot(ROBOT)
+    for j, o in enumerate(obs):
+        o6 = O.obs6(o["l"])
+        ref = [O.dist_arm(r, t, o6) for t in th]
+        dref = np.array([x[0] for x in ref])
+        lref = np.array([x[1] for x in ref])
+        gref = np.array([O.num_jac(r, t, o6) for t in th])
+        assert np.abs(dist[:, j] - dref).max() < 1e-12
+        assert (np.sign(dist[:, j]) == np.sign(dref)).all()
+        assert (lid[:, j] == lref).all()
+        assert np.abs(g[:, j] - gref).max() < 1e-8  # (1e-16 noise in f)/eps=1e-5 -> 1e-11 expected
+
+
+def test_touch_branch_parity(ctx, oracle):
+    """Configurations whose link axis passes within 1e-4 of the obstacle axis take the negative branch."""
+    O = oracle
+    ROBOT, robot, obs, s = common.main_fanuc_config()
+    _set(ctx, ROBOT, robot, obs)
+    x0 = np.array([0.7825, 0.0284, 0.2172, 0.1444, -1.1779])
+    xg = np.array([-0.7825, 0.0284, 0.2172, 0.1444, -1.1779])
+    th = np.stack([x0 + (xg - x0) * k / 30 for k in range(1, 31)])
+    dist, lid, g, flags = ctx.dist_grad(th)
+    r = O.robot(ROBOT)
+    o6 = O.obs6(obs[0]["l"])
+    ref = [O.dist_arm(r, t, o6) for t in th]
+    dref = np.array([x[0] for x in ref])
+    assert (dref < 0).any(), "fixture must exercise the negative branch (waypoint 18 of main_FANUC.m)"
+    assert np.abs(dist[:, 0] - dref).max() < 1e-12
+    assert ((flags & _lib.FLAG_TOUCH) != 0).sum() >= 1
+    assert (np.sign(dist[:, 0]) == np.sign(dref)).all()
+
+
+def test_derivest_gradient_parity(ctx, oracle):
+    O = oracle
+    rng = np.random.default_rng(11)
+    robot = M.robotproperty2("M16iB")
+    obs = [{"l": np.array([[3.906, 3.906], [8.313, 8.313], [0.001, 1.938]]), "D": 0.2, "epsilon": 0.2}]
+    _set(ctx, "M16iB", robot, obs)
+    th = common.sampling_box(rng, 300)
+    dist, lid, g, flags = ctx.dist_grad(th, grad=_lib.GRAD_DERIVEST)
+    r = O.robot("M16iB")
+    o6 = O.obs6(obs[0]["l"])
+    for k in range(th.shape[0]):
+        d, l, _ = O.dist_arm(r, th[k], o6)
+        gref = O.derivest_grad(r, th[k], o6, l)
+        assert abs(dist[k, 0] - d) < 1e-12 and lid[k, 0] == l
+        assert np.abs(g[k, 0] - gref).max() < 1e-7 * max(1.0, np.abs(gref).max()), (k, g[k, 0], gref)
+
+
+def test_get_con_parity(ctx, oracle):
+    O = oracle
+    ROBOT, robot, obs, s = common.main_fanuc_config()
+    _set(ctx, ROBOT, robot, obs, s)
+    P = common.oracle_problem(O, ROBOT, obs, s)
+    rng = np.random.default_rng(3)
+    u = rng.normal(size=s["H"] * 5) * 0.05
+    A, b = ctx.get_con(s["xR"][:, 0], s["x_"], u)
+    Ar, br, *_ = P.get_con(s["xR"][:, 0], s["x_"], u)
+    assert A.shape == Ar.shape
+    assert np.abs(A - Ar).max() < 1e-8
+    assert np.abs(b - br).max() < 1e-8
+
+
+def _compare_solve(out, ref, tol_x=1e-6, tol_c=1e-6):
+    st_g, st_r = out["status"], ref["status"]
+    assert (st_g == st_r).all(), (np.where(st_g != st_r)[0][:10], st_g[st_g != st_r][:10], st_r[st_g != st_r][:10])
+    assert (out["iters"] == ref["iters"]).all()
+    ok = (st_r & 0xFF) < 2
+    dx = np.abs(out["x"][ok] - ref["x"][ok]).max() if ok.any() else 0.0
+    du = np.abs(out["u"][ok] - ref["u"][ok]).max() if ok.any() else 0.0
+    assert dx < tol_x and du < tol_x, (dx, du)
+    for b in np.where(ok)[0]:
+        it = ref["iters"][b]
+        cg, cr = out["cost_hist"][b, :it], ref["cost_hist"][b, :it]
+        assert np.all(np.abs(cg - cr) <= tol_c * np.abs(cr)), (b, cg, cr)
+        assert np.isnan(out["cost_hist"][b, it:]).all()
+        eg, er = out["e_u_hist"][b, :it], ref["e_u_hist"][b, :it]
+        assert np.abs(eg - er).max() < 1e-6 if it else True
+    return dx, du
+
+
+def test_main_fanuc_solve_parity(ctx, oracle):
+    O = oracle
+    ROBOT, robot, obs, s = common.main_fanuc_config()
+    _set(ctx, ROBOT, robot, obs, s)
+    P = common.oracle_problem(O, ROBOT, obs, s)
+    args = (s["xR"][:, 0][None], s["ff"][None], np.array([s["caug"]]), s["x_"][None])
+    ref = P.solve_batch(*args)
+    out = ctx.solve_batch(*args, s["epsilon_O"], s["MAX_O_ITER"])
+    assert ref["iters"][0] == 10 and abs(ref["cost_hist"][0, 9] - 122532.09) < 0.01  # frozen oracle golden
+    _compare_solve(out, ref)
+    assert out["status"][0] == (_lib.STATUS_CONVERGED | _lib.FLAG_TOUCH)
+
+
+def test_main_2l_solve_parity(ctx, oracle):
+    O = oracle
+    ROBOT, robot, obs, s = common.main_2l_config()
+    _set(ctx, ROBOT, robot, obs, s)
+    P = common.oracle_problem(O, ROBOT, obs, s)
+    args = (s["xR"][:, 0][None], s["ff"][None], np.array([s["caug"]]), s["x_"][None])
+    ref = P.solve_batch(*args)
+    out = ctx.solve_batch(*args, s["epsilon_O"], s["MAX_O_ITER"])
+    _compare_solve(out, ref)
+
+
+def test_batch_m16ib_solve_parity(ctx, oracle):
+    """Seeded random start/goal batch at the headline configuration (H=50), including infeasible problems."""
+    O = oracle
+    cfg = common.batch_m16ib(O, 192)
+    s = cfg["sys_info"]
+    _set(ctx, "M16iB", cfg["robot"], cfg["obs"], s)
+    P = common.oracle_problem(O, "M16iB", cfg["obs"], s)
+    ref = P.solve_batch(cfg["x0"], cfg["ff"], cfg["caug"], cfg["xref"], nthreads=8)
+    out = ctx.solve_batch(cfg["x0"], cfg["ff"], cfg["caug"], cfg["xref"], s["epsilon_O"], s["MAX_O_ITER"])
+    assert ((ref["status"] & 0xFF) == 2).any() and ((ref["status"] & 0xFF) == 0).any()
+    _compare_solve(out, ref)
+
+
+def test_nodes_feasible_and_nearest(ctx, oracle):
+    O = oracle
+    rng = np.random.default_rng(5)
+    ROBOT, robot, obs, s = common.rrtstar_cfs_config(np.zeros((5, 41)))
+    _set(ctx, ROBOT, robot, obs)
+    th = (rng.random((2000, 5)) - 0.5) * 2 * np.array([np.pi / 2, np.pi / 2, np.pi / 2, np.pi / 1.5, np.pi / 1.5])
+    feas, dmin = ctx.nodes_feasible(th)
+    r = O.robot(ROBOT)
+    ref = [O.rrt_feasible(r, t, [o["l"] for o in obs], [o["D"] for o in obs]) for t in th]
+    assert (feas == np.array([x[0] for x in ref])).all()
+    assert np.abs(dmin - np.array([x[1] for x in ref])).max() < 1e-12
+    nodes = th[:401]
+    samples = th[500:700]
+    ratial = np.array([1, 1, 0.5, 0.1, 0.1])
+    parent, new = ctx.nearest_steer(nodes, samples, ratial, 0.1)
+    for k in range(samples.shape[0]):
+        p, d = O.rrt_nearest(nodes, samples[k], ratial)
+        assert parent[k] == p
+        ref_new = nodes[p] + (samples[k] - nodes[p]) * 0.1 / np.linalg.norm(nodes[p] - samples[k])
+        assert np.abs(new[k] - ref_new).max() < 1e-14
