@@ -127,6 +127,13 @@ typedef struct {
 int cfs_get_stats(const cfs_ctx *ctx, cfs_stats *out);
 /* level 1 (default): whole-solve time only; level 2: per-kernel CUDA events (ms_grad / ms_qp) */
 int cfs_set_timing(cfs_ctx *ctx, int level);
+/* per-outer-iteration kernel times of the last level-2 solve: grad_ms[k], qp_ms[k], k < min(cap, max_outer); returns count */
+int cfs_get_iter_times(const cfs_ctx *ctx, double *grad_ms, double *qp_ms, int cap);
+/* dual active-set steps spent on each problem of the last solve (sum over outer iterations), steps[B] */
+int cfs_get_problem_steps(cfs_ctx *ctx, int *steps, int B);
+/* timing level 3: clock64 phase profile of the QP kernel (thread 0 of every CTA, summed): out8 = {prologue, primal
+ * refresh, violation scan, gram+solve+step length, working-set update, epilogue} ticks, problems, outer steps */
+int cfs_get_qp_profile(cfs_ctx *ctx, long long *out8);
 /* FP64 FMA micro-benchmark (roofline denominator: MEASURED_PEAKS.json has no FP64 entry). Returns TFLOP/s. */
 int cfs_measure_fp64_peak(cfs_ctx *ctx, double *tflops, double *sm_clock_mhz_est);
 

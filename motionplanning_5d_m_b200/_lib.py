@@ -20,7 +20,7 @@ FLAG_TOUCH = 0x100
 # every symbol include/cfs_b200.h declares (tests check that the library exports all of them)
 SYMBOLS = ["cfs_create", "cfs_destroy", "cfs_last_error", "cfs_version", "cfs_set_stream", "cfs_set_robot", "cfs_set_obstacles",
            "cfs_set_cost", "cfs_solve_batch", "cfs_solve_batch_device", "cfs_dist_grad", "cfs_get_con",
-           "cfs_nodes_feasible", "cfs_nearest_steer", "cfs_get_stats", "cfs_set_timing", "cfs_measure_fp64_peak"]
+           "cfs_nodes_feasible", "cfs_nearest_steer", "cfs_get_stats", "cfs_set_timing", "cfs_get_iter_times", "cfs_get_problem_steps", "cfs_get_qp_profile", "cfs_measure_fp64_peak"]
 
 
 class CfsError(RuntimeError):
@@ -220,6 +220,22 @@ class Context:
 
     def set_timing(self, level):
         self._check(self._lib.cfs_set_timing(self._h, C.c_int(level)), "cfs_set_timing")
+
+    def iter_times(self, cap=256):
+        g = np.zeros(cap)
+        q = np.zeros(cap)
+        cnt = self._lib.cfs_get_iter_times(self._h, _dp(g), _dp(q), C.c_int(cap))
+        return g[:max(cnt, 0)], q[:max(cnt, 0)]
+
+    def problem_steps(self, B):
+        st = np.zeros(B, dtype=np.int32)
+        self._check(self._lib.cfs_get_problem_steps(self._h, _dp(st), C.c_int(B)), "cfs_get_problem_steps")
+        return st
+
+    def qp_profile(self):
+        o = np.zeros(8, dtype=np.int64)
+        self._check(self._lib.cfs_get_qp_profile(self._h, _dp(o)), "cfs_get_qp_profile")
+        return o
 
     def measure_fp64_peak(self):
         tf, mhz = C.c_double(), C.c_double()

@@ -48,12 +48,13 @@ struct cfs_ctx {
   bool have_GI = false;
   // batch buffers
   DevBuf x0, ff, caug, xref, noise, u, x, cost, eu, u0, v0, cost0, dist, grad, lid, iters, status, flags, listA, listB,
-      counters, slab, scratch_theta, scratch_out, qpsteps, fupper;
+      counters, slab, scratch_theta, scratch_out, qpsteps, fupper, probsteps;
   int slab_grid = 0, slab_ld = 0;
   // timing
   std::vector<cudaEvent_t> ev;
   cudaEvent_t ev_a = nullptr, ev_b = nullptr;
   int timing_level = 1;
+  std::vector<double> it_grad_ms, it_qp_ms;
   cfs_stats stats;
 };
 
@@ -196,7 +197,7 @@ extern "C" void cfs_destroy(cfs_ctx *ctx) {
   DevBuf *bufs[] = {&ctx->x0, &ctx->ff, &ctx->caug, &ctx->xref, &ctx->noise, &ctx->u, &ctx->x, &ctx->cost, &ctx->eu,
                     &ctx->u0, &ctx->v0, &ctx->cost0, &ctx->dist, &ctx->grad, &ctx->lid, &ctx->iters, &ctx->status,
                     &ctx->flags, &ctx->listA, &ctx->listB, &ctx->counters, &ctx->slab, &ctx->scratch_theta,
-                    &ctx->scratch_out, &ctx->qpsteps, &ctx->fupper};
+                    &ctx->scratch_out, &ctx->qpsteps, &ctx->fupper, &ctx->probsteps};
   for (DevBuf *b : bufs) free_buf(*b);
   double *ds[] = {ctx->dQQ, ctx->dG, ctx->dgn, ctx->dGI, ctx->dgnI, ctx->dlim, ctx->dumax, ctx->dworkL, ctx->dworkY};
   for (double *d : ds)
@@ -368,13 +369,14 @@ static int solve_device(cfs_ctx *ctx, int B, int solver, int grad, const double 
   if ((rc = ensure(ctx, ctx->v0, sizeof(double) * (size_t)np * B))) return rc;
   if ((rc = ensure(ctx, ctx->cost0, sizeof(double) * B))) return rc;
   if ((rc = ensure(ctx, ctx->fupper, sizeof(double) * B))) return rc;
+  if ((rc = ensure(ctx, ctx->probsteps, sizeof(int) * B))) return rc;
   if ((rc = ensure(ctx, ctx->dist, sizeof(double) * (size_t)(OH > 0 ? OH : 1) * B))) return rc;
   if ((rc = ensure(ctx, ctx->grad, sizeof(double) * (size_t)(OH > 0 ? OH : 1) * nj * B))) return rc;
   if ((rc = ensure(ctx, ctx->flags, sizeof(int) * B))) return rc;
   if ((rc = ensure(ctx, ctx->listA, sizeof(int) * B))) return rc;
   if ((rc = ensure(ctx, ctx->listB, sizeof(int) * B))) return rc;
   if ((rc = ensure(ctx, ctx->counters, sizeof(int) * 8))) return rc;
-  if ((rc = ensure(ctx, ctx->qpsteps, sizeof(long long) * 2))) return rc;
+  if ((rc = ensure(ctx, ctx->qpsteps, sizeof(long long) * 16))) return rc;
 
   SolveArgs a;
   memset(&a, 0, sizeof(a));
@@ -403,6 +405,8 @@ static int solve_device(cfs_ctx *ctx, int B, int solver, int grad, const double 
   int *cnt = ptr<int>(ctx->counters);  // [0]=count A, [1]=count B, [2]=work counter, [3]=max_active
   a.qp_steps = ptr<long long>(ctx->qpsteps);
   a.max_active = cnt + 3;
+  a.prob_steps = ptr<int>(ctx->probsteps);
+  a.prof = ctx->timing_level >= 3 ? ptr<long long>(ctx->qpsteps) + 8 : nullptr;
   a.slab_ld = n;
 
   int grid = qp_max_grid(a, ctx->device);
@@ -426,7 +430,8 @@ static int solve_device(cfs_ctx *ctx, int B, int solver, int grad, const double 
   int launches = 0;
   CU(cudaEventRecord(ctx->ev_a, st));
   CU(cudaMemsetAsync(cnt, 0, sizeof(int) * 8, st));
-  CU(cudaMemsetAsync(ctx->qpsteps.p, 0, sizeof(long long) * 2, st));
+  CU(cudaMemsetAsync(ctx->qpsteps.p, 0, sizeof(long long) * 16, st));
+  CU(cudaMemsetAsync(ctx->probsteps.p, 0, sizeof(int) * B, st));
   a.list_cur = ptr<int>(ctx->listA); a.count_cur = cnt + 0;
   a.list_next = ptr<int>(ctx->listB); a.count_next = cnt + 1;
   a.work_counter = cnt + 2;
@@ -489,6 +494,8 @@ static int collect_stats(cfs_ctx *ctx, int B, int max_outer, const int *d_iters,
   ctx->stats.problem_iters = pit;
   ctx->stats.grad_waypoints = gev * ctx->H * ctx->nobs;
   ctx->stats.ms_grad = ctx->stats.ms_qp = 0;
+  ctx->it_grad_ms.clear();
+  ctx->it_qp_ms.clear();
   if (ctx->timing_level >= 2) {
     for (int k = 0; k < max_outer; ++k) {
       float a = 0, b = 0;
@@ -496,6 +503,8 @@ static int collect_stats(cfs_ctx *ctx, int B, int max_outer, const int *d_iters,
       cudaEventElapsedTime(&b, ctx->ev[3 * k + 1], ctx->ev[3 * k + 2]);
       ctx->stats.ms_grad += a;
       ctx->stats.ms_qp += b;
+      ctx->it_grad_ms.push_back(a);
+      ctx->it_qp_ms.push_back(b);
     }
   }
   return 0;
@@ -709,6 +718,35 @@ extern "C" int cfs_nearest_steer(cfs_ctx *ctx, int n_nodes, const double *nodes,
 extern "C" int cfs_get_stats(const cfs_ctx *ctx, cfs_stats *out) {
   if (!ctx || !out) return CFS_E_ARG;
   *out = ctx->stats;
+  return 0;
+}
+
+extern "C" int cfs_get_iter_times(const cfs_ctx *ctx, double *grad_ms, double *qp_ms, int cap) {
+  if (!ctx) return CFS_E_ARG;
+  int cnt = (int)ctx->it_grad_ms.size();
+  if (cnt > cap) cnt = cap;
+  for (int k = 0; k < cnt; ++k) {
+    if (grad_ms) grad_ms[k] = ctx->it_grad_ms[k];
+    if (qp_ms) qp_ms[k] = ctx->it_qp_ms[k];
+  }
+  return cnt;
+}
+
+extern "C" int cfs_get_qp_profile(cfs_ctx *ctx, long long *out8) {
+  if (!ctx || !out8) return CFS_E_ARG;
+  if (ctx->qpsteps.cap < sizeof(long long) * 16) return fail(ctx, CFS_E_STATE, "cfs_get_qp_profile: no solve yet");
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaMemcpyAsync(out8, ptr<long long>(ctx->qpsteps) + 8, sizeof(long long) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+extern "C" int cfs_get_problem_steps(cfs_ctx *ctx, int *steps, int B) {
+  if (!ctx || !steps || B < 0) return CFS_E_ARG;
+  if ((size_t)B * sizeof(int) > ctx->probsteps.cap) return fail(ctx, CFS_E_ARG, "cfs_get_problem_steps: B exceeds the last batch");
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaMemcpyAsync(steps, ctx->probsteps.p, sizeof(int) * B, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
   return 0;
 }
 

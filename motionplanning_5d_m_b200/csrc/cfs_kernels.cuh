@@ -77,6 +77,8 @@ struct SolveArgs {
   int outer_iter;             // 1-based iteration being executed
   long long *qp_steps;        // device counter
   int *max_active;            // device max
+  int *prob_steps;            // per-problem step counter (B)
+  long long *prof;            // optional 8-slot phase profile of k_qp (clock64 ticks of thread 0), or nullptr
 };
 cudaError_t launch_solve_init(const SolveArgs &a, cudaStream_t s);
 cudaError_t launch_v0(const SolveArgs &a, cudaStream_t s);

@@ -8,40 +8,59 @@
 //   Lib/EVAL.m:51-73          get_cost, store_result, stop_outer
 //
 // Design (B200-first, not a translation of quadprog):
-//   * one persistent CTA per SM slot pulls problems from a device work queue (no host round trip, no tail of idle SMs);
+//   * persistent CTAs pull problems from a device work queue (no host round trip, no tail of idle SMs);
 //   * the QP is solved by a dual active-set method (Goldfarb-Idnani) written entirely in "primitive space":
 //     v = P u (3n values: joint displacements B_theta u, joint velocities B_omega u, controls u) lives in shared
 //     memory; every constraint reads <= nj entries of v, and every metric inner product the method needs is a small
 //     bilinear form over the batch-shared Gram matrix G = P QQ^{-1} P' (k_setup.cu) held in L2.  No n x n
 //     per-problem factorisation, no dense Ainq (550 x 250 per problem in the reference) is ever formed;
 //   * the only per-problem matrix is the inverse of the working-set Gram matrix (q x q, q = #active rows, typically
-//     < 8), updated by rank-1 bordering on add / drop;
+//     < 8): in shared memory up to q = QP_QS, spilled to a per-CTA global slab beyond, rank-1 updated on add / drop;
+//   * the primal point is never stepped: at the top of every outer step v is re-evaluated from the multipliers,
+//     v = v0 - G (C_W' lambda), as one pass over the flat list of active (primitive row, weight) terms with many
+//     independent L2 loads in flight (small working sets: all 3n entries straight from G; large ones: the n control
+//     entries from G followed by the closed-form B_theta / B_omega sums).  The inner loop only needs scalars;
 //   * the optimal cost comes from duality: f(u) = f(u0) + 1/2 sum_w lambda_w * (violation of row w at u0).
 #include "cfs_kernels.cuh"
 
 namespace cfs {
 
 #define QP_THREADS 128
-#define QP_DEP_TOL 1e-8
 #define QP_WARPS (QP_THREADS / 32)
+#define QP_DEP_TOL 1e-8
+#define QP_QS 64          // working sets up to QP_QS keep their inverse in shared memory
+#define QP_SMALL_T 16     // term lists up to this length refresh all 3n primitives directly from G
 
 struct QpView {  // decoded shared-memory layout
   double *v;       // np
   double *ocoef;   // OH*nj   (-g)
   double *orhs;    // OH
   double *onrm;    // OH      sqrt(c QQ^-1 c')
-  double *lam;     // n+1
-  double *r;       // n+1
-  double *g;       // n+1
-  double *red;     // 4*QP_WARPS
-  int *act;        // n+1
-  int *ctl;        // 8 ints of control words
+  double *lam;     // n+2
+  double *r;       // n+2
+  double *g;       // n+2
+  double *red;     // 16
+  double *tcoef;   // TMAX    coefficient of each active term
+  double *twgt;    // TMAX    lambda_owner * coefficient
+  double *Msm;     // QP_QS*QP_QS
+  double *lim;     // 8: velocity limits
+  double *w0;      // 8: initial joint velocities
+  int *act;        // n+2
+  int *toff;       // n+3     first term of each working-set member
+  int *trow;       // TMAX    primitive row of each active term
+  int *towner;     // TMAX
+  int *ctl;        // 8
   unsigned char *inact;  // m
+  double *v0s;     // np      v at the unconstrained minimiser (per problem)
+  double *gns;     // 2n      QQ^-1 norms of the omega / control primitive rows (per kernel)
+  double *ums;     // n       MAX_input (per kernel)
 };
 
-__host__ __device__ inline size_t qp_smem_layout(int n, int nj, int OH, int m, size_t *off /*[11]*/) {
+#define QP_NOFF 22
+__host__ __device__ inline size_t qp_smem_layout(int n, int nj, int OH, int m, size_t *off /*[QP_NOFF]*/) {
   size_t o = 0;
   const int np = 3 * n;
+  const int tmax = nj * OH + n + 2;
   off[0] = o; o += sizeof(double) * np;
   off[1] = o; o += sizeof(double) * (size_t)OH * nj;
   off[2] = o; o += sizeof(double) * OH;
@@ -49,15 +68,26 @@ __host__ __device__ inline size_t qp_smem_layout(int n, int nj, int OH, int m, s
   off[4] = o; o += sizeof(double) * (n + 2);
   off[5] = o; o += sizeof(double) * (n + 2);
   off[6] = o; o += sizeof(double) * (n + 2);
-  off[7] = o; o += sizeof(double) * 4 * QP_WARPS;
-  off[8] = o; o += sizeof(int) * (n + 2);
-  off[9] = o; o += sizeof(int) * 8;
-  off[10] = o; o += (size_t)((m + 15) / 16) * 16;
+  off[7] = o; o += sizeof(double) * 16;
+  off[8] = o; o += sizeof(double) * tmax;
+  off[9] = o; o += sizeof(double) * tmax;
+  off[10] = o; o += sizeof(double) * QP_QS * QP_QS;
+  off[11] = o; o += sizeof(double) * 8;
+  off[12] = o; o += sizeof(double) * 8;
+  off[13] = o; o += sizeof(int) * (n + 2);
+  off[14] = o; o += sizeof(int) * (n + 4);
+  off[15] = o; o += sizeof(int) * tmax;
+  off[16] = o; o += sizeof(int) * tmax;
+  off[17] = o; o += sizeof(int) * 8;
+  off[18] = o; o += (size_t)((m + 15) / 16) * 16;
+  off[19] = o; o += sizeof(double) * np;
+  off[20] = o; o += sizeof(double) * 2 * n;
+  off[21] = o; o += sizeof(double) * n;
   return (o + 15) / 16 * 16;
 }
 
 size_t qp_smem_bytes(const SolveArgs &a) {
-  size_t off[11];
+  size_t off[QP_NOFF];
   const int OH = a.nobs * a.H;
   return qp_smem_layout(a.n, a.nj, OH, OH + 4 * a.n, off);
 }
@@ -92,6 +122,7 @@ __device__ __forceinline__ Desc decode(int cid, int OH, int H, int n, int nj, co
 }
 
 __device__ __forceinline__ double gram(const Desc &a, const Desc &b, const double *__restrict__ G, int np) {
+  if (a.nterm == 1 && b.nterm == 1) return a.coef * b.coef * G[(size_t)a.row0 * np + b.row0];
   double s = 0.0;
   for (int k = 0; k < a.nterm; ++k) {
     const double ca = a.cv ? a.cv[k] : a.coef;
@@ -103,22 +134,8 @@ __device__ __forceinline__ double gram(const Desc &a, const Desc &b, const doubl
   return s;
 }
 
-// (P QQ^-1 c_a')[pi]
-__device__ __forceinline__ double gcol(const Desc &a, int pi, const double *__restrict__ G, int np) {
-  if (a.nterm == 1) return a.coef * G[(size_t)a.row0 * np + pi];
-  double s = 0.0;
-  for (int k = 0; k < a.nterm; ++k) s += a.cv[k] * G[(size_t)(a.row0 + k) * np + pi];
-  return s;
-}
-
-struct Limits {
-  const double *lim, *umax;
-  double w0[CFS_MAXL];
-  int has_lim, has_bounds;
-};
-
 // slack = rhs - c u, evaluated from the primitive values v
-__device__ __forceinline__ double slack_of(int cid, int OH, int H, int n, int nj, const QpView &s, const Limits &L) {
+__device__ __forceinline__ double slack_of(int cid, int OH, int H, int n, int nj, const QpView &s, const double *umax) {
   if (cid < OH) {
     const int i = cid % H;
     const double *c = s.ocoef + (size_t)cid * nj;
@@ -132,18 +149,18 @@ __device__ __forceinline__ double slack_of(int cid, int OH, int H, int n, int nj
   if (e < 2 * n) {  // CFS_FANUC.m:126-129 : +-Baug_w u <= lim -+ Aaug_w x0
     const int k = idx % nj;
     const double vv = s.v[n + idx];
-    return neg ? (L.lim[k] + L.w0[k]) + vv : (L.lim[k] - L.w0[k]) - vv;
+    return neg ? (s.lim[k] + s.w0[k]) + vv : (s.lim[k] - s.w0[k]) - vv;
   }
   const int c = idx - n;
   const double vv = s.v[2 * n + c];
-  return neg ? L.umax[c] + vv : L.umax[c] - vv;
+  return neg ? umax[c] + vv : umax[c] - vv;
 }
 
-__device__ __forceinline__ double rhs_scale(int cid, int OH, int n, int nj, const QpView &s, const Limits &L) {
+__device__ __forceinline__ double rhs_scale(int cid, int OH, int n, int nj, const QpView &s, const double *umax) {
   if (cid < OH) return fabs(s.orhs[cid]);
   const int e = cid - OH, idx = e >> 1;
-  if (e < 2 * n) return L.lim[idx % nj];
-  return L.umax[idx - n];
+  if (e < 2 * n) return s.lim[idx % nj];
+  return umax[idx - n];
 }
 
 // ---- block reductions (QP_THREADS threads) --------------------------------------------------------------------
@@ -193,34 +210,55 @@ __device__ __forceinline__ double block_sum(double val, double *red) {
 // ============================================================================================================
 // The kernel
 // ============================================================================================================
-__global__ void __launch_bounds__(QP_THREADS) k_qp(SolveArgs a) {
+__global__ void __launch_bounds__(QP_THREADS, 3) k_qp(SolveArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int n = a.n, nj = a.nj, H = a.H, np = 3 * n, OH = a.nobs * H, m = OH + 4 * n;
   const int tid = threadIdx.x;
-  size_t off[11];
-  qp_smem_layout(n, nj, OH, m, off);
   QpView s;
-  s.v = reinterpret_cast<double *>(smem_raw + off[0]);
-  s.ocoef = reinterpret_cast<double *>(smem_raw + off[1]);
-  s.orhs = reinterpret_cast<double *>(smem_raw + off[2]);
-  s.onrm = reinterpret_cast<double *>(smem_raw + off[3]);
-  s.lam = reinterpret_cast<double *>(smem_raw + off[4]);
-  s.r = reinterpret_cast<double *>(smem_raw + off[5]);
-  s.g = reinterpret_cast<double *>(smem_raw + off[6]);
-  s.red = reinterpret_cast<double *>(smem_raw + off[7]);
-  s.act = reinterpret_cast<int *>(smem_raw + off[8]);
-  s.ctl = reinterpret_cast<int *>(smem_raw + off[9]);
-  s.inact = smem_raw + off[10];
-
+  {
+    size_t off[QP_NOFF];
+    qp_smem_layout(n, nj, OH, m, off);
+    s.v = reinterpret_cast<double *>(smem_raw + off[0]);
+    s.ocoef = reinterpret_cast<double *>(smem_raw + off[1]);
+    s.orhs = reinterpret_cast<double *>(smem_raw + off[2]);
+    s.onrm = reinterpret_cast<double *>(smem_raw + off[3]);
+    s.lam = reinterpret_cast<double *>(smem_raw + off[4]);
+    s.r = reinterpret_cast<double *>(smem_raw + off[5]);
+    s.g = reinterpret_cast<double *>(smem_raw + off[6]);
+    s.red = reinterpret_cast<double *>(smem_raw + off[7]);
+    s.tcoef = reinterpret_cast<double *>(smem_raw + off[8]);
+    s.twgt = reinterpret_cast<double *>(smem_raw + off[9]);
+    s.Msm = reinterpret_cast<double *>(smem_raw + off[10]);
+    s.lim = reinterpret_cast<double *>(smem_raw + off[11]);
+    s.w0 = reinterpret_cast<double *>(smem_raw + off[12]);
+    s.act = reinterpret_cast<int *>(smem_raw + off[13]);
+    s.toff = reinterpret_cast<int *>(smem_raw + off[14]);
+    s.trow = reinterpret_cast<int *>(smem_raw + off[15]);
+    s.towner = reinterpret_cast<int *>(smem_raw + off[16]);
+    s.ctl = reinterpret_cast<int *>(smem_raw + off[17]);
+    s.inact = smem_raw + off[18];
+    s.v0s = reinterpret_cast<double *>(smem_raw + off[19]);
+    s.gns = reinterpret_cast<double *>(smem_raw + off[20]);
+    s.ums = reinterpret_cast<double *>(smem_raw + off[21]);
+  }
   const double *__restrict__ G = a.G;
   const double *__restrict__ gnorm = a.gdiag;  // sqrt(diag(G))
-  const double dt = a.tab->dt;
-  const int ld = a.slab_ld;
-  double *Minv = a.slab + (size_t)blockIdx.x * ld * ld;  // working-set inverse, column-major
-  const int count = *a.count_cur;
   const int has_vel = a.has_lim, has_bnd = a.has_bounds;
+  for (int e = tid; e < 2 * n; e += QP_THREADS) s.gns[e] = gnorm[n + e];
+  for (int e = tid; e < n; e += QP_THREADS) s.ums[e] = has_bnd ? a.max_input[e] : 0.0;
+  const double *umax = s.ums;
+  const double dt = a.tab->dt;
+  const int ldg = a.slab_ld;
+  double *Mgl = a.slab + (size_t)blockIdx.x * ldg * ldg;  // spill area of the working-set inverse
+  const int count = *a.count_cur;
   long long steps_total = 0;
   int qmax_seen = 0;
+  // optional phase profile (thread 0 clocks): 0 prologue, 1 refresh, 2 scan, 3 gram+solve+steplen, 4 update, 5 epilogue,
+  // 6 problems, 7 outer steps
+  long long pf[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  long long tck = 0;
+#define PF_START() do { if (a.prof && tid == 0) tck = clock64(); } while (0)
+#define PF_ADD(k) do { if (a.prof && tid == 0) { const long long now_ = clock64(); pf[k] += now_ - tck; tck = now_; } } while (0)
 
   for (;;) {
     __syncthreads();
@@ -234,23 +272,23 @@ __global__ void __launch_bounds__(QP_THREADS) k_qp(SolveArgs a) {
     double *xb = a.x + (size_t)b * 2 * n;
     const double *v0 = a.v0 + (size_t)b * np;
 
-    Limits L;
-    L.lim = a.lim;
-    L.umax = a.max_input;
-    L.has_lim = has_vel;
-    L.has_bounds = has_bnd;
-#pragma unroll
-    for (int k = 0; k < CFS_MAXL; ++k) L.w0[k] = (k < nj) ? x0[nj + k] : 0.0;
-
     // ---- prologue: v = v0; disp = B_theta u_cur; obstacle rows ------------------------------------------------
-    for (int pi = tid; pi < np; pi += QP_THREADS) s.v[pi] = v0[pi];
+    PF_START();
+    for (int pi = tid; pi < np; pi += QP_THREADS) {
+      const double t_ = v0[pi];
+      s.v0s[pi] = t_;
+      s.v[pi] = t_;
+    }
     for (int e = tid; e < m; e += QP_THREADS) s.inact[e] = 0;
-    // disp(i,k) = sum_{j<=i} (0.5 dt^2 + (i-j) dt dt) u(j,k)   ( = Bj(1:njoint,:)*u of CFS_FANUC.m:120 ) -> s.g
+    if (tid < 8) {
+      s.lim[tid] = (tid < nj && has_vel) ? a.lim[tid] : 0.0;
+      s.w0[tid] = (tid < nj) ? x0[nj + tid] : 0.0;
+    }
+    // disp(i,k) = (Bj(1:njoint,:)*u)(k) of CFS_FANUC.m:120 -> s.g.  In the first outer iteration u = 0 (CFS_FANUC.m:56)
+    // while x_ is the reference line; afterwards x_ is the roll-out of u, so B_theta u = theta_i - (theta_0 + i dt w_0).
     for (int e = tid; e < n; e += QP_THREADS) {
       const int i = e / nj, k = e % nj;
-      double acc = 0.0;
-      for (int j = 0; j <= i; ++j) acc += (0.5 * dt * dt + ((i - j) * dt) * dt) * ub[j * nj + k];
-      s.g[e] = acc;
+      s.g[e] = (a.outer_iter == 1) ? 0.0 : xb[(size_t)i * 2 * nj + k] - (x0[k] + ((i + 1) * dt) * x0[nj + k]);
     }
     __syncthreads();
     for (int cid = tid; cid < OH; cid += QP_THREADS) {
@@ -271,28 +309,94 @@ __global__ void __launch_bounds__(QP_THREADS) k_qp(SolveArgs a) {
       const double sg = gram(d, d, G, np);
       s.onrm[cid] = sg > 0.0 ? sqrt(sg) : 0.0;
     }
+    if (tid == 0) s.toff[0] = 0;
     __syncthreads();
+    PF_ADD(0);
+    pf[6] += 1;
 
     // ---- dual active-set iterations --------------------------------------------------------------------------
     int q = 0, status = -1, steps = 0;
+    bool in_smem = true;
     double fval = a.cost0[b];
     const double fupper = (has_bnd && a.fupper) ? a.fupper[b] : INFINITY;
     const int max_steps = 20 * (m + n) + 100;
+#define MAT(r_, c_) (in_smem ? s.Msm[(r_) + QP_QS * (c_)] : Mgl[(r_) + (size_t)ldg * (c_)])
     while (status < 0) {
+      // (0) primal recovery from the multipliers: v = v0 - G (C_W' lambda)
+      if (q > 0) {
+        const int T = s.toff[q];
+        for (int t = tid; t < T; t += QP_THREADS) s.twgt[t] = s.lam[s.towner[t]] * s.tcoef[t];
+        __syncthreads();
+        if (T <= QP_SMALL_T) {
+          for (int base = 0; base < np; base += 6 * QP_THREADS) {  // 6 primitives per thread, 2 terms per pass: 12 loads in flight
+            double acc[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+            int t = 0;
+            for (; t + 2 <= T; t += 2) {
+              const double w0_ = s.twgt[t], w1_ = s.twgt[t + 1];
+              const double *g0 = G + (size_t)s.trow[t] * np + base + tid, *g1 = G + (size_t)s.trow[t + 1] * np + base + tid;
+              double l0[6], l1[6];
+#pragma unroll
+              for (int j = 0; j < 6; ++j) {
+                const bool ok = base + tid + j * QP_THREADS < np;
+                l0[j] = ok ? g0[j * QP_THREADS] : 0.0;
+                l1[j] = ok ? g1[j * QP_THREADS] : 0.0;
+              }
+#pragma unroll
+              for (int j = 0; j < 6; ++j) acc[j] += w0_ * l0[j] + w1_ * l1[j];
+            }
+            if (t < T) {
+              const double w0_ = s.twgt[t];
+              const double *g0 = G + (size_t)s.trow[t] * np + base + tid;
+#pragma unroll
+              for (int j = 0; j < 6; ++j)
+                if (base + tid + j * QP_THREADS < np) acc[j] += w0_ * g0[j * QP_THREADS];
+            }
+#pragma unroll
+            for (int j = 0; j < 6; ++j) {
+              const int pi = base + tid + j * QP_THREADS;
+              if (pi < np) s.v[pi] = s.v0s[pi] - acc[j];
+            }
+          }
+        } else {
+          const double *__restrict__ Gu = G + 2 * n;  // control block of every primitive row
+          for (int c = tid; c < n; c += QP_THREADS) {
+            double acc8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            int t = 0;
+            for (; t + 8 <= T; t += 8) {
+              double ld8[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) ld8[j] = Gu[(size_t)s.trow[t + j] * np + c];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) acc8[j] += s.twgt[t + j] * ld8[j];
+            }
+            for (; t < T; ++t) acc8[0] += s.twgt[t] * Gu[(size_t)s.trow[t] * np + c];
+            s.v[2 * n + c] = s.v0s[2 * n + c] - (((acc8[0] + acc8[1]) + (acc8[2] + acc8[3])) + ((acc8[4] + acc8[5]) + (acc8[6] + acc8[7])));
+          }
+          __syncthreads();
+          for (int e = tid; e < n; e += QP_THREADS) {  // B_theta u and B_omega u in closed form
+            const int i = e / nj, k = e % nj;
+            double at = 0.0, aw = 0.0;
+            for (int j = 0; j <= i; ++j) {
+              const double uj = s.v[2 * n + j * nj + k];
+              at += (0.5 * dt * dt + ((i - j) * dt) * dt) * uj;
+              aw += dt * uj;
+            }
+            s.v[e] = at;
+            s.v[n + e] = aw;
+          }
+        }
+        __syncthreads();
+      }
+      PF_ADD(1);
+      pf[7] += 1;
       // (1) most violated inactive row, normalised by its QQ^-1 norm
       double best = 0.0;
       int bidx = -1;
-      for (int cid = tid; cid < m; cid += QP_THREADS) {
-        if (cid >= OH) {
-          const int e = cid - OH;
-          if (e < 2 * n ? !has_vel : !has_bnd) continue;
-        }
-        if (s.inact[cid]) continue;
-        const double nr = cid < OH ? s.onrm[cid] : gnorm[n + ((cid - OH) >> 1)];
-        if (!(nr > 0.0)) continue;
-        const double sl = slack_of(cid, OH, H, n, nj, s, L);
-        const double tol = 1e-11 * (1.0 + rhs_scale(cid, OH, n, nj, s, L));
-        if (sl < -tol) {
+      for (int cid = tid; cid < OH; cid += QP_THREADS) {
+        const double nr = s.onrm[cid];
+        if (s.inact[cid] || !(nr > 0.0)) continue;
+        const double sl = slack_of(cid, OH, H, n, nj, s, umax);
+        if (sl < -1e-11 * (1.0 + fabs(s.orhs[cid]))) {
           const double val = sl / nr;
           if (val < best || bidx < 0) {
             best = val;
@@ -300,13 +404,51 @@ __global__ void __launch_bounds__(QP_THREADS) k_qp(SolveArgs a) {
           }
         }
       }
+      // omega / control primitives: both signs of a row share its value and its norm
+      for (int e = tid; e < 2 * n; e += QP_THREADS) {
+        const bool is_w = e < n;
+        if (is_w ? !has_vel : !has_bnd) continue;
+        const double nr = s.gns[e];
+        if (!(nr > 0.0)) continue;
+        const double vv = s.v[n + e];
+        double up, lo, sc;
+        if (is_w) {
+          const int k = e % nj;
+          up = (s.lim[k] - s.w0[k]) - vv;
+          lo = (s.lim[k] + s.w0[k]) + vv;
+          sc = s.lim[k];
+        } else {
+          up = umax[e - n] - vv;
+          lo = umax[e - n] + vv;
+          sc = umax[e - n];
+        }
+        const double tol = 1e-11 * (1.0 + sc);
+        const int cu = OH + 2 * e;
+        if (up < -tol && !s.inact[cu]) {
+          const double val = up / nr;
+          if (val < best || bidx < 0) {
+            best = val;
+            bidx = cu;
+          }
+        }
+        if (lo < -tol && !s.inact[cu + 1]) {
+          const double val = lo / nr;
+          if (val < best || bidx < 0) {
+            best = val;
+            bidx = cu + 1;
+          }
+        }
+      }
       block_argmin(best, bidx, s.red);
+      PF_ADD(2);
       if (bidx < 0) {
         status = 0;
         break;
       }
       const int p = bidx;
       const Desc dp = decode(p, OH, H, n, nj, s.ocoef);
+      const double sigma = gram(dp, dp, G, np);
+      double sp = slack_of(p, OH, H, n, nj, s, umax);
       double lam_p = 0.0;
       // (2) bring row p into the working set
       for (;;) {
@@ -316,13 +458,21 @@ __global__ void __launch_bounds__(QP_THREADS) k_qp(SolveArgs a) {
         }
         // g_w = c_w QQ^-1 c_p'
         for (int w = tid; w < q; w += QP_THREADS) s.g[w] = gram(decode(s.act[w], OH, H, n, nj, s.ocoef), dp, G, np);
-        const double sigma = gram(dp, dp, G, np);
         __syncthreads();
         // r = Minv g
         double part = 0.0;
         for (int w = tid; w < q; w += QP_THREADS) {
-          double acc = 0.0;
-          for (int c = 0; c < q; ++c) acc += Minv[w + (size_t)ld * c] * s.g[c];
+          double acc8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+          int c = 0;
+          for (; c + 8 <= q; c += 8) {
+            double ld8[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) ld8[j] = MAT(w, c + j);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc8[j] += ld8[j] * s.g[c + j];
+          }
+          for (; c < q; ++c) acc8[0] += MAT(w, c) * s.g[c];
+          const double acc = ((acc8[0] + acc8[1]) + (acc8[2] + acc8[3])) + ((acc8[4] + acc8[5]) + (acc8[6] + acc8[7]));
           s.r[w] = acc;
           part += s.g[w] * acc;
         }
@@ -347,8 +497,7 @@ __global__ void __launch_bounds__(QP_THREADS) k_qp(SolveArgs a) {
         // Row p is treated as linearly dependent on the working set when its QQ^-1-orthogonal remainder is below
         // 1e-8 of its norm^2: in Gram form delta carries cancellation noise ~eps*cond(S_W)*sigma, and a step of
         // length -sp/delta along such a direction only manufactures astronomically large multipliers.
-        const bool dependent = !(delta > QP_DEP_TOL * sigma);
-        const double sp = slack_of(p, OH, H, n, nj, s, L);
+        const bool dependent = !(delta > QP_DEP_TOL * sigma) || q >= n;
         double t2 = INFINITY;
         if (!dependent) {
           t2 = -sp / delta;
@@ -362,74 +511,127 @@ __global__ void __launch_bounds__(QP_THREADS) k_qp(SolveArgs a) {
         const double t = full ? t2 : t1;
         // dual objective (Goldfarb-Idnani: f += t z'n+ (t/2 + u+_{q+1})); weak duality: if it exceeds an upper bound of
         // the primal objective over the box |u| <= MAX_input the QP has no feasible point.
-        if (!dependent) fval += t * delta * (0.5 * t + lam_p);
+        if (!dependent) {
+          fval += t * delta * (0.5 * t + lam_p);
+          sp += t * delta;  // slack of p moves by t z'n+
+        }
         if (fval > fupper) {
           status = 2;
           break;
         }
-        // multipliers
         for (int w = tid; w < q; w += QP_THREADS) s.lam[w] -= t * s.r[w];
         lam_p += t;
-        // primal move in primitive space: v += -t * (G c_p' - sum_w r_w G c_w')
-        if (!dependent && t > 0.0) {
-          for (int pi = tid; pi < np; pi += QP_THREADS) {
-            double acc = gcol(dp, pi, G, np);
-            for (int w = 0; w < q; ++w) acc -= s.r[w] * gcol(decode(s.act[w], OH, H, n, nj, s.ocoef), pi, G, np);
-            s.v[pi] -= t * acc;
-          }
-        }
         __syncthreads();
+        PF_ADD(3);
         if (full) {
+          if (in_smem && q + 1 > QP_QS) {  // spill the inverse to the global slab
+            for (int e = tid; e < q * q; e += QP_THREADS) Mgl[(e % q) + (size_t)ldg * (e / q)] = s.Msm[(e % q) + QP_QS * (e / q)];
+            in_smem = false;
+            __syncthreads();
+          }
           // add p: bordered inverse  [[M + r r'/d, -r/d], [-r'/d, 1/d]]
           const double id = 1.0 / delta;
-          for (int e = tid; e < (q + 1) * (q + 1); e += QP_THREADS) {
-            const int r_ = e % (q + 1), c_ = e / (q + 1);
-            double val;
-            if (r_ < q && c_ < q)
-              val = Minv[r_ + (size_t)ld * c_] + s.r[r_] * s.r[c_] * id;
-            else if (r_ == q && c_ == q)
-              val = id;
-            else
-              val = -s.r[r_ < q ? r_ : c_] * id;
-            Minv[r_ + (size_t)ld * c_] = val;
+          {
+            const int q1 = q + 1, tot = q1 * q1;
+            for (int e0 = tid; e0 < tot; e0 += 4 * QP_THREADS) {
+              double old4[4];
+              int rr4[4], cc4[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const int e = e0 + j * QP_THREADS;
+                rr4[j] = e % q1;
+                cc4[j] = e / q1;
+                old4[j] = (e < tot && rr4[j] < q && cc4[j] < q) ? MAT(rr4[j], cc4[j]) : 0.0;
+              }
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const int e = e0 + j * QP_THREADS;
+                if (e >= tot) continue;
+                const int r_ = rr4[j], c_ = cc4[j];
+                double val;
+                if (r_ < q && c_ < q)
+                  val = old4[j] + s.r[r_] * s.r[c_] * id;
+                else if (r_ == q && c_ == q)
+                  val = id;
+                else
+                  val = -s.r[r_ < q ? r_ : c_] * id;
+                MAT(r_, c_) = val;
+              }
+            }
+          }
+          const int t0 = s.toff[q];
+          if (tid < dp.nterm) {
+            s.trow[t0 + tid] = dp.row0 + tid;
+            s.tcoef[t0 + tid] = dp.cv ? dp.cv[tid] : dp.coef;
+            s.towner[t0 + tid] = q;
           }
           if (tid == 0) {
             s.act[q] = p;
             s.lam[q] = lam_p;
             s.inact[p] = 1;
+            s.toff[q + 1] = t0 + dp.nterm;
           }
           ++q;
           if (q > qmax_seen) qmax_seen = q;
           __syncthreads();
+          PF_ADD(4);
           break;
         }
         // drop working-set member l: M <- M - M(:,l) M(l,:)/M(l,l), then move the last member into slot l
         {
           const int last = q - 1;
-          for (int w = tid; w < q; w += QP_THREADS) s.g[w] = Minv[w + (size_t)ld * l];
+          for (int w = tid; w < q; w += QP_THREADS) s.g[w] = MAT(w, l);
           __syncthreads();
           const double ip = 1.0 / s.g[l];
-          for (int e = tid; e < q * q; e += QP_THREADS) {
-            const int r_ = e % q, c_ = e / q;
-            Minv[r_ + (size_t)ld * c_] -= s.g[r_] * s.g[c_] * ip;
+          for (int e0 = tid; e0 < q * q; e0 += 4 * QP_THREADS) {
+            double old4[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int e = e0 + j * QP_THREADS;
+              old4[j] = e < q * q ? MAT(e % q, e / q) : 0.0;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int e = e0 + j * QP_THREADS;
+              if (e < q * q) MAT(e % q, e / q) = old4[j] - s.g[e % q] * s.g[e / q] * ip;
+            }
           }
           __syncthreads();
           if (l != last) {
-            for (int w = tid; w < q; w += QP_THREADS) Minv[w + (size_t)ld * l] = Minv[w + (size_t)ld * last];
+            for (int w = tid; w < q; w += QP_THREADS) MAT(w, l) = MAT(w, last);
             __syncthreads();
-            for (int w = tid; w < q; w += QP_THREADS) Minv[l + (size_t)ld * w] = Minv[last + (size_t)ld * w];
+            for (int w = tid; w < q; w += QP_THREADS) MAT(l, w) = MAT(last, w);
           }
           if (tid == 0) {
             s.inact[s.act[l]] = 0;
             s.act[l] = s.act[last];
             s.lam[l] = s.lam[last];
+            int o = 0;  // rebuild the term offsets (drops are rare)
+            for (int w = 0; w < last; ++w) {
+              s.toff[w] = o;
+              o += (s.act[w] < OH) ? nj : 1;
+            }
+            s.toff[last] = o;
           }
           --q;
           __syncthreads();
+          for (int w = tid; w < q; w += QP_THREADS) {
+            const Desc d = decode(s.act[w], OH, H, n, nj, s.ocoef);
+            const int t0 = s.toff[w];
+            for (int k = 0; k < d.nterm; ++k) {
+              s.trow[t0 + k] = d.row0 + k;
+              s.tcoef[t0 + k] = d.cv ? d.cv[k] : d.coef;
+              s.towner[t0 + k] = w;
+            }
+          }
+          __syncthreads();
+          PF_ADD(4);
         }
       }
     }
+#undef MAT
     steps_total += steps;
+    if (tid == 0 && a.prob_steps) a.prob_steps[b] += steps;
 
     // ---- epilogue ------------------------------------------------------------------------------------------------
     const int it = a.outer_iter;  // 1-based
@@ -451,22 +653,28 @@ __global__ void __launch_bounds__(QP_THREADS) k_qp(SolveArgs a) {
         if (cid < OH) {
           const int i = cid % H;
           double val = 0.0;
-          for (int k = 0; k < nj; ++k) val += s.ocoef[cid * nj + k] * v0[i * nj + k];
+          for (int k = 0; k < nj; ++k) val += s.ocoef[cid * nj + k] * s.v0s[i * nj + k];
           val0 = val - s.orhs[cid];
         } else {
           const int e = cid - OH, idx = e >> 1, neg = e & 1;
           if (e < 2 * n) {
             const int k = idx % nj;
-            val0 = neg ? -v0[n + idx] - (L.lim[k] + L.w0[k]) : v0[n + idx] - (L.lim[k] - L.w0[k]);
+            val0 = neg ? -s.v0s[n + idx] - (s.lim[k] + s.w0[k]) : s.v0s[n + idx] - (s.lim[k] - s.w0[k]);
           } else {
             const int c = idx - n;
-            val0 = neg ? -v0[2 * n + c] - L.umax[c] : v0[2 * n + c] - L.umax[c];
+            val0 = neg ? -s.v0s[2 * n + c] - umax[c] : s.v0s[2 * n + c] - umax[c];
           }
         }
         pc += s.lam[w] * val0;
       }
       const double cost = a.cost0[b] + 0.5 * block_sum(pc, s.red);
-      // roll-out (CFS_FANUC.m:90-94) by nj threads, accumulating ||x_new - x_old||^2 (EVAL.m:64)
+      // roll-out (CFS_FANUC.m:90-94): x_old is staged in shared memory (coalesced), nj threads run the recurrence
+      // xR(:,i) = A xR(:,i-1) + B u_i there, then the new trajectory is written back coalesced; ||x_new - x_old||^2
+      // (EVAL.m:64) is accumulated on the way.  xbuf aliases the term-weight scratch (tcoef|twgt), free by now.
+      double *xbuf = s.tcoef;
+      __syncthreads();
+      for (int e = tid; e < 2 * n; e += QP_THREADS) xbuf[e] = xb[e];
+      __syncthreads();
       double px = 0.0;
       if (tid < nj) {
         double th = x0[tid], om = x0[nj + tid];
@@ -476,13 +684,15 @@ __global__ void __launch_bounds__(QP_THREADS) k_qp(SolveArgs a) {
           const double omn = om + dt * uk;
           th = thn;
           om = omn;
-          double *xs = xb + (size_t)i * 2 * nj;
+          double *xs = xbuf + (size_t)i * 2 * nj;
           const double d1 = th - xs[tid], d2 = om - xs[nj + tid];
           px += d1 * d1 + d2 * d2;
           xs[tid] = th;
           xs[nj + tid] = om;
         }
       }
+      __syncthreads();
+      for (int e = tid; e < 2 * n; e += QP_THREADS) xb[e] = xbuf[e];
       const double dx = sqrt(block_sum(px, s.red));
       if (tid == 0) {
         a.cost_hist[(size_t)b * a.max_outer + (it - 1)] = cost;
@@ -499,7 +709,11 @@ __global__ void __launch_bounds__(QP_THREADS) k_qp(SolveArgs a) {
     } else if (tid == 0) {
       a.status[b] = status;  // 2 infeasible / 3 numerical: u, x keep the previous iterate
     }
+    PF_ADD(5);
   }
+  if (a.prof && tid == 0)
+    for (int k = 0; k < 8; ++k)
+      if (pf[k]) atomicAdd(reinterpret_cast<unsigned long long *>(a.prof + k), (unsigned long long)pf[k]);
   if (tid == 0) {
     if (steps_total) atomicAdd(reinterpret_cast<unsigned long long *>(a.qp_steps), (unsigned long long)steps_total);
     if (qmax_seen) atomicMax(a.max_active, qmax_seen);
