@@ -22,7 +22,7 @@ class Proto:
         self.Y = np.linalg.solve(L, self.P.T)      # n x 3n
         self.G = self.Y.T @ self.Y
         self.Hinv = self.G[2*n:, 2*n:]
-    def solve(self, ff, ocoef, orhs, lim, w0, umax, refine=True, robust=True, dep_tol=1e-12, verbose=False):
+    def solve(self, ff, ocoef, orhs, lim, w0, umax, refine=True, robust=True, dep_tol=1e-12, verbose=False, polish=0):
         n, H, nj = self.n, self.H, self.nj; G = self.G; Y = self.Y
         OH = len(orhs); m = OH + 4*n
         u0 = -self.Hinv @ ff; v = self.P @ u0
@@ -49,7 +49,15 @@ class Proto:
             sl = RHS - E @ v
             tol = 1e-11*(1+np.abs(RHS))
             viol = (sl < -tol); viol[act] = False
-            if not viol.any(): return 0, v[2*n:], steps, len(act), np.array(lam)
+            if not viol.any():
+                if polish and len(act):
+                    v0_ = self.P @ u0; EW = E[act]; lam = np.array(lam)
+                    bvec = EW @ v0_ - RHS[act]
+                    for _ in range(polish):
+                        Sl = EW @ (G @ (EW.T @ lam))
+                        lam = lam + M @ (bvec - Sl)
+                    v = v0_ - G @ (EW.T @ lam)
+                return 0, v[2*n:], steps, len(act), np.array(lam)
             val = np.where(viol, sl/nrm, 0.0); p = int(np.argmin(val)); ep = E[p]; lam_p = 0.0
             while True:
                 steps += 1

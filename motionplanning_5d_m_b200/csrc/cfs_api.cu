@@ -42,13 +42,14 @@ struct cfs_ctx {
   int H = 0, n = 0;
   bool has_lim = false, has_bounds = false;
   double qq_norm_inf = 0.0;
+  double *dQQraw = nullptr;  // QQ exactly as given (PSGCFS gradient); dQQ holds (QQ+QQ')/2
   double *dQQ = nullptr, *dG = nullptr, *dgn = nullptr, *dGI = nullptr, *dgnI = nullptr;
   double *dlim = nullptr, *dumax = nullptr, *dworkL = nullptr, *dworkY = nullptr;
   int *dinfo = nullptr;
   bool have_GI = false;
   // batch buffers
   DevBuf x0, ff, caug, xref, noise, u, x, cost, eu, u0, v0, cost0, dist, grad, lid, iters, status, flags, listA, listB,
-      counters, slab, scratch_theta, scratch_out, qpsteps, fupper, probsteps;
+      counters, slab, scratch_theta, scratch_out, qpsteps, fupper, probsteps, psg_w, psg_cost, psg_skip;
   int slab_grid = 0, slab_ld = 0;
   // timing
   std::vector<cudaEvent_t> ev;
@@ -197,9 +198,10 @@ extern "C" void cfs_destroy(cfs_ctx *ctx) {
   DevBuf *bufs[] = {&ctx->x0, &ctx->ff, &ctx->caug, &ctx->xref, &ctx->noise, &ctx->u, &ctx->x, &ctx->cost, &ctx->eu,
                     &ctx->u0, &ctx->v0, &ctx->cost0, &ctx->dist, &ctx->grad, &ctx->lid, &ctx->iters, &ctx->status,
                     &ctx->flags, &ctx->listA, &ctx->listB, &ctx->counters, &ctx->slab, &ctx->scratch_theta,
-                    &ctx->scratch_out, &ctx->qpsteps, &ctx->fupper, &ctx->probsteps};
+                    &ctx->scratch_out, &ctx->qpsteps, &ctx->fupper, &ctx->probsteps, &ctx->psg_w, &ctx->psg_cost,
+                    &ctx->psg_skip};
   for (DevBuf *b : bufs) free_buf(*b);
-  double *ds[] = {ctx->dQQ, ctx->dG, ctx->dgn, ctx->dGI, ctx->dgnI, ctx->dlim, ctx->dumax, ctx->dworkL, ctx->dworkY};
+  double *ds[] = {ctx->dQQraw, ctx->dQQ, ctx->dG, ctx->dgn, ctx->dGI, ctx->dgnI, ctx->dlim, ctx->dumax, ctx->dworkL, ctx->dworkY};
   for (double *d : ds)
     if (d) cudaFree(d);
   if (ctx->dtab) cudaFree(ctx->dtab);
@@ -292,13 +294,15 @@ extern "C" int cfs_set_cost(cfs_ctx *ctx, int H, const double *QQ, const double 
   if (H < 1 || !QQ) return fail(ctx, CFS_E_ARG, "cfs_set_cost: H=%d", H);
   CU(cudaSetDevice(ctx->device));
   const int nj = ctx->nj, n = H * nj, np = 3 * n;
-  double *ds[] = {ctx->dQQ, ctx->dG, ctx->dgn, ctx->dGI, ctx->dgnI, ctx->dlim, ctx->dumax, ctx->dworkL, ctx->dworkY};
+  double *ds[] = {ctx->dQQraw, ctx->dQQ, ctx->dG, ctx->dgn, ctx->dGI, ctx->dgnI, ctx->dlim, ctx->dumax, ctx->dworkL, ctx->dworkY};
   for (double *d : ds)
     if (d) cudaFree(d);
-  ctx->dQQ = ctx->dG = ctx->dgn = ctx->dGI = ctx->dgnI = ctx->dlim = ctx->dumax = ctx->dworkL = ctx->dworkY = nullptr;
+  ctx->dQQraw = ctx->dQQ = ctx->dG = ctx->dgn = ctx->dGI = ctx->dgnI = ctx->dlim = ctx->dumax = ctx->dworkL = ctx->dworkY = nullptr;
   ctx->have_cost = false;
   ctx->have_GI = false;
   CU(cudaMalloc(&ctx->dQQ, sizeof(double) * n * n));
+  CU(cudaMalloc(&ctx->dQQraw, sizeof(double) * n * n));
+  CU(cudaMemcpyAsync(ctx->dQQraw, QQ, sizeof(double) * n * n, cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaMalloc(&ctx->dG, sizeof(double) * (size_t)np * np));
   CU(cudaMalloc(&ctx->dgn, sizeof(double) * np));
   CU(cudaMalloc(&ctx->dworkL, sizeof(double) * n * n));
@@ -363,8 +367,14 @@ static int solve_device(cfs_ctx *ctx, int B, int solver, int grad, const double 
                         double alpha, double *u, double *x, double *cost_hist, double *e_u_hist, int *iters, int *status) {
   const int nj = ctx->nj, H = ctx->H, n = ctx->n, np = 3 * n, O = ctx->nobs, OH = O * H;
   cudaStream_t st = ctx->stream;
-  if (solver == CFS_SOLVER_PSGCFS) return fail(ctx, CFS_E_ARG, "PSGCFS solver path not built yet");
+  const bool psg = solver == CFS_SOLVER_PSGCFS;
   int rc;
+  if (psg) {
+    if ((rc = ensure_GI(ctx))) return rc;
+    if ((rc = ensure(ctx, ctx->psg_w, sizeof(double) * (size_t)n * B))) return rc;
+    if ((rc = ensure(ctx, ctx->psg_cost, sizeof(double) * 2 * B))) return rc;
+    if ((rc = ensure(ctx, ctx->psg_skip, sizeof(int) * B))) return rc;
+  }
   if ((rc = ensure(ctx, ctx->u0, sizeof(double) * (size_t)n * B))) return rc;
   if ((rc = ensure(ctx, ctx->v0, sizeof(double) * (size_t)np * B))) return rc;
   if ((rc = ensure(ctx, ctx->cost0, sizeof(double) * B))) return rc;
@@ -387,16 +397,23 @@ static int solve_device(cfs_ctx *ctx, int B, int solver, int grad, const double 
   a.eps_outer = eps_outer;
   a.alpha = alpha;
   a.has_lim = ctx->has_lim;
-  a.has_bounds = ctx->has_bounds;
-  a.margin_is_D = 0;
-  a.G = ctx->dG;
-  a.gdiag = ctx->dgn;
-  a.QQ = ctx->dQQ;
+  // PSGCFS: margin obs.D (PSGCFS_FANUC.m:158), projection quadprog(I,-u_,Ainq,binq) without bounds (:120)
+  a.has_bounds = psg ? 0 : ctx->has_bounds;
+  a.margin_is_D = psg ? 1 : 0;
+  a.G = psg ? ctx->dGI : ctx->dG;
+  a.gdiag = psg ? ctx->dgnI : ctx->dgn;
+  a.QQ = ctx->dQQraw;
+  if (psg) {
+    a.w = ptr<double>(ctx->psg_w);
+    a.cost_old = ptr<double>(ctx->psg_cost);
+    a.cost_new = ptr<double>(ctx->psg_cost) + B;
+    a.skip = ptr<int>(ctx->psg_skip);
+  }
   a.lim = ctx->dlim;
   a.max_input = ctx->dumax;
   a.x0 = x0; a.ff = ff; a.caug = caug; a.xref = xref; a.noise = noise;
   a.u0 = ptr<double>(ctx->u0); a.v0 = ptr<double>(ctx->v0); a.cost0 = ptr<double>(ctx->cost0);
-  a.fupper = ptr<double>(ctx->fupper);
+  a.fupper = psg ? nullptr : ptr<double>(ctx->fupper);
   a.qq_norm_inf = ctx->qq_norm_inf;
   a.u = u; a.x = x;
   a.dist = ptr<double>(ctx->dist); a.grad = ptr<double>(ctx->grad);
@@ -436,9 +453,13 @@ static int solve_device(cfs_ctx *ctx, int B, int solver, int grad, const double 
   a.list_next = ptr<int>(ctx->listB); a.count_next = cnt + 1;
   a.work_counter = cnt + 2;
   CU(launch_solve_init(a, st)); ++launches;
-  // u0 = -QQ^{-1} FF : the control block of G is QQ^{-1}
-  CU(launch_dgemm(n, B, n, -1.0, ctx->dG + (size_t)2 * n * np + 2 * n, np, false, ff, n, a.u0, n, st)); ++launches;
-  CU(launch_v0(a, st)); ++launches;
+  if (psg) {
+    CU(cudaMemsetAsync(a.w, 0, sizeof(double) * (size_t)n * B, st));  // QQ*u at u = 0
+  } else {
+    // u0 = -QQ^{-1} FF : the control block of G is QQ^{-1}
+    CU(launch_dgemm(n, B, n, -1.0, ctx->dG + (size_t)2 * n * np + 2 * n, np, false, ff, n, a.u0, n, st)); ++launches;
+    CU(launch_v0(a, st)); ++launches;
+  }
 
   GradArgs g;
   memset(&g, 0, sizeof(g));
@@ -457,7 +478,12 @@ static int solve_device(cfs_ctx *ctx, int B, int solver, int grad, const double 
       CU(grad == CFS_GRAD_DERIVEST ? launch_grad_derivest(g, st) : launch_grad_numjac(g, st)); ++launches;
     }
     if (detail) CU(cudaEventRecord(ctx->ev[3 * (it - 1) + 1], st));
+    if (psg) { CU(launch_psg_point(a, st)); ++launches; }
     CU(launch_qp(a, grid, st)); ++launches;
+    if (psg) {  // w = QQ*u for EVAL.get_cost now and for the next PSG step
+      CU(launch_dgemm(n, B, n, 1.0, ctx->dQQraw, n, false, a.u, n, a.w, n, st)); ++launches;
+      CU(launch_psg_cost(a, st)); ++launches;
+    }
     if (detail) CU(cudaEventRecord(ctx->ev[3 * (it - 1) + 2], st));
     // swap lists; reset the consumed counter and the work queue
     std::swap(a.list_cur, a.list_next);

@@ -54,7 +54,7 @@ struct SolveArgs {
   double eps_outer, alpha;
   int has_lim, has_bounds, margin_is_D;
   const double *G, *gdiag;       // Gram operator used by the QP (QQ metric for CFS, identity metric for PSGCFS)
-  const double *QQ;              // n x n (PSGCFS gradient / cost)
+  const double *QQ;              // n x n as given by the caller (PSGCFS gradient QQ*u, PSGCFS_FANUC.m:131)
   const double *lim, *max_input;
   // per problem inputs
   const double *x0, *ff, *caug, *xref, *noise;
@@ -78,11 +78,16 @@ struct SolveArgs {
   long long *qp_steps;        // device counter
   int *max_active;            // device max
   int *prob_steps;            // per-problem step counter (B)
+  // PSGCFS state (solver == 1)
+  double *w;                  // n x B   QQ*u of the current iterate (batched GEMM after every projection)
+  double *cost_old, *cost_new;  // B     EVAL.cost_old / cost_new (EVAL.m:29, PSGCFS_FANUC.m:66,76,90)
+  int *skip;                  // B       stop_inner() was already true: no PSG step this outer iteration (PSGCFS_FANUC.m:88,136-142)
   long long *prof;            // optional 8-slot phase profile of k_qp (clock64 ticks of thread 0), or nullptr
 };
 cudaError_t launch_solve_init(const SolveArgs &a, cudaStream_t s);
 cudaError_t launch_v0(const SolveArgs &a, cudaStream_t s);
-cudaError_t launch_psg_point(const SolveArgs &a, cudaStream_t s);
+cudaError_t launch_psg_point(const SolveArgs &a, cudaStream_t s);  // K5: PSG_update_arm point + v0 = P*point
+cudaError_t launch_psg_cost(const SolveArgs &a, cudaStream_t s);   // EVAL.get_cost of the projected iterate
 cudaError_t launch_qp(const SolveArgs &a, int grid, cudaStream_t s);
 size_t qp_smem_bytes(const SolveArgs &a);
 int qp_max_grid(const SolveArgs &a, int device);

@@ -54,9 +54,10 @@ struct QpView {  // decoded shared-memory layout
   double *v0s;     // np      v at the unconstrained minimiser (per problem)
   double *gns;     // 2n      QQ^-1 norms of the omega / control primitive rows (per kernel)
   double *ums;     // n       MAX_input (per kernel)
+  double *pscr;    // QP_THREADS  partial sums of the polish residual
 };
 
-#define QP_NOFF 22
+#define QP_NOFF 23
 __host__ __device__ inline size_t qp_smem_layout(int n, int nj, int OH, int m, size_t *off /*[QP_NOFF]*/) {
   size_t o = 0;
   const int np = 3 * n;
@@ -83,6 +84,7 @@ __host__ __device__ inline size_t qp_smem_layout(int n, int nj, int OH, int m, s
   off[19] = o; o += sizeof(double) * np;
   off[20] = o; o += sizeof(double) * 2 * n;
   off[21] = o; o += sizeof(double) * n;
+  off[22] = o; o += sizeof(double) * QP_THREADS;
   return (o + 15) / 16 * 16;
 }
 
@@ -163,6 +165,23 @@ __device__ __forceinline__ double rhs_scale(int cid, int OH, int n, int nj, cons
   return umax[idx - n];
 }
 
+// c_w u0 - rhs_w : violation of row cid at the unconstrained minimiser (v0s), the right-hand side of S_W lambda = b
+__device__ __forceinline__ double viol_at_u0(int cid, int OH, int H, int n, int nj, const QpView &s, const double *umax) {
+  if (cid < OH) {
+    const int i = cid % H;
+    double val = 0.0;
+    for (int k = 0; k < nj; ++k) val += s.ocoef[cid * nj + k] * s.v0s[i * nj + k];
+    return val - s.orhs[cid];
+  }
+  const int e = cid - OH, idx = e >> 1, neg = e & 1;
+  if (e < 2 * n) {
+    const int k = idx % nj;
+    return neg ? -s.v0s[n + idx] - (s.lim[k] + s.w0[k]) : s.v0s[n + idx] - (s.lim[k] - s.w0[k]);
+  }
+  const int c = idx - n;
+  return neg ? -s.v0s[2 * n + c] - umax[c] : s.v0s[2 * n + c] - umax[c];
+}
+
 // ---- block reductions (QP_THREADS threads) --------------------------------------------------------------------
 __device__ __forceinline__ void block_argmin(double &val, int &idx, double *red) {
 #pragma unroll
@@ -240,10 +259,12 @@ __global__ void __launch_bounds__(QP_THREADS, 3) k_qp(SolveArgs a) {
     s.v0s = reinterpret_cast<double *>(smem_raw + off[19]);
     s.gns = reinterpret_cast<double *>(smem_raw + off[20]);
     s.ums = reinterpret_cast<double *>(smem_raw + off[21]);
+    s.pscr = reinterpret_cast<double *>(smem_raw + off[22]);
   }
   const double *__restrict__ G = a.G;
   const double *__restrict__ gnorm = a.gdiag;  // sqrt(diag(G))
   const int has_vel = a.has_lim, has_bnd = a.has_bounds;
+  const bool psg = a.solver == 1;
   for (int e = tid; e < 2 * n; e += QP_THREADS) s.gns[e] = gnorm[n + e];
   for (int e = tid; e < n; e += QP_THREADS) s.ums[e] = has_bnd ? a.max_input[e] : 0.0;
   const double *umax = s.ums;
@@ -316,7 +337,12 @@ __global__ void __launch_bounds__(QP_THREADS, 3) k_qp(SolveArgs a) {
 
     // ---- dual active-set iterations --------------------------------------------------------------------------
     int q = 0, status = -1, steps = 0;
-    bool in_smem = true;
+    bool in_smem = true, polished = false;
+    if (psg && a.skip[b]) {  // stop_inner() already true: u stays, no projection (PSGCFS_FANUC.m:88)
+      for (int c = tid; c < n; c += QP_THREADS) s.v[2 * n + c] = ub[c];
+      __syncthreads();
+      status = 0;
+    }
     double fval = a.cost0[b];
     const double fupper = (has_bnd && a.fupper) ? a.fupper[b] : INFINITY;
     const int max_steps = 20 * (m + n) + 100;
@@ -442,9 +468,51 @@ __global__ void __launch_bounds__(QP_THREADS, 3) k_qp(SolveArgs a) {
       block_argmin(best, bidx, s.red);
       PF_ADD(2);
       if (bidx < 0) {
-        status = 0;
-        break;
+        if (q == 0 || polished) {
+          status = 0;
+          break;
+        }
+        // Polish: the working-set inverse M has been rank-1 updated `steps` times; one step of iterative refinement on
+        // S_W lambda = b (S_W = C_W QQ^-1 C_W' re-read from G, b = violations at u0) removes the accumulated drift
+        // (measured: 7e-10 -> 3e-13 in u).  Then v is re-evaluated from the refined multipliers and scanned once more.
+        {
+          const int nch = QP_THREADS / q > 0 ? QP_THREADS / q : 1;  // chunks of columns per row, fixed summation order
+          if (q <= QP_THREADS) {
+            const int w = tid % q, ch = tid / q;
+            if (ch < nch) {
+              const Desc dw = decode(s.act[w], OH, H, n, nj, s.ocoef);
+              double acc = 0.0;
+              for (int c = ch; c < q; c += nch) acc += gram(dw, decode(s.act[c], OH, H, n, nj, s.ocoef), G, np) * s.lam[c];
+              s.pscr[ch * q + w] = acc;
+            }
+            __syncthreads();
+            if (tid < q) {
+              double acc = 0.0;
+              for (int ch2 = 0; ch2 < nch; ++ch2) acc += s.pscr[ch2 * q + tid];
+              s.g[tid] = viol_at_u0(s.act[tid], OH, H, n, nj, s, umax) - acc;
+            }
+          } else {
+            for (int w = tid; w < q; w += QP_THREADS) {
+              const Desc dw = decode(s.act[w], OH, H, n, nj, s.ocoef);
+              double acc = 0.0;
+              for (int c = 0; c < q; ++c) acc += gram(dw, decode(s.act[c], OH, H, n, nj, s.ocoef), G, np) * s.lam[c];
+              s.g[w] = viol_at_u0(s.act[w], OH, H, n, nj, s, umax) - acc;
+            }
+          }
+          __syncthreads();
+          for (int w = tid; w < q; w += QP_THREADS) {
+            double acc = 0.0;
+            for (int c = 0; c < q; ++c) acc += MAT(w, c) * s.g[c];
+            s.r[w] = acc;
+          }
+          __syncthreads();
+          for (int w = tid; w < q; w += QP_THREADS) s.lam[w] += s.r[w];
+          __syncthreads();
+        }
+        polished = true;
+        continue;
       }
+      polished = false;
       const int p = bidx;
       const Desc dp = decode(p, OH, H, n, nj, s.ocoef);
       const double sigma = gram(dp, dp, G, np);
@@ -648,26 +716,10 @@ __global__ void __launch_bounds__(QP_THREADS, 3) k_qp(SolveArgs a) {
       // cost by duality: f(u) = f(u0) + 1/2 sum_w lam_w * (c_w u0 - rhs_w)
       double pc = 0.0;
       for (int w = tid; w < q; w += QP_THREADS) {
-        const int cid = s.act[w];
-        double val0;  // c_w u0 - rhs_w = -slack at u0
-        if (cid < OH) {
-          const int i = cid % H;
-          double val = 0.0;
-          for (int k = 0; k < nj; ++k) val += s.ocoef[cid * nj + k] * s.v0s[i * nj + k];
-          val0 = val - s.orhs[cid];
-        } else {
-          const int e = cid - OH, idx = e >> 1, neg = e & 1;
-          if (e < 2 * n) {
-            const int k = idx % nj;
-            val0 = neg ? -s.v0s[n + idx] - (s.lim[k] + s.w0[k]) : s.v0s[n + idx] - (s.lim[k] - s.w0[k]);
-          } else {
-            const int c = idx - n;
-            val0 = neg ? -s.v0s[2 * n + c] - umax[c] : s.v0s[2 * n + c] - umax[c];
-          }
-        }
+        const double val0 = viol_at_u0(s.act[w], OH, H, n, nj, s, umax);
         pc += s.lam[w] * val0;
       }
-      const double cost = a.cost0[b] + 0.5 * block_sum(pc, s.red);
+      const double cost = psg ? 0.0 : a.cost0[b] + 0.5 * block_sum(pc, s.red);  // PSGCFS: k_psg_cost
       // roll-out (CFS_FANUC.m:90-94): x_old is staged in shared memory (coalesced), nj threads run the recurrence
       // xR(:,i) = A xR(:,i-1) + B u_i there, then the new trajectory is written back coalesced; ||x_new - x_old||^2
       // (EVAL.m:64) is accumulated on the way.  xbuf aliases the term-weight scratch (tcoef|twgt), free by now.
@@ -685,7 +737,8 @@ __global__ void __launch_bounds__(QP_THREADS, 3) k_qp(SolveArgs a) {
           th = thn;
           om = omn;
           double *xs = xbuf + (size_t)i * 2 * nj;
-          const double d1 = th - xs[tid], d2 = om - xs[nj + tid];
+          // CFS: x_old = previous x_ (CFS_FANUC.m:88); PSGCFS never updates eval.x_old, it stays ones (EVAL.m:47)
+          const double d1 = th - (psg ? 1.0 : xs[tid]), d2 = om - (psg ? 1.0 : xs[nj + tid]);
           px += d1 * d1 + d2 * d2;
           xs[tid] = th;
           xs[nj + tid] = om;
@@ -695,7 +748,7 @@ __global__ void __launch_bounds__(QP_THREADS, 3) k_qp(SolveArgs a) {
       for (int e = tid; e < 2 * n; e += QP_THREADS) xb[e] = xbuf[e];
       const double dx = sqrt(block_sum(px, s.red));
       if (tid == 0) {
-        a.cost_hist[(size_t)b * a.max_outer + (it - 1)] = cost;
+        if (!psg) a.cost_hist[(size_t)b * a.max_outer + (it - 1)] = cost;
         if (a.e_u_hist) a.e_u_hist[(size_t)b * a.max_outer + (it - 1)] = e_u;
         a.iters[b] = it;
         if (dx < a.eps_outer) {
@@ -760,6 +813,11 @@ __global__ void __launch_bounds__(128) k_solve_init(SolveArgs a) {
   if (tid == 0) {
     a.iters[b] = 0;
     a.flags[b] = 0;
+    if (a.solver == 1) {
+      a.cost_old[b] = 100000.0;   // EVAL.m:29
+      a.cost_new[b] = a.caug[b];  // get_cost(u = 0), PSGCFS_FANUC.m:66
+      a.skip[b] = 0;
+    }
     if (nrm < a.eps_outer) {
       a.status[b] = 0;
     } else if (1 > a.max_outer) {
@@ -840,7 +898,84 @@ cudaError_t launch_finalize(const SolveArgs &a, cudaStream_t s) {
   return cudaGetLastError();
 }
 
-cudaError_t launch_psg_point(const SolveArgs &, cudaStream_t) { return cudaErrorNotSupported; }
+// ---- K5: PSG_update_arm (PSGCFS_FANUC.m:106-112), one CTA per active problem ------------------------------------
+//   u_ = u - alpha*((QQ*u + ff) + 10*noise/(iter_O^2+1));   then v0 = P u_ for the projection QP (Hessian I, no bounds).
+// stop_inner (PSGCFS_FANUC.m:136-142) is evaluated first: |cost_new - cost_old| < epsilon_I = 1e-4 skips the step.
+__global__ void __launch_bounds__(128) k_psg_point(SolveArgs a) {
+  extern __shared__ double u0s[];
+  if ((int)blockIdx.x >= *a.count_cur) return;
+  const int b = a.list_cur[blockIdx.x], tid = threadIdx.x;
+  const int n = a.n, nj = a.nj, np = 3 * n;
+  const double dt = a.tab->dt;
+  const double cn = a.cost_new[b], co = a.cost_old[b];
+  if (fabs(cn - co) < 1e-4) {  // uniform across the CTA
+    if (tid == 0) a.skip[b] = 1;
+    return;
+  }
+  const double it = (double)a.outer_iter;
+  const double *nz = a.noise ? a.noise + ((size_t)b * a.max_outer + (a.outer_iter - 1)) * n : nullptr;
+  for (int e = tid; e < n; e += blockDim.x) {
+    const double g = a.w[(size_t)b * n + e] + a.ff[(size_t)b * n + e];
+    const double uv = a.u[(size_t)b * n + e] - a.alpha * (g + 10 * (nz ? nz[e] : 0.0) / (it * it + 1));
+    u0s[e] = uv;
+    a.u0[(size_t)b * n + e] = uv;
+  }
+  if (tid == 0) {
+    a.skip[b] = 0;
+    a.cost_old[b] = cn;  // PSGCFS_FANUC.m:89
+    a.cost0[b] = 0.0;
+  }
+  __syncthreads();
+  for (int pi = tid; pi < np; pi += blockDim.x) {
+    double acc;
+    if (pi < n) {
+      const int i = pi / nj, k = pi % nj;
+      acc = 0.0;
+      for (int j = 0; j <= i; ++j) acc += (0.5 * dt * dt + ((i - j) * dt) * dt) * u0s[j * nj + k];
+    } else if (pi < 2 * n) {
+      const int qq = pi - n, i = qq / nj, k = qq % nj;
+      acc = 0.0;
+      for (int j = 0; j <= i; ++j) acc += dt * u0s[j * nj + k];
+    } else {
+      acc = u0s[pi - 2 * n];
+    }
+    a.v0[(size_t)b * np + pi] = acc;
+  }
+}
+
+cudaError_t launch_psg_point(const SolveArgs &a, cudaStream_t s) {
+  if (a.B <= 0) return cudaSuccess;
+  k_psg_point<<<a.B, 128, sizeof(double) * a.n, s>>>(a);
+  return cudaGetLastError();
+}
+
+// EVAL.get_cost (EVAL.m:51-53) of the projected iterate, w = QQ*u from the batched GEMM; one CTA per problem of the list
+// the QP kernel just consumed.  Problems whose projection failed this iteration (iters[b] != outer_iter) are skipped.
+__global__ void __launch_bounds__(128) k_psg_cost(SolveArgs a) {
+  __shared__ double red[QP_WARPS];
+  if ((int)blockIdx.x >= *a.count_cur) return;
+  const int b = a.list_cur[blockIdx.x], tid = threadIdx.x, n = a.n;
+  if (a.iters[b] != a.outer_iter) return;
+  double pq = 0.0, pl = 0.0;
+  for (int e = tid; e < n; e += blockDim.x) {
+    const double uv = a.u[(size_t)b * n + e];
+    pq += uv * a.w[(size_t)b * n + e];
+    pl += uv * a.ff[(size_t)b * n + e];
+  }
+  const double quad = block_sum(pq, red);
+  const double lin = block_sum(pl, red);
+  if (tid == 0) {
+    const double cost = (0.5 * quad + lin) + a.caug[b];
+    a.cost_new[b] = cost;
+    a.cost_hist[(size_t)b * a.max_outer + (a.outer_iter - 1)] = cost;
+  }
+}
+
+cudaError_t launch_psg_cost(const SolveArgs &a, cudaStream_t s) {
+  if (a.B <= 0) return cudaSuccess;
+  k_psg_cost<<<a.B, 128, 0, s>>>(a);
+  return cudaGetLastError();
+}
 
 // ============================================================================================================
 // Dense get_con rows for one problem, in the reference's order (CFS_FANUC.m:110-131); parity/debug entry.

@@ -4,12 +4,14 @@ build_cost_matrices  <- main_FANUC.m:64-97  (Aaug, Baug, Qaug, R -> QQ);  RRTsta
 build_linear_term    <- main_FANUC.m:98-103 (gaug, ff, caug)
 straight_line_reference <- main_FANUC.m:38-49
 make_sys_info        <- main_FANUC.m:106-127 (the struct handed to CFS_FANUC / PSGCFS_FANUC)
+cubicpolytraj        <- RRTstar_CFS.m:96-100 (Robotics System Toolbox call; default zero waypoint velocities)
 """
 import numpy as np
 
 Q_MAIN_FANUC = np.block([[np.diag([10, 10, 1, 1, 1.0]), 0.1 * np.eye(5)], [0.1 * np.eye(5), np.diag([10, 10, 1, 1, 1.0])]])
 Q_RRTSTAR = np.block([[np.diag([10, 10, 1, 1, 1.0]), 0.1 * np.eye(5)], [0.1 * np.eye(5), np.diag([100, 20, 1, 1, 1.0])]])
 R_MAIN_FANUC = np.array([[10, 0, 0, 0, 0], [0, 10, 1, 0, 0], [0, 1, 2, 0, 0], [0, 0, 0, 2, 0], [0, 0, 0, 0, 1.0]])
+Q_M16_SCRIPT = np.block([[np.diag([10, 1, 1, 1, 1.0]), 0.1 * np.eye(5)], [0.1 * np.eye(5), np.diag([10, 1, 1, 1, 1.0])]])  # M16iB/main_CFS.m:69-80
 Q_2L = np.block([[np.diag([10, 1.0]), 0.1 * np.eye(2)], [0.1 * np.eye(2), np.diag([10, 1.0])]])
 R_2L = np.array([[5, 0], [0, 4.0]])
 
@@ -82,3 +84,16 @@ def make_sys_info(robot, njoint, horizon, x0_theta, xg_theta, Q=None, Rblk=None,
                 nstate=2 * njoint, njoint=njoint, xR=x0.reshape(-1, 1), nu=njoint, x_=np.asarray(x_ref, dtype=np.float64),
                 alpha=1.0 / np.linalg.svd(QQ, compute_uv=False).max(), lim=np.asarray(lim, dtype=np.float64),
                 epsilon_O=epsilon_O, MAX_O_ITER=MAX_O_ITER, MAX_input=np.asarray(max_input, dtype=np.float64))
+
+
+def cubicpolytraj(waypoints, wp_times, traj_times):
+    """sampled_route = cubicpolytraj(route, wpTimes, trajTimes) of RRTstar_CFS.m:100 with the toolbox defaults
+    (zero velocity at every waypoint): on segment k, q = q_k + (3 s^2 - 2 s^3)(q_{k+1} - q_k), s = (t - t_k)/(t_{k+1} - t_k).
+    waypoints (nj, W) -> (nj, len(traj_times)).  The toolbox is not part of the reference tree: parity unpinned."""
+    wp = np.asarray(waypoints, dtype=np.float64)
+    tw = np.asarray(wp_times, dtype=np.float64)
+    tt = np.asarray(traj_times, dtype=np.float64)
+    seg = np.clip(np.searchsorted(tw, tt, side="right") - 1, 0, len(tw) - 2)
+    s = (tt - tw[seg]) / (tw[seg + 1] - tw[seg])
+    blend = 3 * s * s - 2 * s * s * s
+    return wp[:, seg] + blend[None, :] * (wp[:, seg + 1] - wp[:, seg])

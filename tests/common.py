@@ -5,6 +5,14 @@ import motionplanning_5d_m_b200 as M
 from motionplanning_5d_m_b200 import problem, synthetic
 
 
+OBS_M16_SCRIPT_ALT = [[4.506, 4.506], [8.513, 8.513], [1.072, 1.538]]  # M16iB/main_CFS.m:53 (commented alternative)
+
+
+def golden(name):
+    import os
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name))
+
+
 def main_fanuc_config():
     """main_FANUC.m:13-60,106-127 : M200i, H=30, one capsule obstacle."""
     robot = M.robotproperty2("M200i")
@@ -36,6 +44,37 @@ def rrtstar_cfs_config(route):
     obs = [{"l": np.array([[3.606, 3.606], [8.413, 8.413], [0.001, 1.038]]), "D": 0.2, "epsilon": 0.2},
            {"l": np.array([[3.406, 3.406], [7.813, 7.813], [0.800, 1.538]]), "D": 0.2, "epsilon": 0.2}]
     return "M200i", robot, obs, s
+
+
+def main_cfs_m16ib_config(xuori):
+    """M16iB/main_CFS.m:15-113 (the DERIVEST script path): H=24, straight line between the ends of data/good_xori.mat with
+    constant-velocity rows (dt=0.05 there, :33-39), QQ = Baug'QaugBaug (R*0, :113), no velocity rows, bounds +-0.2,
+    D = 0.2, stop ||xref-oldref|| < 0.01, at most 10 iterations."""
+    robot = M.robotproperty2("M16iB")  # robotproperty(3): same DH / capsules / dt, base passed explicitly (:17)
+    xuori = np.asarray(xuori, dtype=np.float64).reshape(-1)
+    nj, H = 5, 24
+    x0, xg = xuori[:10], xuori[-10:]
+    th = np.stack([np.linspace(x0[k], xg[k], H + 1) for k in range(nj)])                     # :29-31
+    w = np.stack([np.concatenate([np.full(H, (xg[k] - x0[k]) / (0.05 * H)), [0.0]]) for k in range(nj)])  # :33-36
+    xref_ = np.concatenate([th, w]).T.reshape(-1)                                           # :37-40
+    xori = xref_[10:]
+    Aaug, Baug, Qaug, QQ = problem.build_cost_matrices(robot, nj, H, problem.Q_M16_SCRIPT, np.eye(5), 0.0)
+    ff = ((Aaug @ x0 - xori) @ Qaug @ Baug)
+    caug = float((Aaug @ x0 - xori) @ Qaug @ (Aaug @ x0 - xori))
+    s = dict(Aaug=Aaug, Baug=Baug, QQ=QQ, ff=ff, Qaug=QQ, paug=ff, caug=caug, robot=robot, H=H, nstate=10, njoint=nj, nu=nj,
+             xR=x0.reshape(-1, 1), x_=xori, alpha=0.0, lim=None, epsilon_O=0.01, MAX_O_ITER=10,
+             MAX_input=0.2 * np.ones(H * nj))
+    obs = [{"l": np.array([[3.906, 3.906], [8.313, 8.313], [0.001, 1.938]]), "D": 0.2, "epsilon": 0.2}]
+    return "M16iB", robot, obs, s
+
+
+def rrtstar_route_config(route_wp):
+    """RRTstar_CFS.m:96-100: resample an RRT route to H+1 = 41 waypoints, then the CFS stage set-up (:106-187)."""
+    route_wp = np.asarray(route_wp, dtype=np.float64)
+    dt = 0.5
+    wp_t = np.arange(route_wp.shape[1]) * dt
+    sampled = problem.cubicpolytraj(route_wp, wp_t, np.linspace(0, wp_t[-1], 41))
+    return rrtstar_cfs_config(sampled)
 
 
 def oracle_problem(O, ROBOT, obs, s, solver=0, grad=0, margin=None, max_input="default"):

@@ -96,14 +96,15 @@ def test_get_con_parity(ctx, oracle):
     assert np.abs(b - br).max() < 1e-8
 
 
-def _compare_solve(out, ref, tol_x=1e-6, tol_c=1e-6):
+def _compare_solve(out, ref, tol_x=1e-6, tol_c=1e-6, tol_u=None):
+    tol_u = tol_x if tol_u is None else tol_u
     st_g, st_r = out["status"], ref["status"]
     assert (st_g == st_r).all(), (np.where(st_g != st_r)[0][:10], st_g[st_g != st_r][:10], st_r[st_g != st_r][:10])
     assert (out["iters"] == ref["iters"]).all()
     ok = (st_r & 0xFF) < 2
     dx = np.abs(out["x"][ok] - ref["x"][ok]).max() if ok.any() else 0.0
     du = np.abs(out["u"][ok] - ref["u"][ok]).max() if ok.any() else 0.0
-    assert dx < tol_x and du < tol_x, (dx, du)
+    assert dx < tol_x and du < tol_u, (dx, du)
     for b in np.where(ok)[0]:
         it = ref["iters"][b]
         cg, cr = out["cost_hist"][b, :it], ref["cost_hist"][b, :it]
@@ -148,6 +149,70 @@ def test_batch_m16ib_solve_parity(ctx, oracle):
     ref = P.solve_batch(cfg["x0"], cfg["ff"], cfg["caug"], cfg["xref"], nthreads=8)
     out = ctx.solve_batch(cfg["x0"], cfg["ff"], cfg["caug"], cfg["xref"], s["epsilon_O"], s["MAX_O_ITER"])
     assert ((ref["status"] & 0xFF) == 2).any() and ((ref["status"] & 0xFF) == 0).any()
+    _compare_solve(out, ref)
+
+
+def test_psgcfs_main_fanuc_parity(ctx, oracle):
+    """PSGCFS_FANUC.optimizer on main_FANUC.m's configuration with host-supplied normrnd draws (PSGCFS_FANUC.m:109)."""
+    O = oracle
+    ROBOT, robot, obs, s = common.main_fanuc_config()
+    _set(ctx, ROBOT, robot, obs, s, bounds=False)
+    P = common.oracle_problem(O, ROBOT, obs, s, solver=1)
+    K, n = s["MAX_O_ITER"], s["H"] * 5
+    noise = np.random.default_rng(123).normal(0.0, 0.1, size=(1, K, n))
+    args = (s["xR"][:, 0][None], s["ff"][None], np.array([s["caug"]]), s["x_"][None])
+    ref = P.solve_batch(*args, noise=noise)
+    out = ctx.solve_batch(*args, s["epsilon_O"], K, solver=_lib.SOLVER_PSGCFS, noise=noise, alpha=s["alpha"])
+    assert ref["iters"][0] == K  # eval.x_old stays ones: PSGCFS always runs MAX_O_ITER iterations
+    _compare_solve(out, ref)
+    # without noise (deterministic projected gradient)
+    ref0 = P.solve_batch(*args)
+    out0 = ctx.solve_batch(*args, s["epsilon_O"], K, solver=_lib.SOLVER_PSGCFS, alpha=s["alpha"])
+    _compare_solve(out0, ref0)
+
+
+def test_psgcfs_batch_parity(ctx, oracle):
+    O = oracle
+    cfg = common.batch_m16ib(O, 96, horizon=30)
+    s = dict(cfg["sys_info"])
+    s["alpha"] = 1.0 / np.linalg.svd(s["QQ"], compute_uv=False).max()
+    s["MAX_O_ITER"] = 8
+    _set(ctx, "M16iB", cfg["robot"], cfg["obs"], s, bounds=False)
+    P = common.oracle_problem(O, "M16iB", cfg["obs"], s, solver=1)
+    noise = np.random.default_rng(5).normal(0.0, 0.1, size=(96, 8, 150))
+    ref = P.solve_batch(cfg["x0"], cfg["ff"], cfg["caug"], cfg["xref"], noise=noise, nthreads=8)
+    out = ctx.solve_batch(cfg["x0"], cfg["ff"], cfg["caug"], cfg["xref"], s["epsilon_O"], 8, solver=_lib.SOLVER_PSGCFS,
+                          noise=noise, alpha=s["alpha"])
+    assert ((ref["status"] & 0xFF) == 1).any()
+    _compare_solve(out, ref)
+
+
+@pytest.mark.parametrize("name", ["main_fanuc_cfs", "main_fanuc_psgcfs", "main_2l_cfs", "m16ib_script_derivest",
+                                  "m16ib_script_alt_derivest", "m16ib_script_alt_numjac", "rrtstar_cfs"])
+def test_cuda_reproduces_golden_cases(ctx, oracle, name):
+    """The CUDA path against the committed golden fixtures (tests/golden/cases.npz): no oracle call on this path."""
+    from tests.test_oracle import _golden_cases, check_against_golden
+    gold = common.golden("cases.npz")
+    ROBOT, obs, s, solver, grad, noise = _golden_cases(oracle)[name]
+    robot = s["robot"]
+    r = dict(robot)
+    r["name"] = ROBOT
+    ctx.set_robot(r, s["njoint"])
+    ctx.set_obstacles(obs)
+    ctx.set_cost(s["H"], s["QQ"], s.get("lim"), s["MAX_input"] if solver == 0 else None)
+    out = ctx.solve_batch(s["xR"][:, 0][None], s["ff"][None], np.array([s["caug"]]), s["x_"][None], s["epsilon_O"],
+                          s["MAX_O_ITER"], solver=solver, grad=grad, noise=noise, alpha=s.get("alpha", 0.0))
+    check_against_golden(name, out, gold)
+
+
+def test_cuda_reproduces_golden_batch(ctx, oracle):
+    gold = common.golden("cases.npz")
+    cfg = common.batch_m16ib(oracle, 32)
+    s = cfg["sys_info"]
+    _set(ctx, "M16iB", cfg["robot"], cfg["obs"], s)
+    out = ctx.solve_batch(cfg["x0"], cfg["ff"], cfg["caug"], cfg["xref"], s["epsilon_O"], s["MAX_O_ITER"])
+    ref = {k: gold["batch_m16ib_32." + k] for k in ("u", "x", "cost_hist", "iters", "status")}
+    ref["e_u_hist"] = out["e_u_hist"]
     _compare_solve(out, ref)
 
 

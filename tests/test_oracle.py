@@ -141,3 +141,80 @@ def test_main_fanuc_oracle_golden(oracle):
     # re-linearised at the converged trajectory the constraints hold up to the clearance error seen above
     A, b, *_ = P.get_con(s["xR"][:, 0], x.reshape(-1), ref["u"][0])
     assert (A @ ref["u"][0] - b).max() < 1e-4
+
+
+# ---- golden fixtures (tests/golden/, frozen by tests/golden/make_golden.py) ------------------------------------------
+def _golden_cases(O):
+    """name -> (ROBOT, obs, sys_info, solver, grad, noise): the reference's shipped configurations rebuilt from the
+    committed input fixtures (no /root/reference at test time)."""
+    inp = common.golden("inputs.npz")
+    cases = {}
+    ROBOT, robot, obs, s = common.main_fanuc_config()
+    cases["main_fanuc_cfs"] = (ROBOT, obs, s, 0, 0, None)
+    noise = np.random.default_rng(123).normal(0.0, 0.1, size=(1, s["MAX_O_ITER"], s["H"] * 5))
+    cases["main_fanuc_psgcfs"] = (ROBOT, obs, s, 1, 0, noise)
+    ROBOT, robot, obs, s = common.main_2l_config()
+    cases["main_2l_cfs"] = (ROBOT, obs, s, 0, 0, None)
+    ROBOT, robot, obs, s = common.main_cfs_m16ib_config(inp["xuori"])
+    cases["m16ib_script_derivest"] = (ROBOT, obs, s, 0, 1, None)
+    obs2 = [dict(obs[0], l=np.array(common.OBS_M16_SCRIPT_ALT))]
+    cases["m16ib_script_alt_derivest"] = (ROBOT, obs2, s, 0, 1, None)
+    cases["m16ib_script_alt_numjac"] = (ROBOT, obs2, s, 0, 0, None)
+    ROBOT, robot, obs, s = common.rrtstar_route_config(inp["route_wp"])
+    cases["rrtstar_cfs"] = (ROBOT, obs, s, 0, 0, None)
+    return cases
+
+
+def check_against_golden(name, out, gold, tol_x=1e-6, tol_c=1e-6):
+    """out: dict of per-problem arrays (first axis = problem) ; gold: tests/golden/cases.npz"""
+    g = {k: gold["%s.%s" % (name, k)] for k in ("u", "x", "cost_hist", "iters", "status")}
+    assert int(out["status"][0]) == int(g["status"]) and int(out["iters"][0]) == int(g["iters"]), name
+    it = int(g["iters"])
+    if (int(g["status"]) & 0xFF) < 2:
+        assert np.abs(out["x"][0] - g["x"]).max() < tol_x and np.abs(out["u"][0] - g["u"]).max() < tol_x, name
+    if it:
+        assert np.all(np.abs(out["cost_hist"][0][:it] - g["cost_hist"][:it]) <= tol_c * np.abs(g["cost_hist"][:it])), name
+
+
+@pytest.mark.parametrize("name", ["main_fanuc_cfs", "main_fanuc_psgcfs", "main_2l_cfs", "m16ib_script_derivest",
+                                  "m16ib_script_alt_derivest", "m16ib_script_alt_numjac", "rrtstar_cfs"])
+def test_oracle_reproduces_golden_cases(oracle, name):
+    gold = common.golden("cases.npz")
+    ROBOT, obs, s, solver, grad, noise = _golden_cases(oracle)[name]
+    P = common.oracle_problem(oracle, ROBOT, obs, s, solver=solver, grad=grad)
+    out = P.solve_batch(s["xR"][:, 0][None], s["ff"][None], np.array([s["caug"]]), s["x_"][None], noise=noise)
+    check_against_golden(name, out, gold, tol_x=1e-9, tol_c=1e-12)
+
+
+def test_golden_kat_file_matches_oracle(oracle):
+    import json, os
+    kat = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "kat.json")))
+    k = kat["distLinSeg"]
+    d, pts = oracle.dist_lin_seg(k["p1"], k["p2"], k["p3"], k["p4"])
+    assert abs(d - k["dist"]) < 0.5 * 10 ** -k["digits"] and np.allclose(pts, k["points"], atol=1e-15)
+    which = {"exp": 0, "sin": 1, "sinh": 2, "log": 3}
+    for e in kat["derivest"]:
+        der, err, _ = oracle.derivest_named(which[e["fun"]], e["x0"])
+        assert abs(der - e["der"]) <= 0.5 * 10 ** -e["digits"] * max(1.0, abs(e["der"])), e
+        if "errest" in e:
+            assert abs(err - e["errest"]) < 1e-19
+
+
+def test_golden_batch_inputs_regenerate(oracle):
+    gold = common.golden("cases.npz")
+    cfg = common.batch_m16ib(oracle, 32)
+    assert np.array_equal(cfg["theta0"], gold["batch_m16ib_32.theta0"])
+    assert np.array_equal(cfg["thetag"], gold["batch_m16ib_32.thetag"])
+
+
+def test_cubicpolytraj_restatement():
+    """RRTstar_CFS.m:96-100: zero-velocity cubic blend through the waypoints (toolbox defaults)."""
+    from motionplanning_5d_m_b200 import problem
+    wp = np.array([[0.0, 1.0, 3.0], [1.0, 1.0, -1.0]])
+    t = np.array([0.0, 0.5, 1.0])
+    q = problem.cubicpolytraj(wp, t, np.array([0.0, 0.25, 0.5, 0.75, 1.0]))
+    assert np.allclose(q[:, [0, 2, 4]], wp)
+    assert np.allclose(q[:, 1], (wp[:, 0] + wp[:, 1]) / 2) and np.allclose(q[:, 3], (wp[:, 1] + wp[:, 2]) / 2)
+    eps = 1e-6  # zero velocity at interior waypoints
+    qa = problem.cubicpolytraj(wp, t, np.array([0.5 - eps, 0.5 + eps]))
+    assert np.abs(qa[:, 1] - qa[:, 0]).max() < 1e-10
