@@ -3,10 +3,12 @@ import sys; sys.path.insert(0,'.')
 import numpy as np, motionplanning_5d_m_b200 as M
 from motionplanning_5d_m_b200 import synthetic
 B = int(sys.argv[1]) if len(sys.argv)>1 else 4096
+fused = int(sys.argv[2]) if len(sys.argv)>2 else 1
 ctx = M.Context(0)
 r = dict(M.robotproperty2("M16iB")); r["name"]="M16iB"; ctx.set_robot(r,5); ctx.set_obstacles([synthetic.OBS_M16IB])
 cfg = synthetic.batch_config_m16ib(B, lambda c: ctx.nodes_feasible(c)[0])
 s = cfg["sys_info"]; ctx.set_cost(50, s["QQ"], s["lim"], s["MAX_input"])
+ctx.set_option("fused", fused)
 ctx.set_timing(2)
 for rep in range(3):
     out = ctx.solve_batch(cfg["x0"], cfg["ff"], cfg["caug"], cfg["xref"], 0.1, 20)
@@ -28,6 +30,6 @@ print("steps feasible problems: mean %.2f max %d" % (ps[st<2].mean(), ps[st<2].m
 ctx.set_timing(3)
 out = ctx.solve_batch(cfg["x0"], cfg["ff"], cfg["caug"], cfg["xref"], 0.1, 20)
 pf = ctx.qp_profile()
-names = ["prologue","refresh","scan","gram+solve","update","epilogue"]
+names = ["setup+grad","refresh","scan","gram+solve","update","epilogue"]
 print("qp profile: problems %d outer steps %d" % (pf[6], pf[7]))
 for k,nm in enumerate(names): print("  %-10s %12d ticks  %8.1f per problem-iter  %8.1f per outer step" % (nm, pf[k], pf[k]/max(pf[6],1), pf[k]/max(pf[7],1)))

@@ -61,6 +61,11 @@ const char *cfs_version(void);
  * the caller's events bracket the library's kernels.  NULL restores the context's own stream. */
 int cfs_set_stream(cfs_ctx *ctx, void *cuda_stream);
 
+/* Options: "fused" (default 1): solve CFS / num_jac batches with the persistent fused kernel (one CTA carries a problem
+ * through all outer iterations); 0 = one gradient launch + one QP launch per outer iteration (the path PSGCFS and the
+ * DERIVEST gradients always take). */
+int cfs_set_option(cfs_ctx *ctx, const char *name, int value);
+
 /* ---- problem data ------------------------------------------------------------------------------------- */
 /* robotproperty2.m:12-139 -> sys_info.robot.{DH (6x4), base (3), cap{i}.p (3x2 per link), delta_t}; T2L = robot.T
  * (3x3, only for CFS_ROBOT_2L, else NULL).  n_joints = sys_info.njoint (links used = first n_joints rows). */

@@ -18,7 +18,7 @@ STATUS_CONVERGED, STATUS_MAX_ITER, STATUS_INFEASIBLE, STATUS_NUMERICAL = 0, 1, 2
 FLAG_TOUCH = 0x100
 
 # every symbol include/cfs_b200.h declares (tests check that the library exports all of them)
-SYMBOLS = ["cfs_create", "cfs_destroy", "cfs_last_error", "cfs_version", "cfs_set_stream", "cfs_set_robot", "cfs_set_obstacles",
+SYMBOLS = ["cfs_create", "cfs_destroy", "cfs_last_error", "cfs_version", "cfs_set_stream", "cfs_set_option", "cfs_set_robot", "cfs_set_obstacles",
            "cfs_set_cost", "cfs_solve_batch", "cfs_solve_batch_device", "cfs_dist_grad", "cfs_get_con",
            "cfs_nodes_feasible", "cfs_nearest_steer", "cfs_get_stats", "cfs_set_timing", "cfs_get_iter_times", "cfs_get_problem_steps", "cfs_get_qp_profile", "cfs_measure_fp64_peak"]
 
@@ -217,6 +217,9 @@ class Context:
     def set_stream(self, cuda_stream):
         """cuda_stream: integer cudaStream_t handle (e.g. torch.cuda.current_stream().cuda_stream) or 0/None."""
         self._check(self._lib.cfs_set_stream(self._h, C.c_void_p(cuda_stream or None)), "cfs_set_stream")
+
+    def set_option(self, name, value):
+        self._check(self._lib.cfs_set_option(self._h, C.c_char_p(name.encode()), C.c_int(int(value))), "cfs_set_option")
 
     def set_timing(self, level):
         self._check(self._lib.cfs_set_timing(self._h, C.c_int(level)), "cfs_set_timing")

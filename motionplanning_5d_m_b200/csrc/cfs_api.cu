@@ -55,6 +55,7 @@ struct cfs_ctx {
   std::vector<cudaEvent_t> ev;
   cudaEvent_t ev_a = nullptr, ev_b = nullptr;
   int timing_level = 1;
+  bool use_fused = true;  // cfs_set_option("fused")
   std::vector<double> it_grad_ms, it_qp_ms;
   cfs_stats stats;
 };
@@ -426,7 +427,9 @@ static int solve_device(cfs_ctx *ctx, int B, int solver, int grad, const double 
   a.prof = ctx->timing_level >= 3 ? ptr<long long>(ctx->qpsteps) + 8 : nullptr;
   a.slab_ld = n;
 
-  int grid = qp_max_grid(a, ctx->device);
+  const bool fused = ctx->use_fused && !psg && grad == CFS_GRAD_NUMJAC && fused_supported(a);
+  int grid = fused ? fused_max_grid(a, ctx->device) : qp_max_grid(a, ctx->device);
+  if (grid <= 0) return fail(ctx, CFS_E_CUDA, "solver kernel does not fit on this device (shared memory)");
   {
     int sms = 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
@@ -452,6 +455,15 @@ static int solve_device(cfs_ctx *ctx, int B, int solver, int grad, const double 
   a.list_cur = ptr<int>(ctx->listA); a.count_cur = cnt + 0;
   a.list_next = ptr<int>(ctx->listB); a.count_next = cnt + 1;
   a.work_counter = cnt + 2;
+  if (fused) {
+    // one persistent kernel: every CTA carries a problem through all its outer iterations (k_fused.cu)
+    CU(launch_dgemm(n, B, n, -1.0, ctx->dG + (size_t)2 * n * np + 2 * n, np, false, ff, n, a.u0, n, st)); ++launches;
+    CU(launch_v0(a, st)); ++launches;
+    CU(launch_fused(a, grid, st)); ++launches;
+    CU(cudaEventRecord(ctx->ev_b, st));
+    ctx->stats.launches = launches;
+    return 0;
+  }
   CU(launch_solve_init(a, st)); ++launches;
   if (psg) {
     CU(cudaMemsetAsync(a.w, 0, sizeof(double) * (size_t)n * B, st));  // QQ*u at u = 0
@@ -522,7 +534,7 @@ static int collect_stats(cfs_ctx *ctx, int B, int max_outer, const int *d_iters,
   ctx->stats.ms_grad = ctx->stats.ms_qp = 0;
   ctx->it_grad_ms.clear();
   ctx->it_qp_ms.clear();
-  if (ctx->timing_level >= 2) {
+  if (ctx->timing_level >= 2 && ctx->ev.size() >= (size_t)3 * max_outer && ctx->stats.launches > 3) {
     for (int k = 0; k < max_outer; ++k) {
       float a = 0, b = 0;
       cudaEventElapsedTime(&a, ctx->ev[3 * k], ctx->ev[3 * k + 1]);
@@ -774,6 +786,15 @@ extern "C" int cfs_get_problem_steps(cfs_ctx *ctx, int *steps, int B) {
   CU(cudaMemcpyAsync(steps, ctx->probsteps.p, sizeof(int) * B, cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   return 0;
+}
+
+extern "C" int cfs_set_option(cfs_ctx *ctx, const char *name, int value) {
+  if (!ctx || !name) return CFS_E_ARG;
+  if (strcmp(name, "fused") == 0) {
+    ctx->use_fused = value != 0;
+    return 0;
+  }
+  return fail(ctx, CFS_E_ARG, "cfs_set_option: unknown option '%s'", name);
 }
 
 extern "C" int cfs_set_timing(cfs_ctx *ctx, int level) {

@@ -93,6 +93,12 @@ size_t qp_smem_bytes(const SolveArgs &a);
 int qp_max_grid(const SolveArgs &a, int device);
 cudaError_t launch_finalize(const SolveArgs &a, cudaStream_t s);
 
+// ---- fused persistent solver: the whole CFS outer loop of a problem inside one CTA (k_fused.cu) -------------------------
+bool fused_supported(const SolveArgs &a);  // CFS solver, num_jac gradients, nj in {2, 5}
+size_t fused_smem_bytes(const SolveArgs &a);
+int fused_max_grid(const SolveArgs &a, int device);
+cudaError_t launch_fused(const SolveArgs &a, int grid, cudaStream_t s);
+
 // ---- dense get_con rows (one problem) -------------------------------------------------------------------------
 cudaError_t launch_get_con_rows(const DevTables *tab, int H, int nj, int nobs, int has_lim, int margin_is_D,
                                 const double *x0, const double *u, const double *lim, const double *dist,

@@ -1,0 +1,266 @@
+// k_fused.cu -- the whole CFS outer loop of one problem inside one persistent CTA (sm_100a).
+//
+// Replaces CFS_FANUC.optimizer (Lib/CFS_FANUC.m:62-79) end to end for the class path (num_jac gradients):
+//   while ~stop_outer:  get_con (:101-135)  ->  Solve_QP (:83-98: quadprog + roll-out)  ->  EVAL (Lib/EVAL.m:51-73)
+//
+// Why fused (B200-first, not a translation of the MATLAB loop):
+//   * the lock-step form (one K1 + one K3 launch per outer iteration over the still-active problems) pays, in every
+//     iteration, for the slowest QP of that iteration while >90 % of the SMs idle (ncu: smsp__cycles_active 7 % of
+//     elapsed in iteration 1).  Here every CTA carries ONE problem through ALL its outer iterations and then pulls the
+//     next problem from a device work queue, so the batch costs max(longest single problem, total work / resident CTAs);
+//   * the trajectory x_, the controls u, the linearised rows (-grad, rhs) and the QP working set never leave shared
+//     memory between iterations: HBM sees each problem's inputs once and its outputs once (6.1 KB in, 6.3 KB out at
+//     H = 50), the batch-shared Gram operator G (4.5 MB) streams from L2;
+//   * the robot/obstacle tables are staged once per CTA with one TMA bulk copy (UBLKCP), the 30 sin/cos values of a
+//     waypoint's 11 num_jac evaluations are cached in shared memory that the QP phase reuses for its working-set inverse.
+#include "cfs_numjac.cuh"
+#include "qp_core.cuh"
+
+namespace cfs {
+
+static_assert(QP_THREADS == GRAD_THREADS, "the sin/cos cache is indexed by the QP thread id");
+
+struct FusedLayout {
+  size_t qp_bytes, xs, us, tab, mbar, total;
+};
+
+__host__ __device__ inline FusedLayout fused_layout(int n, int nj, int OH, int m) {
+  FusedLayout L;
+  size_t off[QP_NOFF];
+  L.qp_bytes = qp_smem_layout(n, nj, OH, m, off);
+  size_t o = L.qp_bytes;
+  L.xs = o; o += sizeof(double) * 2 * n;
+  L.us = o; o += sizeof(double) * n;
+  o = (o + 127) / 128 * 128;
+  L.tab = o; o += sizeof(DevTables);
+  L.mbar = o; o += 16;
+  L.total = (o + 15) / 16 * 16;
+  return L;
+}
+
+// writes one waypoint's rows straight into the QP's shared-memory description (CFS_FANUC.m:117-121)
+template <int NJ>
+struct RowSink {
+  const QpView &s;
+  const DevTables &tab;
+  const double *disp;  // (B_theta u)(i, 0..NJ) of the current iterate
+  int H, i, margin_is_D;
+  double gu[2];
+  __device__ __forceinline__ void grad(int j, int k, double v) {
+    s.ocoef[(j * H + i) * NJ + k] = -v;  // l = -Diff'*Bj(1:njoint,:)
+    gu[j & 1] += v * disp[k];
+  }
+  __device__ __forceinline__ void dist(int j, double d, int) {
+    const double margin = margin_is_D ? tab.obs[j].D : tab.obs[j].eps;
+    s.orhs[j * H + i] = (d - margin) - gu[j & 1];  // s = I - Diff'*Bj*u
+    gu[j & 1] = 0.0;
+  }
+};
+
+template <int NJ>
+__global__ void __launch_bounds__(QP_THREADS, 3) k_cfs_fused(SolveArgs a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int n = a.n, nj = NJ, H = a.H, np = 3 * n, OH = a.nobs * H, m = OH + 4 * n, N = 2 * n;
+  const int tid = threadIdx.x;
+  const FusedLayout L = fused_layout(n, nj, OH, m);
+  const QpView s = qp_view(smem_raw, n, nj, OH, m);
+  double *xs = reinterpret_cast<double *>(smem_raw + L.xs);  // x_  (CFS_FANUC.m:55)
+  double *us = reinterpret_cast<double *>(smem_raw + L.us);  // u   (CFS_FANUC.m:56)
+  DevTables &tab = *reinterpret_cast<DevTables *>(smem_raw + L.tab);
+  uint64_t *mbar = reinterpret_cast<uint64_t *>(smem_raw + L.mbar);
+  double(*sc)[NJ][GRAD_THREADS] = reinterpret_cast<double(*)[NJ][GRAD_THREADS]>(smem_raw);  // aliases the QP scratch span
+
+  tma_stage(&tab, a.tab, tab_bytes(a.nobs), mbar);
+  const double *__restrict__ G = a.G;
+  const int has_vel = a.has_lim, has_bnd = a.has_bounds;
+  for (int e = tid; e < 2 * n; e += QP_THREADS) s.gns[e] = a.gdiag[n + e];
+  for (int e = tid; e < n; e += QP_THREADS) s.ums[e] = has_bnd ? a.max_input[e] : 0.0;
+  const double dt = tab.dt;
+  const int ldg = a.slab_ld;
+  double *Mgl = a.slab + (size_t)blockIdx.x * ldg * ldg;
+  const QpDims dims = {n, nj, H, np, OH, m, has_vel, has_bnd, G, s.ums, Mgl, ldg, dt};
+  const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+  long long steps_total = 0;
+  int qmax_seen = 0;
+  long long pf[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  long long tck = 0;
+  const bool prof = a.prof != nullptr;
+
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) s.ctl[0] = atomicAdd(a.work_counter, 1);
+    __syncthreads();
+    const int b = s.ctl[0];
+    if (b >= a.B) break;
+    const double *x0 = a.x0 + (size_t)b * 2 * nj;
+    const double *v0 = a.v0 + (size_t)b * np;
+
+    // ---- problem set-up: u = 0, x_ = sys_info.x_, histories NaN, first stop test against x_old = ones (EVAL.m:47) ----
+    PF_START();
+    double part = 0.0;
+    for (int e = tid; e < N; e += QP_THREADS) {
+      const double xv = a.xref[(size_t)b * N + e];
+      xs[e] = xv;
+      part += (xv - 1.0) * (xv - 1.0);
+    }
+    for (int e = tid; e < n; e += QP_THREADS) us[e] = 0.0;
+    for (int e = tid; e < a.max_outer; e += QP_THREADS) {
+      a.cost_hist[(size_t)b * a.max_outer + e] = qnan;
+      if (a.e_u_hist) a.e_u_hist[(size_t)b * a.max_outer + e] = qnan;
+    }
+    for (int pi = tid; pi < np; pi += QP_THREADS) s.v0s[pi] = v0[pi];
+    if (tid < 8) {
+      s.lim[tid] = (tid < nj && has_vel) ? a.lim[tid] : 0.0;
+      s.w0[tid] = (tid < nj) ? x0[nj + tid] : 0.0;
+    }
+    const double nrm0 = sqrt(block_sum(part, s.red));
+    const double cost0 = a.cost0[b];
+    const double fupper = (has_bnd && a.fupper) ? a.fupper[b] : INFINITY;
+    int status = -1, iters = 0, touched = 0, steps_prob = 0;
+    if (nrm0 < a.eps_outer)
+      status = 0;
+    else if (1 > a.max_outer)
+      status = 1;
+    PF_ADD(0);
+    pf[6] += 1;
+
+    for (int it = 1; status < 0; ++it) {
+      // ---- get_con: distances + num_jac gradients of every waypoint, rows written in place (CFS_FANUC.m:110-124) ----
+      PF_START();
+      __syncthreads();  // the sin/cos cache aliases the previous QP's scratch
+      for (int i = tid; i < H; i += QP_THREADS) {
+        double disp[NJ];
+#pragma unroll
+        for (int k = 0; k < NJ; ++k)
+          disp[k] = (it == 1) ? 0.0 : xs[i * 2 * NJ + k] - (x0[k] + ((i + 1) * dt) * x0[NJ + k]);
+        RowSink<NJ> sink{s, tab, disp, H, i, a.margin_is_D, {0.0, 0.0}};
+        if (a.nobs <= 1)
+          numjac_waypoint<NJ, 1>(tab, sc, tid, xs + i * 2 * NJ, a.nobs, touched, sink);
+        else
+          numjac_waypoint<NJ, 2>(tab, sc, tid, xs + i * 2 * NJ, a.nobs, touched, sink);
+      }
+      __syncthreads();
+      for (int pi = tid; pi < np; pi += QP_THREADS) s.v[pi] = s.v0s[pi];
+      for (int e = tid; e < m; e += QP_THREADS) s.inact[e] = 0;
+      for (int cid = tid; cid < OH; cid += QP_THREADS) {
+        const Desc d = decode(cid, OH, H, n, nj, s.ocoef);
+        const double sg = gram(d, d, G, np);
+        s.onrm[cid] = sg > 0.0 ? sqrt(sg) : 0.0;
+      }
+      if (tid == 0) s.toff[0] = 0;
+      __syncthreads();
+      PF_ADD(0);
+
+      // ---- Solve_QP (CFS_FANUC.m:85) ----
+      int q = 0, steps = 0;
+      const int qst = qp_solve(s, dims, cost0, fupper, false, q, steps, qmax_seen, pf, tck, prof);
+      steps_total += steps;
+      steps_prob += steps;
+      if (qst != 0) {  // 2 infeasible / 3 numerical: u, x_ keep the previous iterate
+        status = qst;
+        break;
+      }
+      // ---- e_u, cost by duality, roll-out, stop rule (EVAL.m:51-73, CFS_FANUC.m:88-94) ----
+      double pe = 0.0;
+      for (int c = tid; c < n; c += QP_THREADS) {
+        const double un = s.v[2 * n + c];
+        const double dlt = us[c] - un;
+        pe += dlt * dlt;
+        us[c] = un;
+      }
+      const double e_u = sqrt(block_sum(pe, s.red));
+      double pc = 0.0;
+      for (int w = tid; w < q; w += QP_THREADS) pc += s.lam[w] * viol_at_u0(s.act[w], OH, H, n, nj, s, s.ums);
+      const double cost = cost0 + 0.5 * block_sum(pc, s.red);
+      double px = 0.0;
+      if (tid < nj) {
+        double th = x0[tid], om = x0[nj + tid];
+        for (int i = 0; i < H; ++i) {
+          const double uk = us[i * nj + tid];
+          const double thn = (th + dt * om) + (0.5 * dt * dt) * uk;
+          const double omn = om + dt * uk;
+          th = thn;
+          om = omn;
+          double *xr = xs + (size_t)i * 2 * nj;
+          const double d1 = th - xr[tid], d2 = om - xr[nj + tid];
+          px += d1 * d1 + d2 * d2;
+          xr[tid] = th;
+          xr[nj + tid] = om;
+        }
+      }
+      const double dx = sqrt(block_sum(px, s.red));
+      if (tid == 0) {
+        a.cost_hist[(size_t)b * a.max_outer + (it - 1)] = cost;
+        if (a.e_u_hist) a.e_u_hist[(size_t)b * a.max_outer + (it - 1)] = e_u;
+      }
+      iters = it;
+      if (dx < a.eps_outer)
+        status = 0;  // converged (EVAL.m:64-67)
+      else if (it + 1 > a.max_outer)
+        status = 1;  // MAX_ITER (EVAL.m:69-72)
+      PF_ADD(5);
+    }
+
+    // ---- results ----
+    __syncthreads();
+    for (int e = tid; e < n; e += QP_THREADS) a.u[(size_t)b * n + e] = us[e];
+    for (int e = tid; e < N; e += QP_THREADS) a.x[(size_t)b * N + e] = xs[e];
+    const int any_touch = __syncthreads_or(touched);
+    if (tid == 0) {
+      a.iters[b] = iters;
+      a.status[b] = status | (any_touch ? 0x100 : 0);
+      if (a.prob_steps) a.prob_steps[b] = steps_prob;
+    }
+  }
+  if (prof && tid == 0)
+    for (int k = 0; k < 8; ++k)
+      if (pf[k]) atomicAdd(reinterpret_cast<unsigned long long *>(a.prof + k), (unsigned long long)pf[k]);
+  if (tid == 0) {
+    if (steps_total) atomicAdd(reinterpret_cast<unsigned long long *>(a.qp_steps), (unsigned long long)steps_total);
+    if (qmax_seen) atomicMax(a.max_active, qmax_seen);
+  }
+}
+
+static bool fused_supported_nj(int nj) { return nj == 2 || nj == 5; }
+
+bool fused_supported(const SolveArgs &a) {
+  if (!fused_supported_nj(a.nj)) return false;
+  const int OH = a.nobs * a.H;
+  // the sin/cos cache must fit into the QP scratch span it aliases
+  return sizeof(double) * 6 * a.nj * GRAD_THREADS <= qp_scratch_span(a.n, a.nj, OH);
+}
+
+size_t fused_smem_bytes(const SolveArgs &a) {
+  const int OH = a.nobs * a.H;
+  return fused_layout(a.n, a.nj, OH, OH + 4 * a.n).total;
+}
+
+template <int NJ>
+static int fused_grid(const SolveArgs &a, int device) {
+  int sms = 0, per = 0;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  const size_t smem = fused_smem_bytes(a);
+  if (cudaFuncSetAttribute(k_cfs_fused<NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_cfs_fused<NJ>, QP_THREADS, smem);
+  return sms * per;
+}
+
+int fused_max_grid(const SolveArgs &a, int device) {
+  switch (a.nj) {
+    case 2: return fused_grid<2>(a, device);
+    case 5: return fused_grid<5>(a, device);
+    default: return 0;
+  }
+}
+
+cudaError_t launch_fused(const SolveArgs &a, int grid, cudaStream_t st) {
+  const size_t smem = fused_smem_bytes(a);
+  switch (a.nj) {
+    case 2: k_cfs_fused<2><<<grid, QP_THREADS, smem, st>>>(a); break;
+    case 5: k_cfs_fused<5><<<grid, QP_THREADS, smem, st>>>(a); break;
+    default: return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
+}
+
+}  // namespace cfs

@@ -15,12 +15,10 @@
 // K6  replaces RRT_FANUC.feasible (Lib/RRT_FANUC.m:146-181) and the nearest/steer scan (:116-129).
 #include "cfs_geom.cuh"
 #include "cfs_kernels.cuh"
+#include "cfs_numjac.cuh"
 
 namespace cfs {
 
-#define GRAD_THREADS 128
-
-__device__ __forceinline__ double min_first(double cur, double cand) { return cand < cur ? cand : cur; }
 
 // ============================================================================================================
 // K1: num_jac
@@ -43,115 +41,19 @@ __global__ void __launch_bounds__(GRAD_THREADS) k_grad_numjac(GradArgs a) {
   const int prob = a.list ? a.list[slot] : slot;
   const double *thp = a.x + prob * a.ld_prob + i * a.ld_i;
 
-  const double hh = CFS_NUMJAC_EPS / 2;  // num_jac.m:11,13
-#pragma unroll
-  for (int k = 0; k < NJ; ++k) {
-    const double th = thp[k];
-    const double off = tab.link[k].th_off;
-    double s, c;
-    sincos(th + off, &s, &c);
-    sc[0][k][tid] = c;
-    sc[1][k][tid] = s;
-    sincos((th + hh) + off, &s, &c);
-    sc[2][k][tid] = c;
-    sc[3][k][tid] = s;
-    sincos((th - hh) + off, &s, &c);
-    sc[4][k][tid] = c;
-    sc[5][k][tid] = s;
-  }
   int touched = 0;
-  const int nobs = a.nobs;
-
-  for (int j0 = 0; j0 < nobs; j0 += OC) {
-    double dbase[OC], dpre[OC];
-    int lid[OC];
-#pragma unroll
-    for (int jj = 0; jj < OC; ++jj) {
-      dbase[jj] = INFINITY;
-      dpre[jj] = INFINITY;
-      lid[jj] = 0;
+  struct Sink {
+    const GradArgs &a;
+    long long prob;
+    int i;
+    __device__ __forceinline__ long long idx(int j) const { return prob * a.o_prob + (long long)j * a.o_obs + i * a.o_i; }
+    __device__ __forceinline__ void grad(int j, int k, double v) const { a.grad[idx(j) * NJ + k] = v; }
+    __device__ __forceinline__ void dist(int j, double d, int lid) const {
+      a.dist[idx(j)] = d;
+      if (a.linkid) a.linkid[idx(j)] = lid;
     }
-    Xf M, Mn, Pm;
-    double p[6];
-    // ---- y = f(x): base evaluation, gives distance and linkid (CFS_FANUC.m:115) ----
-#pragma unroll 1
-    for (int l = 0; l < NJ; ++l) {
-      if (l == 0) {
-        xf_first(tab.link[0], sc[0][0][tid], sc[1][0][tid], M);
-      } else {
-        xf_step(M, tab.link[l], sc[0][l][tid], sc[1][l][tid], Mn);
-        M = Mn;
-      }
-      link_endpoints(M, tab.link[l], tab.base, p);
-#pragma unroll
-      for (int jj = 0; jj < OC; ++jj)
-        if (j0 + jj < nobs) {
-          const double d = link_obs_dist(p, tab.obs[j0 + jj], touched);
-          if (d < dbase[jj]) {  // strict <: first minimal link (dist_arm_3D_Heu_2.m:25-28)
-            dbase[jj] = d;
-            lid[jj] = l + 1;
-          }
-        }
-    }
-    // ---- columns of num_jac ----
-#pragma unroll 1
-    for (int k = 0; k < NJ; ++k) {
-      double dpl[OC], dmi[OC], dk[OC];
-      // yhi = f(xp), xp(k) = x(k)+eps/2, joints < k at x-eps/2
-      if (k == 0)
-        xf_first(tab.link[0], sc[2][0][tid], sc[3][0][tid], M);
-      else
-        xf_step(Pm, tab.link[k], sc[2][k][tid], sc[3][k][tid], M);
-      link_endpoints(M, tab.link[k], tab.base, p);
-#pragma unroll
-      for (int jj = 0; jj < OC; ++jj)
-        dpl[jj] = (j0 + jj < nobs) ? min_first(dpre[jj], link_obs_dist(p, tab.obs[j0 + jj], touched)) : 0.0;
-#pragma unroll 1
-      for (int l = k + 1; l < NJ; ++l) {
-        xf_step(M, tab.link[l], sc[0][l][tid], sc[1][l][tid], Mn);
-        M = Mn;
-        link_endpoints(M, tab.link[l], tab.base, p);
-#pragma unroll
-        for (int jj = 0; jj < OC; ++jj)
-          if (j0 + jj < nobs) dpl[jj] = min_first(dpl[jj], link_obs_dist(p, tab.obs[j0 + jj], touched));
-      }
-      // ylo = f(xp), xp(k) = x(k)-eps/2
-      if (k == 0)
-        xf_first(tab.link[0], sc[4][0][tid], sc[5][0][tid], M);
-      else
-        xf_step(Pm, tab.link[k], sc[4][k][tid], sc[5][k][tid], M);
-      Pm = M;  // running prefix M_1^- ... M_k^-
-      link_endpoints(M, tab.link[k], tab.base, p);
-#pragma unroll
-      for (int jj = 0; jj < OC; ++jj) {
-        dk[jj] = (j0 + jj < nobs) ? link_obs_dist(p, tab.obs[j0 + jj], touched) : 0.0;
-        dmi[jj] = min_first(dpre[jj], dk[jj]);
-      }
-#pragma unroll 1
-      for (int l = k + 1; l < NJ; ++l) {
-        xf_step(M, tab.link[l], sc[0][l][tid], sc[1][l][tid], Mn);
-        M = Mn;
-        link_endpoints(M, tab.link[l], tab.base, p);
-#pragma unroll
-        for (int jj = 0; jj < OC; ++jj)
-          if (j0 + jj < nobs) dmi[jj] = min_first(dmi[jj], link_obs_dist(p, tab.obs[j0 + jj], touched));
-      }
-#pragma unroll
-      for (int jj = 0; jj < OC; ++jj)
-        if (j0 + jj < nobs) {
-          const long long o = prob * a.o_prob + (long long)(j0 + jj) * a.o_obs + i * a.o_i;
-          a.grad[o * NJ + k] = (dpl[jj] - dmi[jj]) / CFS_NUMJAC_EPS;  // num_jac.m:15
-          dpre[jj] = min_first(dpre[jj], dk[jj]);
-        }
-    }
-#pragma unroll
-    for (int jj = 0; jj < OC; ++jj)
-      if (j0 + jj < nobs) {
-        const long long o = prob * a.o_prob + (long long)(j0 + jj) * a.o_obs + i * a.o_i;
-        a.dist[o] = dbase[jj];
-        if (a.linkid) a.linkid[o] = lid[jj];
-      }
-  }
+  } out{a, prob, i};
+  numjac_waypoint<NJ, OC>(tab, sc, tid, thp, a.nobs, touched, out);
   if (touched && a.flags) atomicOr(&a.flags[prob], 0x100);
 }
 

@@ -139,17 +139,22 @@ def test_main_2l_solve_parity(ctx, oracle):
     _compare_solve(out, ref)
 
 
-def test_batch_m16ib_solve_parity(ctx, oracle):
-    """Seeded random start/goal batch at the headline configuration (H=50), including infeasible problems."""
+@pytest.mark.parametrize("fused", [1, 0])
+def test_batch_m16ib_solve_parity(ctx, oracle, fused):
+    """Seeded random start/goal batch at the headline configuration (H=50), including infeasible problems; through the
+    fused persistent kernel (default) and through the launch-per-iteration path."""
     O = oracle
+    ctx.set_option("fused", fused)
     cfg = common.batch_m16ib(O, 192)
     s = cfg["sys_info"]
     _set(ctx, "M16iB", cfg["robot"], cfg["obs"], s)
     P = common.oracle_problem(O, "M16iB", cfg["obs"], s)
     ref = P.solve_batch(cfg["x0"], cfg["ff"], cfg["caug"], cfg["xref"], nthreads=8)
     out = ctx.solve_batch(cfg["x0"], cfg["ff"], cfg["caug"], cfg["xref"], s["epsilon_O"], s["MAX_O_ITER"])
+    ctx.set_option("fused", 1)
     assert ((ref["status"] & 0xFF) == 2).any() and ((ref["status"] & 0xFF) == 0).any()
     _compare_solve(out, ref)
+    assert ctx.stats()["launches"] == (3 if fused else 44)
 
 
 def test_psgcfs_main_fanuc_parity(ctx, oracle):
@@ -184,7 +189,15 @@ def test_psgcfs_batch_parity(ctx, oracle):
     out = ctx.solve_batch(cfg["x0"], cfg["ff"], cfg["caug"], cfg["xref"], s["epsilon_O"], 8, solver=_lib.SOLVER_PSGCFS,
                           noise=noise, alpha=s["alpha"])
     assert ((ref["status"] & 0xFF) == 1).any()
-    _compare_solve(out, ref)
+    # Controls within 1e-6.  Trajectories: 1e-6 for all but kink-amplified problems.  num_jac (eps = 1e-5) turns the
+    # ~1e-15 evaluation noise of two different FP64 FK implementations (CUDA sincos/FMA vs libm) into ~1e-10 gradient
+    # noise; with noise-driven PSG steps a problem sitting on a closest-link kink doubles that per iteration (measured:
+    # 1e-9 -> 3e-8 in u over 8 iterations for one problem of 96, DESIGN.md "parity noise floor").  Rolled out over H
+    # steps this is x 70, hence 1e-5 on x for the outliers and 1e-6 for at least 98 % of the problems.
+    _compare_solve(out, ref, tol_x=1e-5, tol_u=1e-6)
+    ok = (ref["status"] & 0xFF) < 2
+    dx = np.abs(out["x"][ok] - ref["x"][ok]).max(axis=1)
+    assert (dx < 1e-6).mean() >= 0.98, np.sort(dx)[-5:]
 
 
 @pytest.mark.parametrize("name", ["main_fanuc_cfs", "main_fanuc_psgcfs", "main_2l_cfs", "m16ib_script_derivest",
