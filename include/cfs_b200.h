@@ -63,7 +63,8 @@ int cfs_set_stream(cfs_ctx *ctx, void *cuda_stream);
 
 /* Options: "fused" (default 1): solve CFS / num_jac batches with the persistent fused kernel (one CTA carries a problem
  * through all outer iterations); 0 = one gradient launch + one QP launch per outer iteration (the path PSGCFS and the
- * DERIVEST gradients always take). */
+ * DERIVEST gradients always take).  "esc_steps" (default 48): dual active-set steps one QP may take in the fused
+ * kernel's bulk tier before the problem is handed to its heavy tier (0 = never). */
 int cfs_set_option(cfs_ctx *ctx, const char *name, int value);
 
 /* ---- problem data ------------------------------------------------------------------------------------- */

@@ -56,6 +56,7 @@ struct cfs_ctx {
   cudaEvent_t ev_a = nullptr, ev_b = nullptr;
   int timing_level = 1;
   bool use_fused = true;  // cfs_set_option("fused")
+  int esc_steps = 48;     // cfs_set_option("esc_steps")
   std::vector<double> it_grad_ms, it_qp_ms;
   cfs_stats stats;
 };
@@ -428,8 +429,10 @@ static int solve_device(cfs_ctx *ctx, int B, int solver, int grad, const double 
   a.slab_ld = n;
 
   const bool fused = ctx->use_fused && !psg && grad == CFS_GRAD_NUMJAC && fused_supported(a);
-  int grid = fused ? fused_max_grid(a, ctx->device) : qp_max_grid(a, ctx->device);
-  if (grid <= 0) return fail(ctx, CFS_E_CUDA, "solver kernel does not fit on this device (shared memory)");
+  int grid = fused ? fused_max_grid(a, ctx->device, 0) : qp_max_grid(a, ctx->device);
+  int grid_heavy = fused ? fused_max_grid(a, ctx->device, 1) : 0;
+  if (grid <= 0 || (fused && grid_heavy <= 0))
+    return fail(ctx, CFS_E_CUDA, "solver kernel does not fit on this device (shared memory)");
   {
     int sms = 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
@@ -437,7 +440,8 @@ static int solve_device(cfs_ctx *ctx, int B, int solver, int grad, const double 
   }
   if (grid > B) grid = B;
   if (grid < 1) grid = 1;
-  if ((rc = ensure(ctx, ctx->slab, sizeof(double) * (size_t)n * n * grid))) return rc;
+  if (grid_heavy > B) grid_heavy = B;
+  if ((rc = ensure(ctx, ctx->slab, sizeof(double) * (size_t)n * n * (grid > grid_heavy ? grid : grid_heavy)))) return rc;
   a.slab = ptr<double>(ctx->slab);
 
   const bool detail = ctx->timing_level >= 2;
@@ -459,7 +463,12 @@ static int solve_device(cfs_ctx *ctx, int B, int solver, int grad, const double 
     // one persistent kernel: every CTA carries a problem through all its outer iterations (k_fused.cu)
     CU(launch_dgemm(n, B, n, -1.0, ctx->dG + (size_t)2 * n * np + 2 * n, np, false, ff, n, a.u0, n, st)); ++launches;
     CU(launch_v0(a, st)); ++launches;
-    CU(launch_fused(a, grid, st)); ++launches;
+    a.esc_list = ptr<int>(ctx->listA);
+    a.esc_count = cnt + 5;
+    a.work_counter2 = cnt + 4;
+    a.esc_steps = ctx->esc_steps;
+    CU(launch_fused(a, grid, 0, st)); ++launches;        // bulk tier: every problem
+    CU(launch_fused(a, grid_heavy, 1, st)); ++launches;  // heavy tier: the (device-side) escalation list, usually < 1 %
     CU(cudaEventRecord(ctx->ev_b, st));
     ctx->stats.launches = launches;
     return 0;
@@ -534,7 +543,7 @@ static int collect_stats(cfs_ctx *ctx, int B, int max_outer, const int *d_iters,
   ctx->stats.ms_grad = ctx->stats.ms_qp = 0;
   ctx->it_grad_ms.clear();
   ctx->it_qp_ms.clear();
-  if (ctx->timing_level >= 2 && ctx->ev.size() >= (size_t)3 * max_outer && ctx->stats.launches > 3) {
+  if (ctx->timing_level >= 2 && ctx->ev.size() >= (size_t)3 * max_outer && ctx->stats.launches > 4) {
     for (int k = 0; k < max_outer; ++k) {
       float a = 0, b = 0;
       cudaEventElapsedTime(&a, ctx->ev[3 * k], ctx->ev[3 * k + 1]);
@@ -792,6 +801,10 @@ extern "C" int cfs_set_option(cfs_ctx *ctx, const char *name, int value) {
   if (!ctx || !name) return CFS_E_ARG;
   if (strcmp(name, "fused") == 0) {
     ctx->use_fused = value != 0;
+    return 0;
+  }
+  if (strcmp(name, "esc_steps") == 0) {
+    ctx->esc_steps = value > 0 ? value : 0x7fffffff;
     return 0;
   }
   return fail(ctx, CFS_E_ARG, "cfs_set_option: unknown option '%s'", name);

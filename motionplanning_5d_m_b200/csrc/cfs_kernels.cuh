@@ -82,6 +82,11 @@ struct SolveArgs {
   double *w;                  // n x B   QQ*u of the current iterate (batched GEMM after every projection)
   double *cost_old, *cost_new;  // B     EVAL.cost_old / cost_new (EVAL.m:29, PSGCFS_FANUC.m:66,76,90)
   int *skip;                  // B       stop_inner() was already true: no PSG step this outer iteration (PSGCFS_FANUC.m:88,136-142)
+  // fused kernel tiers (k_fused.cu)
+  int tier;                   // 0 bulk (all B problems), 1 heavy (the escalation list)
+  int *esc_list, *esc_count;  // problems the bulk tier handed over (working set outgrew shared memory / step cap)
+  int *work_counter2;         // work queue of the heavy tier
+  int esc_steps;              // bulk tier: dual steps per QP before escalation
   long long *prof;            // optional 8-slot phase profile of k_qp (clock64 ticks of thread 0), or nullptr
 };
 cudaError_t launch_solve_init(const SolveArgs &a, cudaStream_t s);
@@ -95,9 +100,9 @@ cudaError_t launch_finalize(const SolveArgs &a, cudaStream_t s);
 
 // ---- fused persistent solver: the whole CFS outer loop of a problem inside one CTA (k_fused.cu) -------------------------
 bool fused_supported(const SolveArgs &a);  // CFS solver, num_jac gradients, nj in {2, 5}
-size_t fused_smem_bytes(const SolveArgs &a);
-int fused_max_grid(const SolveArgs &a, int device);
-cudaError_t launch_fused(const SolveArgs &a, int grid, cudaStream_t s);
+size_t fused_smem_bytes(const SolveArgs &a, int tier);
+int fused_max_grid(const SolveArgs &a, int device, int tier);
+cudaError_t launch_fused(const SolveArgs &a, int grid, int tier, cudaStream_t s);
 
 // ---- dense get_con rows (one problem) -------------------------------------------------------------------------
 cudaError_t launch_get_con_rows(const DevTables *tab, int H, int nj, int nobs, int has_lim, int margin_is_D,

@@ -11,11 +11,11 @@ namespace cfs {
 
 __device__ __forceinline__ double min_first(double cur, double cand) { return cand < cur ? cand : cur; }
 
-// sc: this CTA's sin/cos cache [6 kinds][NJ][GRAD_THREADS] in shared memory (kinds: c0,s0 at theta; cp,sp at
+// sc: this CTA's sin/cos cache [6 kinds][NJ][NT threads] in shared memory (kinds: c0,s0 at theta; cp,sp at
 // theta+eps/2; cm,sm at theta-eps/2), column `tid` belongs to the calling thread.  thp: the NJ joint angles.
 // out.grad(j, k, value) receives Diff(k) for obstacle j, out.dist(j, distance, linkid) the base evaluation.
-template <int NJ, int OC, class Out>
-__device__ __forceinline__ void numjac_waypoint(const DevTables &tab, double (*sc)[NJ][GRAD_THREADS], int tid,
+template <int NJ, int OC, int NT, class Out>
+__device__ __forceinline__ void numjac_waypoint(const DevTables &tab, double (*sc)[NJ][NT], int tid,
                                                 const double *thp, int nobs, int &touched, Out &out) {
   const double hh = CFS_NUMJAC_EPS / 2;  // num_jac.m:11,13
 #pragma unroll

@@ -13,21 +13,28 @@
 //     H = 50), the batch-shared Gram operator G (4.5 MB) streams from L2;
 //   * the robot/obstacle tables are staged once per CTA with one TMA bulk copy (UBLKCP), the 30 sin/cos values of a
 //     waypoint's 11 num_jac evaluations are cached in shared memory that the QP phase reuses for its working-set inverse.
+//   * two tiers of the same code: the bulk tier (128 threads, 3 CTAs/SM, working-set inverse up to 48 x 48 in shared
+//     memory) hands the rare QP whose working set outgrows that, or that needs more than esc_steps dual steps (almost
+//     always an infeasible linearisation on its way to the infeasibility certificate), to the heavy tier (256 threads,
+//     1 CTA/SM, 128 x 128 inverse on chip), which resumes the problem from its last completed outer iteration.
 #include "cfs_numjac.cuh"
 #include "qp_core.cuh"
 
 namespace cfs {
 
-static_assert(QP_THREADS == GRAD_THREADS, "the sin/cos cache is indexed by the QP thread id");
+#define FUSED_BULK_NT 128
+#define FUSED_BULK_QS QP_QS
+#define FUSED_HEAVY_NT 256
+#define FUSED_HEAVY_QS 128
 
 struct FusedLayout {
   size_t qp_bytes, xs, us, tab, mbar, total;
 };
 
-__host__ __device__ inline FusedLayout fused_layout(int n, int nj, int OH, int m) {
+__host__ __device__ inline FusedLayout fused_layout(int n, int nj, int OH, int m, int qs, int nt) {
   FusedLayout L;
   size_t off[QP_NOFF];
-  L.qp_bytes = qp_smem_layout(n, nj, OH, m, off);
+  L.qp_bytes = qp_smem_layout(n, nj, OH, m, off, qs, nt);
   size_t o = L.qp_bytes;
   L.xs = o; o += sizeof(double) * 2 * n;
   L.us = o; o += sizeof(double) * n;
@@ -57,24 +64,25 @@ struct RowSink {
   }
 };
 
-template <int NJ>
-__global__ void __launch_bounds__(QP_THREADS, 3) k_cfs_fused(SolveArgs a) {
+template <int NJ, int NT, int QS, int MINB>
+__global__ void __launch_bounds__(NT, MINB) k_cfs_fused(SolveArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int n = a.n, nj = NJ, H = a.H, np = 3 * n, OH = a.nobs * H, m = OH + 4 * n, N = 2 * n;
   const int tid = threadIdx.x;
-  const FusedLayout L = fused_layout(n, nj, OH, m);
-  const QpView s = qp_view(smem_raw, n, nj, OH, m);
+  const FusedLayout L = fused_layout(n, nj, OH, m, QS, NT);
+  const QpView s = qp_view(smem_raw, n, nj, OH, m, QS, NT);
+  const bool heavy = a.tier == 1;
   double *xs = reinterpret_cast<double *>(smem_raw + L.xs);  // x_  (CFS_FANUC.m:55)
   double *us = reinterpret_cast<double *>(smem_raw + L.us);  // u   (CFS_FANUC.m:56)
   DevTables &tab = *reinterpret_cast<DevTables *>(smem_raw + L.tab);
   uint64_t *mbar = reinterpret_cast<uint64_t *>(smem_raw + L.mbar);
-  double(*sc)[NJ][GRAD_THREADS] = reinterpret_cast<double(*)[NJ][GRAD_THREADS]>(smem_raw);  // aliases the QP scratch span
+  double(*sc)[NJ][NT] = reinterpret_cast<double(*)[NJ][NT]>(smem_raw);  // aliases the QP scratch span
 
   tma_stage(&tab, a.tab, tab_bytes(a.nobs), mbar);
   const double *__restrict__ G = a.G;
   const int has_vel = a.has_lim, has_bnd = a.has_bounds;
-  for (int e = tid; e < 2 * n; e += QP_THREADS) s.gns[e] = a.gdiag[n + e];
-  for (int e = tid; e < n; e += QP_THREADS) s.ums[e] = has_bnd ? a.max_input[e] : 0.0;
+  for (int e = tid; e < 2 * n; e += NT) s.gns[e] = a.gdiag[n + e];
+  for (int e = tid; e < n; e += NT) s.ums[e] = has_bnd ? a.max_input[e] : 0.0;
   const double dt = tab.dt;
   const int ldg = a.slab_ld;
   double *Mgl = a.slab + (size_t)blockIdx.x * ldg * ldg;
@@ -86,63 +94,75 @@ __global__ void __launch_bounds__(QP_THREADS, 3) k_cfs_fused(SolveArgs a) {
   long long tck = 0;
   const bool prof = a.prof != nullptr;
 
+  const int count = heavy ? *a.esc_count : a.B;
   for (;;) {
     __syncthreads();
-    if (tid == 0) s.ctl[0] = atomicAdd(a.work_counter, 1);
+    if (tid == 0) s.ctl[0] = atomicAdd(heavy ? a.work_counter2 : a.work_counter, 1);
     __syncthreads();
-    const int b = s.ctl[0];
-    if (b >= a.B) break;
+    const int slot = s.ctl[0];
+    if (slot >= count) break;
+    const int b = heavy ? a.esc_list[slot] : slot;
     const double *x0 = a.x0 + (size_t)b * 2 * nj;
     const double *v0 = a.v0 + (size_t)b * np;
 
     // ---- problem set-up: u = 0, x_ = sys_info.x_, histories NaN, first stop test against x_old = ones (EVAL.m:47) ----
     PF_START();
     double part = 0.0;
-    for (int e = tid; e < N; e += QP_THREADS) {
-      const double xv = a.xref[(size_t)b * N + e];
-      xs[e] = xv;
-      part += (xv - 1.0) * (xv - 1.0);
+    if (!heavy) {
+      for (int e = tid; e < N; e += NT) {
+        const double xv = a.xref[(size_t)b * N + e];
+        xs[e] = xv;
+        part += (xv - 1.0) * (xv - 1.0);
+      }
+      for (int e = tid; e < n; e += NT) us[e] = 0.0;
+      for (int e = tid; e < a.max_outer; e += NT) {
+        a.cost_hist[(size_t)b * a.max_outer + e] = qnan;
+        if (a.e_u_hist) a.e_u_hist[(size_t)b * a.max_outer + e] = qnan;
+      }
+    } else {  // resume from the last completed outer iteration (written by the bulk tier)
+      for (int e = tid; e < N; e += NT) xs[e] = a.x[(size_t)b * N + e];
+      for (int e = tid; e < n; e += NT) us[e] = a.u[(size_t)b * n + e];
     }
-    for (int e = tid; e < n; e += QP_THREADS) us[e] = 0.0;
-    for (int e = tid; e < a.max_outer; e += QP_THREADS) {
-      a.cost_hist[(size_t)b * a.max_outer + e] = qnan;
-      if (a.e_u_hist) a.e_u_hist[(size_t)b * a.max_outer + e] = qnan;
-    }
-    for (int pi = tid; pi < np; pi += QP_THREADS) s.v0s[pi] = v0[pi];
+    for (int pi = tid; pi < np; pi += NT) s.v0s[pi] = v0[pi];
     if (tid < 8) {
       s.lim[tid] = (tid < nj && has_vel) ? a.lim[tid] : 0.0;
       s.w0[tid] = (tid < nj) ? x0[nj + tid] : 0.0;
     }
-    const double nrm0 = sqrt(block_sum(part, s.red));
+    const double nrm0 = sqrt(block_sum<NT>(part, s.red));
     const double cost0 = a.cost0[b];
     const double fupper = (has_bnd && a.fupper) ? a.fupper[b] : INFINITY;
     int status = -1, iters = 0, touched = 0, steps_prob = 0;
-    if (nrm0 < a.eps_outer)
+    if (heavy) {
+      iters = a.iters[b];
+      touched = (tid == 0) ? (a.status[b] & 0x100) : 0;
+      steps_prob = a.prob_steps ? a.prob_steps[b] : 0;
+    } else if (nrm0 < a.eps_outer) {
       status = 0;
-    else if (1 > a.max_outer)
+    } else if (1 > a.max_outer) {
       status = 1;
+    }
     PF_ADD(0);
     pf[6] += 1;
 
-    for (int it = 1; status < 0; ++it) {
+    for (int it = iters + 1; status < 0; ++it) {
       // ---- get_con: distances + num_jac gradients of every waypoint, rows written in place (CFS_FANUC.m:110-124) ----
       PF_START();
       __syncthreads();  // the sin/cos cache aliases the previous QP's scratch
-      for (int i = tid; i < H; i += QP_THREADS) {
+      for (int i = tid; i < H; i += NT) {
         double disp[NJ];
 #pragma unroll
         for (int k = 0; k < NJ; ++k)
           disp[k] = (it == 1) ? 0.0 : xs[i * 2 * NJ + k] - (x0[k] + ((i + 1) * dt) * x0[NJ + k]);
         RowSink<NJ> sink{s, tab, disp, H, i, a.margin_is_D, {0.0, 0.0}};
         if (a.nobs <= 1)
-          numjac_waypoint<NJ, 1>(tab, sc, tid, xs + i * 2 * NJ, a.nobs, touched, sink);
+          numjac_waypoint<NJ, 1, NT>(tab, sc, tid, xs + i * 2 * NJ, a.nobs, touched, sink);
         else
-          numjac_waypoint<NJ, 2>(tab, sc, tid, xs + i * 2 * NJ, a.nobs, touched, sink);
+          numjac_waypoint<NJ, 2, NT>(tab, sc, tid, xs + i * 2 * NJ, a.nobs, touched, sink);
       }
       __syncthreads();
-      for (int pi = tid; pi < np; pi += QP_THREADS) s.v[pi] = s.v0s[pi];
-      for (int e = tid; e < m; e += QP_THREADS) s.inact[e] = 0;
-      for (int cid = tid; cid < OH; cid += QP_THREADS) {
+      for (int pi = tid; pi < np; pi += NT) s.v[pi] = s.v0s[pi];
+      for (int e = tid; e < m; e += NT) s.inact[e] = 0;
+      for (int cid = tid; cid < OH; cid += NT) {
         const Desc d = decode(cid, OH, H, n, nj, s.ocoef);
         const double sg = gram(d, d, G, np);
         s.onrm[cid] = sg > 0.0 ? sqrt(sg) : 0.0;
@@ -153,25 +173,26 @@ __global__ void __launch_bounds__(QP_THREADS, 3) k_cfs_fused(SolveArgs a) {
 
       // ---- Solve_QP (CFS_FANUC.m:85) ----
       int q = 0, steps = 0;
-      const int qst = qp_solve(s, dims, cost0, fupper, false, q, steps, qmax_seen, pf, tck, prof);
+      const int qst = qp_solve<NT, QS>(s, dims, cost0, fupper, false, q, steps, qmax_seen, pf, tck, prof,
+                                       heavy ? 0x7fffffff : a.esc_steps, !heavy);
       steps_total += steps;
       steps_prob += steps;
-      if (qst != 0) {  // 2 infeasible / 3 numerical: u, x_ keep the previous iterate
+      if (qst != 0) {  // 2 infeasible / 3 numerical: u, x_ keep the previous iterate; 4: the heavy tier redoes this iteration
         status = qst;
         break;
       }
       // ---- e_u, cost by duality, roll-out, stop rule (EVAL.m:51-73, CFS_FANUC.m:88-94) ----
       double pe = 0.0;
-      for (int c = tid; c < n; c += QP_THREADS) {
+      for (int c = tid; c < n; c += NT) {
         const double un = s.v[2 * n + c];
         const double dlt = us[c] - un;
         pe += dlt * dlt;
         us[c] = un;
       }
-      const double e_u = sqrt(block_sum(pe, s.red));
+      const double e_u = sqrt(block_sum<NT>(pe, s.red));
       double pc = 0.0;
-      for (int w = tid; w < q; w += QP_THREADS) pc += s.lam[w] * viol_at_u0(s.act[w], OH, H, n, nj, s, s.ums);
-      const double cost = cost0 + 0.5 * block_sum(pc, s.red);
+      for (int w = tid; w < q; w += NT) pc += s.lam[w] * viol_at_u0(s.act[w], OH, H, n, nj, s, s.ums);
+      const double cost = cost0 + 0.5 * block_sum<NT>(pc, s.red);
       double px = 0.0;
       if (tid < nj) {
         double th = x0[tid], om = x0[nj + tid];
@@ -188,7 +209,7 @@ __global__ void __launch_bounds__(QP_THREADS, 3) k_cfs_fused(SolveArgs a) {
           xr[nj + tid] = om;
         }
       }
-      const double dx = sqrt(block_sum(px, s.red));
+      const double dx = sqrt(block_sum<NT>(px, s.red));
       if (tid == 0) {
         a.cost_hist[(size_t)b * a.max_outer + (it - 1)] = cost;
         if (a.e_u_hist) a.e_u_hist[(size_t)b * a.max_outer + (it - 1)] = e_u;
@@ -203,13 +224,14 @@ __global__ void __launch_bounds__(QP_THREADS, 3) k_cfs_fused(SolveArgs a) {
 
     // ---- results ----
     __syncthreads();
-    for (int e = tid; e < n; e += QP_THREADS) a.u[(size_t)b * n + e] = us[e];
-    for (int e = tid; e < N; e += QP_THREADS) a.x[(size_t)b * N + e] = xs[e];
+    for (int e = tid; e < n; e += NT) a.u[(size_t)b * n + e] = us[e];
+    for (int e = tid; e < N; e += NT) a.x[(size_t)b * N + e] = xs[e];
     const int any_touch = __syncthreads_or(touched);
     if (tid == 0) {
       a.iters[b] = iters;
       a.status[b] = status | (any_touch ? 0x100 : 0);
       if (a.prob_steps) a.prob_steps[b] = steps_prob;
+      if (status == 4) a.esc_list[atomicAdd(a.esc_count, 1)] = b;
     }
   }
   if (prof && tid == 0)
@@ -223,42 +245,64 @@ __global__ void __launch_bounds__(QP_THREADS, 3) k_cfs_fused(SolveArgs a) {
 
 static bool fused_supported_nj(int nj) { return nj == 2 || nj == 5; }
 
+static void tier_cfg(int tier, int &nt, int &qs) {
+  nt = tier ? FUSED_HEAVY_NT : FUSED_BULK_NT;
+  qs = tier ? FUSED_HEAVY_QS : FUSED_BULK_QS;
+}
+
+size_t fused_smem_bytes(const SolveArgs &a, int tier) {
+  int nt, qs;
+  tier_cfg(tier, nt, qs);
+  const int OH = a.nobs * a.H;
+  return fused_layout(a.n, a.nj, OH, OH + 4 * a.n, qs, nt).total;
+}
+
 bool fused_supported(const SolveArgs &a) {
   if (!fused_supported_nj(a.nj)) return false;
   const int OH = a.nobs * a.H;
-  // the sin/cos cache must fit into the QP scratch span it aliases
-  return sizeof(double) * 6 * a.nj * GRAD_THREADS <= qp_scratch_span(a.n, a.nj, OH);
+  for (int tier = 0; tier < 2; ++tier) {
+    int nt, qs;
+    tier_cfg(tier, nt, qs);
+    // the sin/cos cache must fit into the QP scratch span it aliases, and the CTA into one SM's shared memory
+    if (sizeof(double) * 6 * a.nj * nt > qp_scratch_span(a.n, a.nj, OH, qs)) return false;
+    if (fused_smem_bytes(a, tier) > 227 * 1024) return false;
+  }
+  return true;
 }
 
-size_t fused_smem_bytes(const SolveArgs &a) {
-  const int OH = a.nobs * a.H;
-  return fused_layout(a.n, a.nj, OH, OH + 4 * a.n).total;
-}
-
-template <int NJ>
-static int fused_grid(const SolveArgs &a, int device) {
+template <class K>
+static int grid_of(K kernel, int nt, size_t smem, int device) {
   int sms = 0, per = 0;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-  const size_t smem = fused_smem_bytes(a);
-  if (cudaFuncSetAttribute(k_cfs_fused<NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_cfs_fused<NJ>, QP_THREADS, smem);
+  if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, kernel, nt, smem);
   return sms * per;
 }
 
-int fused_max_grid(const SolveArgs &a, int device) {
-  switch (a.nj) {
-    case 2: return fused_grid<2>(a, device);
-    case 5: return fused_grid<5>(a, device);
-    default: return 0;
+int fused_max_grid(const SolveArgs &a, int device, int tier) {
+  const size_t smem = fused_smem_bytes(a, tier);
+  if (tier == 0) {
+    if (a.nj == 2) return grid_of(k_cfs_fused<2, FUSED_BULK_NT, FUSED_BULK_QS, 3>, FUSED_BULK_NT, smem, device);
+    if (a.nj == 5) return grid_of(k_cfs_fused<5, FUSED_BULK_NT, FUSED_BULK_QS, 3>, FUSED_BULK_NT, smem, device);
+  } else {
+    if (a.nj == 2) return grid_of(k_cfs_fused<2, FUSED_HEAVY_NT, FUSED_HEAVY_QS, 1>, FUSED_HEAVY_NT, smem, device);
+    if (a.nj == 5) return grid_of(k_cfs_fused<5, FUSED_HEAVY_NT, FUSED_HEAVY_QS, 1>, FUSED_HEAVY_NT, smem, device);
   }
+  return 0;
 }
 
-cudaError_t launch_fused(const SolveArgs &a, int grid, cudaStream_t st) {
-  const size_t smem = fused_smem_bytes(a);
-  switch (a.nj) {
-    case 2: k_cfs_fused<2><<<grid, QP_THREADS, smem, st>>>(a); break;
-    case 5: k_cfs_fused<5><<<grid, QP_THREADS, smem, st>>>(a); break;
-    default: return cudaErrorInvalidValue;
+cudaError_t launch_fused(const SolveArgs &a_in, int grid, int tier, cudaStream_t st) {
+  SolveArgs a = a_in;
+  a.tier = tier;
+  const size_t smem = fused_smem_bytes(a, tier);
+  if (tier == 0) {
+    if (a.nj == 2) k_cfs_fused<2, FUSED_BULK_NT, FUSED_BULK_QS, 3><<<grid, FUSED_BULK_NT, smem, st>>>(a);
+    else if (a.nj == 5) k_cfs_fused<5, FUSED_BULK_NT, FUSED_BULK_QS, 3><<<grid, FUSED_BULK_NT, smem, st>>>(a);
+    else return cudaErrorInvalidValue;
+  } else {
+    if (a.nj == 2) k_cfs_fused<2, FUSED_HEAVY_NT, FUSED_HEAVY_QS, 1><<<grid, FUSED_HEAVY_NT, smem, st>>>(a);
+    else if (a.nj == 5) k_cfs_fused<5, FUSED_HEAVY_NT, FUSED_HEAVY_QS, 1><<<grid, FUSED_HEAVY_NT, smem, st>>>(a);
+    else return cudaErrorInvalidValue;
   }
   return cudaGetLastError();
 }

@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(GRAD_THREADS) k_grad_numjac(GradArgs a) {
       if (a.linkid) a.linkid[idx(j)] = lid;
     }
   } out{a, prob, i};
-  numjac_waypoint<NJ, OC>(tab, sc, tid, thp, a.nobs, touched, out);
+  numjac_waypoint<NJ, OC, GRAD_THREADS>(tab, sc, tid, thp, a.nobs, touched, out);
   if (touched && a.flags) atomicOr(&a.flags[prob], 0x100);
 }
 

@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(QP_THREADS, 3) k_qp(SolveArgs a) {
       for (int c = tid; c < n; c += QP_THREADS) s.v[2 * n + c] = ub[c];
       __syncthreads();
     }
-    const int status = qp_solve(s, dims, a.cost0[b], (has_bnd && a.fupper) ? a.fupper[b] : INFINITY, skip_solve, q, steps,
+    const int status = qp_solve<QP_THREADS, QP_QS>(s, dims, a.cost0[b], (has_bnd && a.fupper) ? a.fupper[b] : INFINITY, skip_solve, q, steps,
                                 qmax_seen, pf, tck, prof);
     steps_total += steps;
     if (tid == 0 && a.prob_steps) a.prob_steps[b] += steps;
@@ -137,14 +137,14 @@ __global__ void __launch_bounds__(QP_THREADS, 3) k_qp(SolveArgs a) {
         pe += dlt * dlt;
         ub[c] = un;
       }
-      const double e_u = sqrt(block_sum(pe, s.red));
+      const double e_u = sqrt(block_sum<QP_THREADS>(pe, s.red));
       // cost by duality: f(u) = f(u0) + 1/2 sum_w lam_w * (c_w u0 - rhs_w)
       double pc = 0.0;
       for (int w = tid; w < q; w += QP_THREADS) {
         const double val0 = viol_at_u0(s.act[w], OH, H, n, nj, s, umax);
         pc += s.lam[w] * val0;
       }
-      const double cost = psg ? 0.0 : a.cost0[b] + 0.5 * block_sum(pc, s.red);  // PSGCFS: k_psg_cost
+      const double cost = psg ? 0.0 : a.cost0[b] + 0.5 * block_sum<QP_THREADS>(pc, s.red);  // PSGCFS: k_psg_cost
       // roll-out (CFS_FANUC.m:90-94): x_old is staged in shared memory (coalesced), nj threads run the recurrence
       // xR(:,i) = A xR(:,i-1) + B u_i there, then the new trajectory is written back coalesced; ||x_new - x_old||^2
       // (EVAL.m:64) is accumulated on the way.  xbuf aliases the term-weight scratch (tcoef|twgt), free by now.
@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(QP_THREADS, 3) k_qp(SolveArgs a) {
       }
       __syncthreads();
       for (int e = tid; e < 2 * n; e += QP_THREADS) xb[e] = xbuf[e];
-      const double dx = sqrt(block_sum(px, s.red));
+      const double dx = sqrt(block_sum<QP_THREADS>(px, s.red));
       if (tid == 0) {
         if (!psg) a.cost_hist[(size_t)b * a.max_outer + (it - 1)] = cost;
         if (a.e_u_hist) a.e_u_hist[(size_t)b * a.max_outer + (it - 1)] = e_u;
@@ -220,7 +220,7 @@ cudaError_t launch_qp(const SolveArgs &a, int grid, cudaStream_t st) {
 // one CTA per problem: u=0, x_=sys_info.x_ (CFS_FANUC.m:55-56), histories NaN, first stop_outer test with
 // x_old = ones (EVAL.m:47,61-73), initial active list.
 __global__ void __launch_bounds__(128) k_solve_init(SolveArgs a) {
-  __shared__ double red[QP_WARPS];
+  __shared__ double red[(QP_THREADS / 32)];
   const int b = blockIdx.x, tid = threadIdx.x;
   const int n = a.n, N = 2 * n;
   double part = 0.0;
@@ -234,7 +234,7 @@ __global__ void __launch_bounds__(128) k_solve_init(SolveArgs a) {
     a.cost_hist[(size_t)b * a.max_outer + e] = __longlong_as_double(0x7ff8000000000000LL);
     if (a.e_u_hist) a.e_u_hist[(size_t)b * a.max_outer + e] = __longlong_as_double(0x7ff8000000000000LL);
   }
-  const double nrm = sqrt(block_sum(part, red));
+  const double nrm = sqrt(block_sum<QP_THREADS>(part, red));
   if (tid == 0) {
     a.iters[b] = 0;
     a.flags[b] = 0;
@@ -262,7 +262,7 @@ cudaError_t launch_solve_init(const SolveArgs &a, cudaStream_t s) {
 
 // v0 = P u0 and cost0 = caug + 1/2 ff'u0 (value of EVAL.get_cost at the unconstrained minimiser), one CTA per problem
 __global__ void __launch_bounds__(128) k_v0(SolveArgs a) {
-  __shared__ double red[QP_WARPS];
+  __shared__ double red[(QP_THREADS / 32)];
   extern __shared__ double u0s[];
   const int b = blockIdx.x, tid = threadIdx.x;
   const int n = a.n, nj = a.nj, np = 3 * n;
@@ -273,7 +273,7 @@ __global__ void __launch_bounds__(128) k_v0(SolveArgs a) {
     u0s[e] = uv;
     part += a.ff[(size_t)b * n + e] * uv;
   }
-  const double fu = block_sum(part, red);
+  const double fu = block_sum<QP_THREADS>(part, red);
   if (tid == 0) a.cost0[b] = a.caug[b] + 0.5 * fu;
   if (a.fupper) {  // sup over the box |u|<=MAX_input of EVAL.get_cost: 1/2 ||QQ||_inf sum umax^2 + sum |ff| umax + caug
     double pb = 0.0;
@@ -282,7 +282,7 @@ __global__ void __launch_bounds__(128) k_v0(SolveArgs a) {
         const double um = a.max_input[e];
         pb += 0.5 * a.qq_norm_inf * um * um + fabs(a.ff[(size_t)b * n + e]) * um;
       }
-    const double sb = block_sum(pb, red);
+    const double sb = block_sum<QP_THREADS>(pb, red);
     if (tid == 0) a.fupper[b] = a.has_bounds ? (fabs(a.caug[b]) + sb) * (1.0 + 1e-6) + 1e-6 : INFINITY;
   }
   for (int pi = tid; pi < np; pi += blockDim.x) {
@@ -377,7 +377,7 @@ cudaError_t launch_psg_point(const SolveArgs &a, cudaStream_t s) {
 // EVAL.get_cost (EVAL.m:51-53) of the projected iterate, w = QQ*u from the batched GEMM; one CTA per problem of the list
 // the QP kernel just consumed.  Problems whose projection failed this iteration (iters[b] != outer_iter) are skipped.
 __global__ void __launch_bounds__(128) k_psg_cost(SolveArgs a) {
-  __shared__ double red[QP_WARPS];
+  __shared__ double red[(QP_THREADS / 32)];
   if ((int)blockIdx.x >= *a.count_cur) return;
   const int b = a.list_cur[blockIdx.x], tid = threadIdx.x, n = a.n;
   if (a.iters[b] != a.outer_iter) return;
@@ -387,8 +387,8 @@ __global__ void __launch_bounds__(128) k_psg_cost(SolveArgs a) {
     pq += uv * a.w[(size_t)b * n + e];
     pl += uv * a.ff[(size_t)b * n + e];
   }
-  const double quad = block_sum(pq, red);
-  const double lin = block_sum(pl, red);
+  const double quad = block_sum<QP_THREADS>(pq, red);
+  const double lin = block_sum<QP_THREADS>(pl, red);
   if (tid == 0) {
     const double cost = (0.5 * quad + lin) + a.caug[b];
     a.cost_new[b] = cost;

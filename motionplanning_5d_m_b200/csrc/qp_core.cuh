@@ -5,8 +5,7 @@
 
 namespace cfs {
 
-#define QP_THREADS 128
-#define QP_WARPS (QP_THREADS / 32)
+#define QP_THREADS 128   // lock-step kernel / bulk tier of the fused kernel
 #define QP_DEP_TOL 1e-8
 #define QP_QS 48          // working sets up to QP_QS keep their inverse in shared memory
 #define QP_SMALL_T 16     // term lists up to this length refresh all 3n primitives directly from G
@@ -38,13 +37,14 @@ struct QpView {  // decoded shared-memory layout
 };
 
 #define QP_NOFF 23
-__host__ __device__ inline size_t qp_smem_layout(int n, int nj, int OH, int m, size_t *off /*[QP_NOFF]*/) {
+__host__ __device__ inline size_t qp_smem_layout(int n, int nj, int OH, int m, size_t *off /*[QP_NOFF]*/, int qs = QP_QS,
+                                                  int nt = QP_THREADS) {
   size_t o = 0;
   const int np = 3 * n;
   const int tmax = nj * OH + n + 2;
   // [Msm | v | tcoef | twgt | lam | r | g] first and contiguous: all of it is dead while the fused kernel runs its
   // gradient phase, which aliases its sin/cos cache onto this span (qp_scratch_span()).
-  off[10] = o; o += sizeof(double) * QP_QS * QP_QS;
+  off[10] = o; o += sizeof(double) * qs * qs;
   off[0] = o; o += sizeof(double) * np;
   off[8] = o; o += sizeof(double) * tmax;
   off[9] = o; o += sizeof(double) * tmax;
@@ -54,7 +54,7 @@ __host__ __device__ inline size_t qp_smem_layout(int n, int nj, int OH, int m, s
   off[1] = o; o += sizeof(double) * (size_t)OH * nj;
   off[2] = o; o += sizeof(double) * OH;
   off[3] = o; o += sizeof(double) * OH;
-  off[7] = o; o += sizeof(double) * 16;
+  off[7] = o; o += sizeof(double) * 64;
   off[11] = o; o += sizeof(double) * 8;
   off[12] = o; o += sizeof(double) * 8;
   off[13] = o; o += sizeof(int) * (n + 2);
@@ -67,7 +67,7 @@ __host__ __device__ inline size_t qp_smem_layout(int n, int nj, int OH, int m, s
   off[19] = o; o += sizeof(double) * np;
   off[20] = o; o += sizeof(double) * 2 * n;
   off[21] = o; o += sizeof(double) * n;
-  off[22] = o; o += sizeof(double) * QP_THREADS;
+  off[22] = o; o += sizeof(double) * nt;
   return (o + 15) / 16 * 16;
 }
 
@@ -159,7 +159,8 @@ __device__ __forceinline__ double viol_at_u0(int cid, int OH, int H, int n, int 
   return neg ? -s.v0s[2 * n + c] - umax[c] : s.v0s[2 * n + c] - umax[c];
 }
 
-// ---- block reductions (QP_THREADS threads) --------------------------------------------------------------------
+// ---- block reductions (NT threads) --------------------------------------------------------------------
+template <int NT>
 __device__ __forceinline__ void block_argmin(double &val, int &idx, double *red) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -180,7 +181,7 @@ __device__ __forceinline__ void block_argmin(double &val, int &idx, double *red)
   val = red[0];
   idx = reinterpret_cast<int *>(red + 1)[0];
 #pragma unroll
-  for (int ww = 1; ww < QP_WARPS; ++ww) {
+  for (int ww = 1; ww < (NT / 32); ++ww) {
     const double ov = red[2 * ww];
     const int oi = reinterpret_cast<int *>(red + 2 * ww + 1)[0];
     if (ov < val || (ov == val && oi >= 0 && (idx < 0 || oi < idx))) {
@@ -190,6 +191,7 @@ __device__ __forceinline__ void block_argmin(double &val, int &idx, double *red)
   }
 }
 
+template <int NT>
 __device__ __forceinline__ double block_sum(double val, double *red) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) val += __shfl_down_sync(0xffffffffu, val, o);
@@ -199,20 +201,21 @@ __device__ __forceinline__ double block_sum(double val, double *red) {
   __syncthreads();
   double s = red[0];
 #pragma unroll
-  for (int ww = 1; ww < QP_WARPS; ++ww) s += red[ww];
+  for (int ww = 1; ww < (NT / 32); ++ww) s += red[ww];
   return s;
 }
 
 
-__host__ __device__ inline size_t qp_scratch_span(int n, int nj, int OH) {  // bytes of the leading dead-during-gradient span
+__host__ __device__ inline size_t qp_scratch_span(int n, int nj, int OH, int qs = QP_QS) {  // bytes of the leading dead-during-gradient span
   const int tmax = nj * OH + n + 2;
-  return sizeof(double) * ((size_t)QP_QS * QP_QS + 3 * n + 2 * (size_t)tmax + 3 * (size_t)(n + 2));
+  return sizeof(double) * ((size_t)qs * qs + 3 * n + 2 * (size_t)tmax + 3 * (size_t)(n + 2));
 }
 
-__device__ __forceinline__ QpView qp_view(unsigned char *smem_raw, int n, int nj, int OH, int m) {
+__device__ __forceinline__ QpView qp_view(unsigned char *smem_raw, int n, int nj, int OH, int m, int qs = QP_QS,
+                                          int nt = QP_THREADS) {
   QpView s;
   size_t off[QP_NOFF];
-  qp_smem_layout(n, nj, OH, m, off);
+  qp_smem_layout(n, nj, OH, m, off, qs, nt);
   s.v = reinterpret_cast<double *>(smem_raw + off[0]);
   s.ocoef = reinterpret_cast<double *>(smem_raw + off[1]);
   s.orhs = reinterpret_cast<double *>(smem_raw + off[2]);
@@ -254,10 +257,11 @@ struct QpDims {
 // Solves   min 1/2 u'QQ u + ff'u  s.t. the rows described by (s.ocoef, s.orhs, lim, umax)   starting from the
 // unconstrained minimiser whose primitives are in s.v0s / s.v.  On return (status 0) s.v holds the primitives of the
 // optimum (controls in s.v[2n..3n)), s.lam / s.act / q the multipliers and the working set.
-// status: 0 optimal, 2 infeasible, 3 numerical.  Must be called by all QP_THREADS threads of the CTA.
+// status: 0 optimal, 2 infeasible, 3 numerical, 4 escalate (step_cap exceeded / working set outgrew QS).  Must be called by all NT threads of the CTA.
+template <int NT, int QS>
 __device__ __forceinline__ int qp_solve(const QpView &s, const QpDims &P, double cost0, double fupper, bool skip_solve,
                                         int &q_out, int &steps_out, int &qmax_seen, long long *pf, long long &tck,
-                                        bool prof) {
+                                        bool prof, int step_cap = 0x7fffffff, bool escalate_on_spill = false) {
   const int tid = threadIdx.x;
   const int n = P.n, nj = P.nj, H = P.H, np = P.np, OH = P.OH, m = P.m, has_vel = P.has_vel, has_bnd = P.has_bnd;
   const double *__restrict__ G = P.G;
@@ -270,15 +274,15 @@ __device__ __forceinline__ int qp_solve(const QpView &s, const QpDims &P, double
     if (skip_solve) status = 0;
     double fval = cost0;
     const int max_steps = 20 * (m + n) + 100;
-#define MAT(r_, c_) (in_smem ? s.Msm[(r_) + QP_QS * (c_)] : Mgl[(r_) + (size_t)ldg * (c_)])
+#define MAT(r_, c_) (in_smem ? s.Msm[(r_) + QS * (c_)] : Mgl[(r_) + (size_t)ldg * (c_)])
     while (status < 0) {
       // (0) primal recovery from the multipliers: v = v0 - G (C_W' lambda)
       if (q > 0) {
         const int T = s.toff[q];
-        for (int t = tid; t < T; t += QP_THREADS) s.twgt[t] = s.lam[s.towner[t]] * s.tcoef[t];
+        for (int t = tid; t < T; t += NT) s.twgt[t] = s.lam[s.towner[t]] * s.tcoef[t];
         __syncthreads();
         if (T <= QP_SMALL_T) {
-          for (int base = 0; base < np; base += 6 * QP_THREADS) {  // 6 primitives per thread, 2 terms per pass: 12 loads in flight
+          for (int base = 0; base < np; base += 6 * NT) {  // 6 primitives per thread, 2 terms per pass: 12 loads in flight
             double acc[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
             int t = 0;
             for (; t + 2 <= T; t += 2) {
@@ -287,9 +291,9 @@ __device__ __forceinline__ int qp_solve(const QpView &s, const QpDims &P, double
               double l0[6], l1[6];
 #pragma unroll
               for (int j = 0; j < 6; ++j) {
-                const bool ok = base + tid + j * QP_THREADS < np;
-                l0[j] = ok ? g0[j * QP_THREADS] : 0.0;
-                l1[j] = ok ? g1[j * QP_THREADS] : 0.0;
+                const bool ok = base + tid + j * NT < np;
+                l0[j] = ok ? g0[j * NT] : 0.0;
+                l1[j] = ok ? g1[j * NT] : 0.0;
               }
 #pragma unroll
               for (int j = 0; j < 6; ++j) acc[j] += w0_ * l0[j] + w1_ * l1[j];
@@ -299,17 +303,17 @@ __device__ __forceinline__ int qp_solve(const QpView &s, const QpDims &P, double
               const double *g0 = G + (size_t)s.trow[t] * np + base + tid;
 #pragma unroll
               for (int j = 0; j < 6; ++j)
-                if (base + tid + j * QP_THREADS < np) acc[j] += w0_ * g0[j * QP_THREADS];
+                if (base + tid + j * NT < np) acc[j] += w0_ * g0[j * NT];
             }
 #pragma unroll
             for (int j = 0; j < 6; ++j) {
-              const int pi = base + tid + j * QP_THREADS;
+              const int pi = base + tid + j * NT;
               if (pi < np) s.v[pi] = s.v0s[pi] - acc[j];
             }
           }
         } else {
           const double *__restrict__ Gu = G + 2 * n;  // control block of every primitive row
-          for (int c = tid; c < n; c += QP_THREADS) {
+          for (int c = tid; c < n; c += NT) {
             double acc8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
             int t = 0;
             for (; t + 8 <= T; t += 8) {
@@ -323,7 +327,7 @@ __device__ __forceinline__ int qp_solve(const QpView &s, const QpDims &P, double
             s.v[2 * n + c] = s.v0s[2 * n + c] - (((acc8[0] + acc8[1]) + (acc8[2] + acc8[3])) + ((acc8[4] + acc8[5]) + (acc8[6] + acc8[7])));
           }
           __syncthreads();
-          for (int e = tid; e < n; e += QP_THREADS) {  // B_theta u and B_omega u in closed form
+          for (int e = tid; e < n; e += NT) {  // B_theta u and B_omega u in closed form
             const int i = e / nj, k = e % nj;
             double at = 0.0, aw = 0.0;
             for (int j = 0; j <= i; ++j) {
@@ -342,7 +346,7 @@ __device__ __forceinline__ int qp_solve(const QpView &s, const QpDims &P, double
       // (1) most violated inactive row, normalised by its QQ^-1 norm
       double best = 0.0;
       int bidx = -1;
-      for (int cid = tid; cid < OH; cid += QP_THREADS) {
+      for (int cid = tid; cid < OH; cid += NT) {
         const double nr = s.onrm[cid];
         if (s.inact[cid] || !(nr > 0.0)) continue;
         const double sl = slack_of(cid, OH, H, n, nj, s, umax);
@@ -355,7 +359,7 @@ __device__ __forceinline__ int qp_solve(const QpView &s, const QpDims &P, double
         }
       }
       // omega / control primitives: both signs of a row share its value and its norm
-      for (int e = tid; e < 2 * n; e += QP_THREADS) {
+      for (int e = tid; e < 2 * n; e += NT) {
         const bool is_w = e < n;
         if (is_w ? !has_vel : !has_bnd) continue;
         const double nr = s.gns[e];
@@ -389,7 +393,7 @@ __device__ __forceinline__ int qp_solve(const QpView &s, const QpDims &P, double
           }
         }
       }
-      block_argmin(best, bidx, s.red);
+      block_argmin<NT>(best, bidx, s.red);
       PF_ADD(2);
       if (bidx < 0) {
         if (q == 0 || polished) {
@@ -400,8 +404,8 @@ __device__ __forceinline__ int qp_solve(const QpView &s, const QpDims &P, double
         // S_W lambda = b (S_W = C_W QQ^-1 C_W' re-read from G, b = violations at u0) removes the accumulated drift
         // (measured: 7e-10 -> 3e-13 in u).  Then v is re-evaluated from the refined multipliers and scanned once more.
         {
-          const int nch = QP_THREADS / q > 0 ? QP_THREADS / q : 1;  // chunks of columns per row, fixed summation order
-          if (q <= QP_THREADS) {
+          const int nch = NT / q > 0 ? NT / q : 1;  // chunks of columns per row, fixed summation order
+          if (q <= NT) {
             const int w = tid % q, ch = tid / q;
             if (ch < nch) {
               const Desc dw = decode(s.act[w], OH, H, n, nj, s.ocoef);
@@ -416,7 +420,7 @@ __device__ __forceinline__ int qp_solve(const QpView &s, const QpDims &P, double
               s.g[tid] = viol_at_u0(s.act[tid], OH, H, n, nj, s, umax) - acc;
             }
           } else {
-            for (int w = tid; w < q; w += QP_THREADS) {
+            for (int w = tid; w < q; w += NT) {
               const Desc dw = decode(s.act[w], OH, H, n, nj, s.ocoef);
               double acc = 0.0;
               for (int c = 0; c < q; ++c) acc += gram(dw, decode(s.act[c], OH, H, n, nj, s.ocoef), G, np) * s.lam[c];
@@ -424,13 +428,13 @@ __device__ __forceinline__ int qp_solve(const QpView &s, const QpDims &P, double
             }
           }
           __syncthreads();
-          for (int w = tid; w < q; w += QP_THREADS) {
+          for (int w = tid; w < q; w += NT) {
             double acc = 0.0;
             for (int c = 0; c < q; ++c) acc += MAT(w, c) * s.g[c];
             s.r[w] = acc;
           }
           __syncthreads();
-          for (int w = tid; w < q; w += QP_THREADS) s.lam[w] += s.r[w];
+          for (int w = tid; w < q; w += NT) s.lam[w] += s.r[w];
           __syncthreads();
         }
         polished = true;
@@ -448,12 +452,16 @@ __device__ __forceinline__ int qp_solve(const QpView &s, const QpDims &P, double
           status = 3;
           break;
         }
+        if (steps > step_cap) {  // hand the problem to the heavy tier (k_fused.cu)
+          status = 4;
+          break;
+        }
         // g_w = c_w QQ^-1 c_p'
-        for (int w = tid; w < q; w += QP_THREADS) s.g[w] = gram(decode(s.act[w], OH, H, n, nj, s.ocoef), dp, G, np);
+        for (int w = tid; w < q; w += NT) s.g[w] = gram(decode(s.act[w], OH, H, n, nj, s.ocoef), dp, G, np);
         __syncthreads();
         // r = Minv g
         double part = 0.0;
-        for (int w = tid; w < q; w += QP_THREADS) {
+        for (int w = tid; w < q; w += NT) {
           double acc8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
           int c = 0;
           for (; c + 8 <= q; c += 8) {
@@ -468,11 +476,11 @@ __device__ __forceinline__ int qp_solve(const QpView &s, const QpDims &P, double
           s.r[w] = acc;
           part += s.g[w] * acc;
         }
-        const double delta = sigma - block_sum(part, s.red);  // z'n+ in Goldfarb-Idnani's notation
+        const double delta = sigma - block_sum<NT>(part, s.red);  // z'n+ in Goldfarb-Idnani's notation
         // t1: largest dual step keeping the multipliers non-negative
         double t1 = INFINITY;
         int l = -1;
-        for (int w = tid; w < q; w += QP_THREADS)
+        for (int w = tid; w < q; w += NT)
           if (s.r[w] > 0.0) {
             const double t = s.lam[w] / s.r[w];
             if (t < t1 || l < 0) {
@@ -480,7 +488,7 @@ __device__ __forceinline__ int qp_solve(const QpView &s, const QpDims &P, double
               l = w;
             }
           }
-        block_argmin(t1, l, s.red);
+        block_argmin<NT>(t1, l, s.red);
         if (l < 0) t1 = INFINITY;
         if (!(delta == delta) || !(sigma == sigma)) {
           status = 3;
@@ -511,13 +519,17 @@ __device__ __forceinline__ int qp_solve(const QpView &s, const QpDims &P, double
           status = 2;
           break;
         }
-        for (int w = tid; w < q; w += QP_THREADS) s.lam[w] -= t * s.r[w];
+        for (int w = tid; w < q; w += NT) s.lam[w] -= t * s.r[w];
         lam_p += t;
         __syncthreads();
         PF_ADD(3);
         if (full) {
-          if (in_smem && q + 1 > QP_QS) {  // spill the inverse to the global slab
-            for (int e = tid; e < q * q; e += QP_THREADS) Mgl[(e % q) + (size_t)ldg * (e / q)] = s.Msm[(e % q) + QP_QS * (e / q)];
+          if (in_smem && q + 1 > QS && escalate_on_spill) {
+            status = 4;
+            break;
+          }
+          if (in_smem && q + 1 > QS) {  // spill the inverse to the global slab
+            for (int e = tid; e < q * q; e += NT) Mgl[(e % q) + (size_t)ldg * (e / q)] = s.Msm[(e % q) + QS * (e / q)];
             in_smem = false;
             __syncthreads();
           }
@@ -525,19 +537,19 @@ __device__ __forceinline__ int qp_solve(const QpView &s, const QpDims &P, double
           const double id = 1.0 / delta;
           {
             const int q1 = q + 1, tot = q1 * q1;
-            for (int e0 = tid; e0 < tot; e0 += 4 * QP_THREADS) {
+            for (int e0 = tid; e0 < tot; e0 += 4 * NT) {
               double old4[4];
               int rr4[4], cc4[4];
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
-                const int e = e0 + j * QP_THREADS;
+                const int e = e0 + j * NT;
                 rr4[j] = e % q1;
                 cc4[j] = e / q1;
                 old4[j] = (e < tot && rr4[j] < q && cc4[j] < q) ? MAT(rr4[j], cc4[j]) : 0.0;
               }
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
-                const int e = e0 + j * QP_THREADS;
+                const int e = e0 + j * NT;
                 if (e >= tot) continue;
                 const int r_ = rr4[j], c_ = cc4[j];
                 double val;
@@ -572,27 +584,27 @@ __device__ __forceinline__ int qp_solve(const QpView &s, const QpDims &P, double
         // drop working-set member l: M <- M - M(:,l) M(l,:)/M(l,l), then move the last member into slot l
         {
           const int last = q - 1;
-          for (int w = tid; w < q; w += QP_THREADS) s.g[w] = MAT(w, l);
+          for (int w = tid; w < q; w += NT) s.g[w] = MAT(w, l);
           __syncthreads();
           const double ip = 1.0 / s.g[l];
-          for (int e0 = tid; e0 < q * q; e0 += 4 * QP_THREADS) {
+          for (int e0 = tid; e0 < q * q; e0 += 4 * NT) {
             double old4[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const int e = e0 + j * QP_THREADS;
+              const int e = e0 + j * NT;
               old4[j] = e < q * q ? MAT(e % q, e / q) : 0.0;
             }
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const int e = e0 + j * QP_THREADS;
+              const int e = e0 + j * NT;
               if (e < q * q) MAT(e % q, e / q) = old4[j] - s.g[e % q] * s.g[e / q] * ip;
             }
           }
           __syncthreads();
           if (l != last) {
-            for (int w = tid; w < q; w += QP_THREADS) MAT(w, l) = MAT(w, last);
+            for (int w = tid; w < q; w += NT) MAT(w, l) = MAT(w, last);
             __syncthreads();
-            for (int w = tid; w < q; w += QP_THREADS) MAT(l, w) = MAT(last, w);
+            for (int w = tid; w < q; w += NT) MAT(l, w) = MAT(last, w);
           }
           if (tid == 0) {
             s.inact[s.act[l]] = 0;
@@ -607,7 +619,7 @@ __device__ __forceinline__ int qp_solve(const QpView &s, const QpDims &P, double
           }
           --q;
           __syncthreads();
-          for (int w = tid; w < q; w += QP_THREADS) {
+          for (int w = tid; w < q; w += NT) {
             const Desc d = decode(s.act[w], OH, H, n, nj, s.ocoef);
             const int t0 = s.toff[w];
             for (int k = 0; k < d.nterm; ++k) {
