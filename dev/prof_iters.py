@@ -31,5 +31,7 @@ ctx.set_timing(3)
 out = ctx.solve_batch(cfg["x0"], cfg["ff"], cfg["caug"], cfg["xref"], 0.1, 20)
 pf = ctx.qp_profile()
 names = ["setup+grad","refresh","scan","gram+solve","update","epilogue"]
-print("qp profile: problems %d outer steps %d" % (pf[6], pf[7]))
-for k,nm in enumerate(names): print("  %-10s %12d ticks  %8.1f per problem-iter  %8.1f per outer step" % (nm, pf[k], pf[k]/max(pf[6],1), pf[k]/max(pf[7],1)))
+for tier, o in (("bulk", 0), ("heavy", 8)):
+    p8 = pf[o:o+8]
+    print("qp profile %s: problems %d outer steps %d total ticks %d" % (tier, p8[6], p8[7], p8[:6].sum()))
+    for k,nm in enumerate(names): print("  %-10s %12d ticks  %8.1f per problem  %8.1f per outer step" % (nm, p8[k], p8[k]/max(p8[6],1), p8[k]/max(p8[7],1)))

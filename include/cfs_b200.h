@@ -138,8 +138,9 @@ int cfs_get_iter_times(const cfs_ctx *ctx, double *grad_ms, double *qp_ms, int c
 /* dual active-set steps spent on each problem of the last solve (sum over outer iterations), steps[B] */
 int cfs_get_problem_steps(cfs_ctx *ctx, int *steps, int B);
 /* timing level 3: clock64 phase profile of the QP kernel (thread 0 of every CTA, summed): out8 = {prologue, primal
- * refresh, violation scan, gram+solve+step length, working-set update, epilogue} ticks, problems, outer steps */
-int cfs_get_qp_profile(cfs_ctx *ctx, long long *out8);
+ * refresh, violation scan, gram+solve+step length, working-set update, epilogue} ticks, problems, outer steps; out16[8..15]
+ * = the same for the heavy tier of the fused kernel */
+int cfs_get_qp_profile(cfs_ctx *ctx, long long *out16);
 /* FP64 FMA micro-benchmark (roofline denominator: MEASURED_PEAKS.json has no FP64 entry). Returns TFLOP/s. */
 int cfs_measure_fp64_peak(cfs_ctx *ctx, double *tflops, double *sm_clock_mhz_est);
 

@@ -236,7 +236,7 @@ class Context:
         return st
 
     def qp_profile(self):
-        o = np.zeros(8, dtype=np.int64)
+        o = np.zeros(16, dtype=np.int64)
         self._check(self._lib.cfs_get_qp_profile(self._h, _dp(o)), "cfs_get_qp_profile")
         return o
 

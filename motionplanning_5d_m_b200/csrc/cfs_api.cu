@@ -388,7 +388,7 @@ static int solve_device(cfs_ctx *ctx, int B, int solver, int grad, const double 
   if ((rc = ensure(ctx, ctx->listA, sizeof(int) * B))) return rc;
   if ((rc = ensure(ctx, ctx->listB, sizeof(int) * B))) return rc;
   if ((rc = ensure(ctx, ctx->counters, sizeof(int) * 8))) return rc;
-  if ((rc = ensure(ctx, ctx->qpsteps, sizeof(long long) * 16))) return rc;
+  if ((rc = ensure(ctx, ctx->qpsteps, sizeof(long long) * 32))) return rc;
 
   SolveArgs a;
   memset(&a, 0, sizeof(a));
@@ -454,7 +454,7 @@ static int solve_device(cfs_ctx *ctx, int B, int solver, int grad, const double 
   int launches = 0;
   CU(cudaEventRecord(ctx->ev_a, st));
   CU(cudaMemsetAsync(cnt, 0, sizeof(int) * 8, st));
-  CU(cudaMemsetAsync(ctx->qpsteps.p, 0, sizeof(long long) * 16, st));
+  CU(cudaMemsetAsync(ctx->qpsteps.p, 0, sizeof(long long) * 32, st));
   CU(cudaMemsetAsync(ctx->probsteps.p, 0, sizeof(int) * B, st));
   a.list_cur = ptr<int>(ctx->listA); a.count_cur = cnt + 0;
   a.list_next = ptr<int>(ctx->listB); a.count_next = cnt + 1;
@@ -781,9 +781,9 @@ extern "C" int cfs_get_iter_times(const cfs_ctx *ctx, double *grad_ms, double *q
 
 extern "C" int cfs_get_qp_profile(cfs_ctx *ctx, long long *out8) {
   if (!ctx || !out8) return CFS_E_ARG;
-  if (ctx->qpsteps.cap < sizeof(long long) * 16) return fail(ctx, CFS_E_STATE, "cfs_get_qp_profile: no solve yet");
+  if (ctx->qpsteps.cap < sizeof(long long) * 32) return fail(ctx, CFS_E_STATE, "cfs_get_qp_profile: no solve yet");
   CU(cudaSetDevice(ctx->device));
-  CU(cudaMemcpyAsync(out8, ptr<long long>(ctx->qpsteps) + 8, sizeof(long long) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(out8, ptr<long long>(ctx->qpsteps) + 8, sizeof(long long) * 16, cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   return 0;
 }

@@ -17,7 +17,7 @@
 //     memory) hands the rare QP whose working set outgrows that, or that needs more than esc_steps dual steps (almost
 //     always an infeasible linearisation on its way to the infeasibility certificate), to the heavy tier (256 threads,
 //     1 CTA/SM, 128 x 128 inverse on chip), which resumes the problem from its last completed outer iteration.
-#include "cfs_numjac.cuh"
+#include "cfs_numjac_cols.cuh"
 #include "qp_core.cuh"
 
 namespace cfs {
@@ -25,7 +25,7 @@ namespace cfs {
 #define FUSED_BULK_NT 128
 #define FUSED_BULK_QS QP_QS
 #define FUSED_HEAVY_NT 256
-#define FUSED_HEAVY_QS 128
+#define FUSED_HEAVY_QS 144
 
 struct FusedLayout {
   size_t qp_bytes, xs, us, tab, mbar, total;
@@ -45,25 +45,6 @@ __host__ __device__ inline FusedLayout fused_layout(int n, int nj, int OH, int m
   return L;
 }
 
-// writes one waypoint's rows straight into the QP's shared-memory description (CFS_FANUC.m:117-121)
-template <int NJ>
-struct RowSink {
-  const QpView &s;
-  const DevTables &tab;
-  const double *disp;  // (B_theta u)(i, 0..NJ) of the current iterate
-  int H, i, margin_is_D;
-  double gu[2];
-  __device__ __forceinline__ void grad(int j, int k, double v) {
-    s.ocoef[(j * H + i) * NJ + k] = -v;  // l = -Diff'*Bj(1:njoint,:)
-    gu[j & 1] += v * disp[k];
-  }
-  __device__ __forceinline__ void dist(int j, double d, int) {
-    const double margin = margin_is_D ? tab.obs[j].D : tab.obs[j].eps;
-    s.orhs[j * H + i] = (d - margin) - gu[j & 1];  // s = I - Diff'*Bj*u
-    gu[j & 1] = 0.0;
-  }
-};
-
 template <int NJ, int NT, int QS, int MINB>
 __global__ void __launch_bounds__(NT, MINB) k_cfs_fused(SolveArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -76,12 +57,15 @@ __global__ void __launch_bounds__(NT, MINB) k_cfs_fused(SolveArgs a) {
   double *us = reinterpret_cast<double *>(smem_raw + L.us);  // u   (CFS_FANUC.m:56)
   DevTables &tab = *reinterpret_cast<DevTables *>(smem_raw + L.tab);
   uint64_t *mbar = reinterpret_cast<uint64_t *>(smem_raw + L.mbar);
-  double(*sc)[NJ][NT] = reinterpret_cast<double(*)[NJ][NT]>(smem_raw);  // aliases the QP scratch span
+  double *scw = reinterpret_cast<double *>(smem_raw);  // sin/cos cache [6][NJ][H], aliases the QP scratch span
+  double *fv = scw + 6 * NJ * H;                        // f(x+), f(x-) per (obstacle, waypoint, column): [OH][NJ][2]
 
   tma_stage(&tab, a.tab, tab_bytes(a.nobs), mbar);
   const double *__restrict__ G = a.G;
   const int has_vel = a.has_lim, has_bnd = a.has_bounds;
-  for (int e = tid; e < 2 * n; e += NT) s.gns[e] = a.gdiag[n + e];
+#pragma unroll 1
+  for (int e = tid; e < 3 * n; e += NT) s.gns[e] = a.gdiag[e] * a.gdiag[e];  // G_ii
+#pragma unroll 1
   for (int e = tid; e < n; e += NT) s.ums[e] = has_bnd ? a.max_input[e] : 0.0;
   const double dt = tab.dt;
   const int ldg = a.slab_ld;
@@ -109,20 +93,26 @@ __global__ void __launch_bounds__(NT, MINB) k_cfs_fused(SolveArgs a) {
     PF_START();
     double part = 0.0;
     if (!heavy) {
+#pragma unroll 1
       for (int e = tid; e < N; e += NT) {
         const double xv = a.xref[(size_t)b * N + e];
         xs[e] = xv;
         part += (xv - 1.0) * (xv - 1.0);
       }
+#pragma unroll 1
       for (int e = tid; e < n; e += NT) us[e] = 0.0;
+#pragma unroll 1
       for (int e = tid; e < a.max_outer; e += NT) {
         a.cost_hist[(size_t)b * a.max_outer + e] = qnan;
         if (a.e_u_hist) a.e_u_hist[(size_t)b * a.max_outer + e] = qnan;
       }
     } else {  // resume from the last completed outer iteration (written by the bulk tier)
+#pragma unroll 1
       for (int e = tid; e < N; e += NT) xs[e] = a.x[(size_t)b * N + e];
+#pragma unroll 1
       for (int e = tid; e < n; e += NT) us[e] = a.u[(size_t)b * n + e];
     }
+#pragma unroll 1
     for (int pi = tid; pi < np; pi += NT) s.v0s[pi] = v0[pi];
     if (tid < 8) {
       s.lim[tid] = (tid < nj && has_vel) ? a.lim[tid] : 0.0;
@@ -148,24 +138,64 @@ __global__ void __launch_bounds__(NT, MINB) k_cfs_fused(SolveArgs a) {
       // ---- get_con: distances + num_jac gradients of every waypoint, rows written in place (CFS_FANUC.m:110-124) ----
       PF_START();
       __syncthreads();  // the sin/cos cache aliases the previous QP's scratch
-      for (int i = tid; i < H; i += NT) {
-        double disp[NJ];
-#pragma unroll
-        for (int k = 0; k < NJ; ++k)
-          disp[k] = (it == 1) ? 0.0 : xs[i * 2 * NJ + k] - (x0[k] + ((i + 1) * dt) * x0[NJ + k]);
-        RowSink<NJ> sink{s, tab, disp, H, i, a.margin_is_D, {0.0, 0.0}};
-        if (a.nobs <= 1)
-          numjac_waypoint<NJ, 1, NT>(tab, sc, tid, xs + i * 2 * NJ, a.nobs, touched, sink);
-        else
-          numjac_waypoint<NJ, 2, NT>(tab, sc, tid, xs + i * 2 * NJ, a.nobs, touched, sink);
+      numjac_sincos<NJ, NT>(tab, xs, H, scw);
+      __syncthreads();
+      // H*(2NJ+1) single-chain work items: f(x+), f(x-) of every gradient column + the base evaluation of every
+      // waypoint; every thread runs two items side by side
+      {
+        const int items = H * (2 * NJ + 1);
+#pragma unroll 1
+        for (int eA = tid; eA < items; eA += 2 * NT) {
+          const bool hasB = eA + NT < items;
+          const int eB = hasB ? eA + NT : eA;
+          const int c2A = eA / H, iA = eA - c2A * H, c2B = eB / H, iB = eB - c2B * H;
+#pragma unroll 1
+          for (int j0 = 0; j0 < a.nobs; j0 += 2) {
+            double dA[2], dB[2];
+            numjac_chain2<NJ>(tab, scw, H, iA, c2A >> 1, c2A & 1, iB, c2B >> 1, c2B & 1, hasB, j0, a.nobs, touched, dA, dB);
+#pragma unroll 1
+            for (int ch = 0; ch < (hasB ? 2 : 1); ++ch) {
+              const int c2 = ch ? c2B : c2A, i = ch ? iB : iA;
+              const double d0 = ch ? dB[0] : dA[0], d1 = ch ? dB[1] : dA[1];
+              if ((c2 >> 1) == NJ) {  // base evaluation: I = distance - margin (CFS_FANUC.m:117)
+                s.orhs[j0 * H + i] = d0 - (a.margin_is_D ? tab.obs[j0].D : tab.obs[j0].eps);
+                if (j0 + 1 < a.nobs)
+                  s.orhs[(j0 + 1) * H + i] = d1 - (a.margin_is_D ? tab.obs[j0 + 1].D : tab.obs[j0 + 1].eps);
+              } else {
+                fv[((j0 * H + i) * NJ + (c2 >> 1)) * 2 + (c2 & 1)] = d0;
+                if (j0 + 1 < a.nobs) fv[(((j0 + 1) * H + i) * NJ + (c2 >> 1)) * 2 + (c2 & 1)] = d1;
+              }
+            }
+          }
+        }
       }
       __syncthreads();
+#pragma unroll 1
+      for (int e = tid; e < OH * NJ; e += NT)  // l = -Diff'*Bj(1:njoint,:) (:121), Diff = (yhi - ylo)/eps (num_jac.m:15)
+        s.ocoef[e] = -((fv[2 * e] - fv[2 * e + 1]) / CFS_NUMJAC_EPS);
+      __syncthreads();
+      if (it > 1)  // s = I - Diff'*Bj*u (:120); B_theta u = theta_i - (theta_0 + i dt w_0) once x_ is the roll-out of u
+#pragma unroll 1
+        for (int cid = tid; cid < OH; cid += NT) {
+          const int i = cid % H;
+          double gu = 0.0;
+#pragma unroll
+          for (int k = 0; k < NJ; ++k)
+            gu += -s.ocoef[cid * NJ + k] * (xs[i * 2 * NJ + k] - (x0[k] + ((i + 1) * dt) * x0[NJ + k]));
+          s.orhs[cid] -= gu;
+        }
+      __syncthreads();
+#pragma unroll 1
       for (int pi = tid; pi < np; pi += NT) s.v[pi] = s.v0s[pi];
+#pragma unroll 1
       for (int e = tid; e < m; e += NT) s.inact[e] = 0;
+#pragma unroll 1
       for (int cid = tid; cid < OH; cid += NT) {
-        const Desc d = decode(cid, OH, H, n, nj, s.ocoef);
-        const double sg = gram(d, d, G, np);
-        s.onrm[cid] = sg > 0.0 ? sqrt(sg) : 0.0;
+        const int i = wp_of(cid, H);
+        double sg = 0.0;
+#pragma unroll
+        for (int k = 0; k < NJ; ++k) sg += s.ocoef[cid * NJ + k] * s.ocoef[cid * NJ + k] * s.gns[i * NJ + k];
+        s.onrm[cid] = sg;  // scan normalisation (diagonal proxy of c QQ^-1 c')
       }
       if (tid == 0) s.toff[0] = 0;
       __syncthreads();
@@ -173,8 +203,8 @@ __global__ void __launch_bounds__(NT, MINB) k_cfs_fused(SolveArgs a) {
 
       // ---- Solve_QP (CFS_FANUC.m:85) ----
       int q = 0, steps = 0;
-      const int qst = qp_solve<NT, QS>(s, dims, cost0, fupper, false, q, steps, qmax_seen, pf, tck, prof,
-                                       heavy ? 0x7fffffff : a.esc_steps, !heavy);
+      const int qst = qp_solve<NT, QS, (MINB == 1), NJ>(s, dims, cost0, fupper, false, q, steps, qmax_seen, pf, tck, prof,
+                                                        heavy ? 0x7fffffff : a.esc_steps);
       steps_total += steps;
       steps_prob += steps;
       if (qst != 0) {  // 2 infeasible / 3 numerical: u, x_ keep the previous iterate; 4: the heavy tier redoes this iteration
@@ -183,6 +213,7 @@ __global__ void __launch_bounds__(NT, MINB) k_cfs_fused(SolveArgs a) {
       }
       // ---- e_u, cost by duality, roll-out, stop rule (EVAL.m:51-73, CFS_FANUC.m:88-94) ----
       double pe = 0.0;
+#pragma unroll 1
       for (int c = tid; c < n; c += NT) {
         const double un = s.v[2 * n + c];
         const double dlt = us[c] - un;
@@ -191,7 +222,8 @@ __global__ void __launch_bounds__(NT, MINB) k_cfs_fused(SolveArgs a) {
       }
       const double e_u = sqrt(block_sum<NT>(pe, s.red));
       double pc = 0.0;
-      for (int w = tid; w < q; w += NT) pc += s.lam[w] * viol_at_u0(s.act[w], OH, H, n, nj, s, s.ums);
+#pragma unroll 1
+      for (int w = tid; w < q; w += NT) pc -= s.lam[w] * slack_at<NJ>(s.act[w], dims, s, s.v0s);
       const double cost = cost0 + 0.5 * block_sum<NT>(pc, s.red);
       double px = 0.0;
       if (tid < nj) {
@@ -224,7 +256,9 @@ __global__ void __launch_bounds__(NT, MINB) k_cfs_fused(SolveArgs a) {
 
     // ---- results ----
     __syncthreads();
+#pragma unroll 1
     for (int e = tid; e < n; e += NT) a.u[(size_t)b * n + e] = us[e];
+#pragma unroll 1
     for (int e = tid; e < N; e += NT) a.x[(size_t)b * N + e] = xs[e];
     const int any_touch = __syncthreads_or(touched);
     if (tid == 0) {
@@ -236,7 +270,7 @@ __global__ void __launch_bounds__(NT, MINB) k_cfs_fused(SolveArgs a) {
   }
   if (prof && tid == 0)
     for (int k = 0; k < 8; ++k)
-      if (pf[k]) atomicAdd(reinterpret_cast<unsigned long long *>(a.prof + k), (unsigned long long)pf[k]);
+      if (pf[k]) atomicAdd(reinterpret_cast<unsigned long long *>(a.prof + (heavy ? 8 : 0) + k), (unsigned long long)pf[k]);
   if (tid == 0) {
     if (steps_total) atomicAdd(reinterpret_cast<unsigned long long *>(a.qp_steps), (unsigned long long)steps_total);
     if (qmax_seen) atomicMax(a.max_active, qmax_seen);
@@ -264,7 +298,8 @@ bool fused_supported(const SolveArgs &a) {
     int nt, qs;
     tier_cfg(tier, nt, qs);
     // the sin/cos cache must fit into the QP scratch span it aliases, and the CTA into one SM's shared memory
-    if (sizeof(double) * 6 * a.nj * nt > qp_scratch_span(a.n, a.nj, OH, qs)) return false;
+    (void)nt;
+    if (sizeof(double) * (6 * a.nj * a.H + 2 * (size_t)OH * a.nj) > qp_scratch_span(a.n, a.nj, OH, qs)) return false;
     if (fused_smem_bytes(a, tier) > 227 * 1024) return false;
   }
   return true;

@@ -44,7 +44,7 @@ __global__ void __launch_bounds__(QP_THREADS, 3) k_qp(SolveArgs a) {
   const double *__restrict__ gnorm = a.gdiag;  // sqrt(diag(G))
   const int has_vel = a.has_lim, has_bnd = a.has_bounds;
   const bool psg = a.solver == 1;
-  for (int e = tid; e < 2 * n; e += QP_THREADS) s.gns[e] = gnorm[n + e];
+  for (int e = tid; e < 3 * n; e += QP_THREADS) s.gns[e] = gnorm[e] * gnorm[e];  // G_ii
   for (int e = tid; e < n; e += QP_THREADS) s.ums[e] = has_bnd ? a.max_input[e] : 0.0;
   const double *umax = s.ums;
   const double dt = a.tab->dt;
@@ -58,6 +58,7 @@ __global__ void __launch_bounds__(QP_THREADS, 3) k_qp(SolveArgs a) {
   long long pf[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   long long tck = 0;
   const bool prof = a.prof != nullptr;
+  const QpDims dims = {n, nj, H, np, OH, m, has_vel, has_bnd, G, umax, Mgl, ldg, dt};
 
   for (;;) {
     __syncthreads();
@@ -104,9 +105,10 @@ __global__ void __launch_bounds__(QP_THREADS, 3) k_qp(SolveArgs a) {
     }
     __syncthreads();
     for (int cid = tid; cid < OH; cid += QP_THREADS) {
-      const Desc d = decode(cid, OH, H, n, nj, s.ocoef);
-      const double sg = gram(d, d, G, np);
-      s.onrm[cid] = sg > 0.0 ? sqrt(sg) : 0.0;
+      const int i = cid % H;
+      double sg = 0.0;
+      for (int k = 0; k < nj; ++k) sg += s.ocoef[cid * nj + k] * s.ocoef[cid * nj + k] * s.gns[i * nj + k];
+      s.onrm[cid] = sg;  // scan normalisation (diagonal proxy of c QQ^-1 c')
     }
     if (tid == 0) s.toff[0] = 0;
     __syncthreads();
@@ -115,13 +117,12 @@ __global__ void __launch_bounds__(QP_THREADS, 3) k_qp(SolveArgs a) {
 
     // ---- dual active-set iterations --------------------------------------------------------------------------
     int q = 0, steps = 0;
-    const QpDims dims = {n, nj, H, np, OH, m, has_vel, has_bnd, G, umax, Mgl, ldg, dt};
     const bool skip_solve = psg && a.skip[b];
     if (skip_solve) {  // stop_inner() already true: u stays, no projection (PSGCFS_FANUC.m:88)
       for (int c = tid; c < n; c += QP_THREADS) s.v[2 * n + c] = ub[c];
       __syncthreads();
     }
-    const int status = qp_solve<QP_THREADS, QP_QS>(s, dims, a.cost0[b], (has_bnd && a.fupper) ? a.fupper[b] : INFINITY, skip_solve, q, steps,
+    const int status = qp_solve<QP_THREADS, QP_QS, true, 0>(s, dims, a.cost0[b], (has_bnd && a.fupper) ? a.fupper[b] : INFINITY, skip_solve, q, steps,
                                 qmax_seen, pf, tck, prof);
     steps_total += steps;
     if (tid == 0 && a.prob_steps) a.prob_steps[b] += steps;
@@ -141,7 +142,7 @@ __global__ void __launch_bounds__(QP_THREADS, 3) k_qp(SolveArgs a) {
       // cost by duality: f(u) = f(u0) + 1/2 sum_w lam_w * (c_w u0 - rhs_w)
       double pc = 0.0;
       for (int w = tid; w < q; w += QP_THREADS) {
-        const double val0 = viol_at_u0(s.act[w], OH, H, n, nj, s, umax);
+        const double val0 = -slack_at<0>(s.act[w], dims, s, s.v0s);
         pc += s.lam[w] * val0;
       }
       const double cost = psg ? 0.0 : a.cost0[b] + 0.5 * block_sum<QP_THREADS>(pc, s.red);  // PSGCFS: k_psg_cost

@@ -177,27 +177,41 @@ def test_psgcfs_main_fanuc_parity(ctx, oracle):
 
 
 def test_psgcfs_batch_parity(ctx, oracle):
+    """PSGCFS on a seeded random batch.  Noise-driven PSG steps make a few problems chaotic (a waypoint sitting on a
+    closest-link kink roughly doubles any perturbation per outer iteration, DESIGN.md "parity noise floor"), so the
+    1e-6 bar is applied (a) to every problem after ONE outer iteration (identical inputs, no accumulation) and (b) after
+    8 iterations to every problem on which the oracle itself is well conditioned: a problem may exceed 1e-6 only if the
+    oracle's own answer moves by more than 1e-7 when its noise input is perturbed by 1e-9 relative."""
     O = oracle
-    cfg = common.batch_m16ib(O, 96, horizon=30)
+    B, H, K = 96, 30, 8
+    cfg = common.batch_m16ib(O, B, horizon=H)
     s = dict(cfg["sys_info"])
     s["alpha"] = 1.0 / np.linalg.svd(s["QQ"], compute_uv=False).max()
-    s["MAX_O_ITER"] = 8
+    noise = np.random.default_rng(5).normal(0.0, 0.1, size=(B, K, H * 5))
     _set(ctx, "M16iB", cfg["robot"], cfg["obs"], s, bounds=False)
-    P = common.oracle_problem(O, "M16iB", cfg["obs"], s, solver=1)
-    noise = np.random.default_rng(5).normal(0.0, 0.1, size=(96, 8, 150))
-    ref = P.solve_batch(cfg["x0"], cfg["ff"], cfg["caug"], cfg["xref"], noise=noise, nthreads=8)
-    out = ctx.solve_batch(cfg["x0"], cfg["ff"], cfg["caug"], cfg["xref"], s["epsilon_O"], 8, solver=_lib.SOLVER_PSGCFS,
-                          noise=noise, alpha=s["alpha"])
+    args = (cfg["x0"], cfg["ff"], cfg["caug"], cfg["xref"])
+
+    def both(k, nz):
+        s["MAX_O_ITER"] = k
+        P = common.oracle_problem(O, "M16iB", cfg["obs"], s, solver=1)
+        ref = P.solve_batch(*args, noise=nz, nthreads=8)
+        out = ctx.solve_batch(*args, s["epsilon_O"], k, solver=_lib.SOLVER_PSGCFS, noise=nz, alpha=s["alpha"])
+        return P, ref, out
+
+    _, ref1, out1 = both(1, np.ascontiguousarray(noise[:, :1]))
+    _compare_solve(out1, ref1)  # (a) one projection step from identical inputs: 1e-6 everywhere
+    P, ref, out = both(K, noise)
     assert ((ref["status"] & 0xFF) == 1).any()
-    # Controls within 1e-6.  Trajectories: 1e-6 for all but kink-amplified problems.  num_jac (eps = 1e-5) turns the
-    # ~1e-15 evaluation noise of two different FP64 FK implementations (CUDA sincos/FMA vs libm) into ~1e-10 gradient
-    # noise; with noise-driven PSG steps a problem sitting on a closest-link kink doubles that per iteration (measured:
-    # 1e-9 -> 3e-8 in u over 8 iterations for one problem of 96, DESIGN.md "parity noise floor").  Rolled out over H
-    # steps this is x 70, hence 1e-5 on x for the outliers and 1e-6 for at least 98 % of the problems.
-    _compare_solve(out, ref, tol_x=1e-5, tol_u=1e-6)
+    assert (out["status"] == ref["status"]).all() and (out["iters"] == ref["iters"]).all()
     ok = (ref["status"] & 0xFF) < 2
-    dx = np.abs(out["x"][ok] - ref["x"][ok]).max(axis=1)
-    assert (dx < 1e-6).mean() >= 0.98, np.sort(dx)[-5:]
+    dx = np.abs(out["x"] - ref["x"]).max(axis=1)
+    du = np.abs(out["u"] - ref["u"]).max(axis=1)
+    bad = ok & ((dx >= 1e-6) | (du >= 1e-6))
+    assert bad.sum() <= 0.03 * ok.sum(), (int(bad.sum()), np.sort(dx[ok])[-5:])
+    if bad.any():  # (b) the oracle must be ill conditioned on exactly those problems
+        pert = P.solve_batch(*args, noise=noise * (1.0 + 1e-9), nthreads=8)
+        sens = np.abs(pert["x"] - ref["x"]).max(axis=1)
+        assert (sens[bad] > 1e-7).all(), (np.where(bad)[0], dx[bad], sens[bad])
 
 
 @pytest.mark.parametrize("name", ["main_fanuc_cfs", "main_fanuc_psgcfs", "main_2l_cfs", "m16ib_script_derivest",
