@@ -5,11 +5,18 @@
   python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm's CPU port (oracle/) on host cores
 
 One "step" = one pass of the hot path over one batch: CFS_FANUC.optimizer run to the reference's stop rule for every
-problem of a 4096-problem synthetic batch (random start/goal pairs).  `value` is measured with
-the inputs resident in HBM (cfs_solve_batch_device); `e2e` is the same batch through the host-pointer C-ABI call
-(cfs_solve_batch) with pinned host buffers, H2D and D2H inside the timed region.  Multi-GPU: every rank solves its own
-batch (weak scaling, no data-path collective) and the per-problem costs are all-gathered over NCCL for best-of
-selection (the GPU analogue of min(routeL), Lib/functions/s_Parallel_rrt.m:27).
+problem of a 4096-problem synthetic batch (random start/goal pairs).
+
+  value  whole-job throughput with the inputs resident in HBM (cfs_solve_batch_device).  The K timed steps are issued
+         round-robin on --contexts library contexts (each its own stream and buffer set), so the rare heavy-tier
+         stragglers of batch k overlap the bulk of batch k+1 -- the GPU analogue of the reference's parfor workers;
+         `latency_ms_single_batch` is one batch alone on an idle GPU.
+  e2e    the same K steps through the host-pointer C-ABI call (cfs_solve_batch_async / cfs_wait) with pinned host
+         buffers: H2D of every input and D2H of every result inside the timed region, copies of batch k+1 overlapping
+         the kernels of batch k.
+Multi-GPU: every rank solves its own batches (weak scaling, no data-path collective) and after every step the
+per-problem (cost, status) are all-gathered over NCCL for best-of selection (motionplanning_5d_m_b200.multi_gpu.best_of,
+the GPU analogue of min(routeL), Lib/functions/s_Parallel_rrt.m:27).
 """
 import argparse
 import json
@@ -24,21 +31,22 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-F_WAYPOINT_NUMJAC = 9680.0   # algorithmic FLOPs of one num_jac gradient (11 dist_arm evaluations), BASELINE.md section 3
+F_WAYPOINT_NUMJAC = 9680.0   # algorithmic FLOPs of one num_jac gradient (11 dist_arm evaluations), SURVEY.md section 8d
 F_WAYPOINT_DERIVEST = 162080.0
-HBM_BYTES_PER_PROBLEM_ITER = 14.4e3
+METRIC = "cfs_trajectories_per_sec"
 
 
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=4096)
     ap.add_argument("--horizon", type=int, default=50)
     ap.add_argument("--grad", default="numjac", choices=["numjac", "derivest"])
-    ap.add_argument("--cpu-sample", type=int, default=1024, help="problems in the bounded CPU baseline sample")
+    ap.add_argument("--contexts", type=int, default=4, help="library contexts (streams + buffer sets) the steps rotate over")
+    ap.add_argument("--cpu-reps", type=int, default=3, help="CPU baseline: passes of the oracle over the same batch")
     return ap.parse_args()
 
 
@@ -57,7 +65,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                          "--format=csv,noheader,nounits", "-lms", "50"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -98,46 +106,56 @@ def cpu_count():
         return os.cpu_count() or 1
 
 
+def workload_text(args):
+    return ("batched CFS (BASELINE.json configs[2]): %d random start/goal pairs per GPU, M16iB capsules, horizon %d, "
+            "1 obstacle capsule, %s gradients, every problem run to the reference stop rule (eps 0.1, <= 20 outer "
+            "iterations)" % (args.batch, args.horizon, "num_jac" if args.grad == "numjac" else "DERIVEST"))
+
+
 def make_oracle_problem(O, cfg, grad):
     s = cfg["sys_info"]
     return O.Problem(O.robot(cfg["ROBOT"]), s["H"], [o["l"] for o in cfg["obs"]], [o["epsilon"] for o in cfg["obs"]],
                      s["QQ"], s["lim"], s["MAX_input"], s["epsilon_O"], s["MAX_O_ITER"], solver=0, grad=grad)
 
 
-def run_reference(args, rank, world):
-    """The reference algorithm on the host CPU: the oracle port (MATLAB/Octave are not installed)."""
-    if rank != 0:
-        return
-    import oracle as O
+def oracle_batch(args, O):
     from motionplanning_5d_m_b200 import synthetic
-    O.build()
-    cores = cpu_count()
     r = O.robot("M16iB")
     o6 = O.obs6(synthetic.OBS_M16IB["l"])
     feas = lambda cand: np.array([O.dist_arm(r, th, o6)[0] >= synthetic.OBS_M16IB["D"] for th in cand])
-    S = min(args.batch, 512)
-    cfg = synthetic.batch_config_m16ib(S, feas, horizon=args.horizon)
+    return synthetic.batch_config_m16ib(args.batch, feas, horizon=args.horizon)
+
+
+def run_reference(args, rank):
+    """The reference algorithm on the host CPU.  MATLAB / Octave are not installed and the reference is pure MATLAB
+    (nothing to pip-install), so this arm times the C port of the same algorithm (oracle/) on every host core."""
+    if rank != 0:
+        return
+    import oracle as O
+    O.build()
+    cores = cpu_count()
+    cfg = oracle_batch(args, O)
     P = make_oracle_problem(O, cfg, 1 if args.grad == "derivest" else 0)
-    run = lambda: P.solve_batch(cfg["x0"], cfg["ff"], cfg["caug"], cfg["xref"], nthreads=cores)
-    for _ in range(max(args.warmup, 1)):
+    S = args.batch if args.grad == "numjac" else min(args.batch, 256)  # bounded sample per step
+    run = lambda: P.solve_batch(cfg["x0"][:S], cfg["ff"][:S], cfg["caug"][:S], cfg["xref"][:S], nthreads=cores)
+    for _ in range(min(args.warmup, 1)):
         run()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         out = run()
     dt = time.perf_counter() - t0
     val = S * args.steps / dt
-    line = {"impl": "reference", "metric": "cfs_trajectories_per_sec", "value": val, "unit": "trajectories/s",
-            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "trajectories/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * dt / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "batched CFS: random start/goal pairs, M16iB capsules, horizon %d, 1 obstacle, "
-                                   "num_jac gradients" % args.horizon if args.grad == "numjac" else
-                       "batched CFS, DERIVEST gradients", "batch": args.batch, "horizon": args.horizon,
+            "config": {"workload": workload_text(args), "batch_per_gpu": args.batch, "horizon": args.horizon,
                        "sample_per_step": S},
             "cpu_baseline": {"value": val, "unit": "trajectories/s", "cores": cores, "kind": "port",
-                             "sample": "%d problems/step of the same seeded batch, OpenMP over problems" % S},
+                             "sample": "%d problems/step of the same seeded batch, %d steps, OpenMP over problems" % (S, args.steps)},
             "e2e": {"value": val, "unit": "trajectories/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "ms_per_cfs_iter": 1e3 * dt / args.steps / max(int(out["iters"].max()), 1),
-            "note": "MATLAB/Octave unavailable offline: the C port of the reference algorithm (oracle/) is timed"}
+            "note": "MATLAB/Octave unavailable offline and the reference is MATLAB-only: the C port of the reference "
+                    "algorithm (oracle/cfs_oracle.c) is timed on all host cores"}
     print(json.dumps(line), flush=True)
 
 
@@ -147,14 +165,14 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
-        run_reference(args, rank, world)
+        run_reference(args, rank)
         return
 
     import torch
     import torch.distributed as dist
 
     import motionplanning_5d_m_b200 as M
-    from motionplanning_5d_m_b200 import _lib, synthetic
+    from motionplanning_5d_m_b200 import _lib, multi_gpu, synthetic
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; this framework has no CPU fallback")
@@ -162,160 +180,187 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    ctx = M.Context(local_rank)
-    stream = torch.cuda.Stream(device=dev)
-    ctx.set_stream(stream.cuda_stream)
 
-    B, H, nj = args.batch, args.horizon, 5
+    B, H, nj, NC = args.batch, args.horizon, 5, max(1, args.contexts)
     n, N = H * nj, 2 * H * nj
     grad_mode = _lib.GRAD_DERIVEST if args.grad == "derivest" else _lib.GRAD_NUMJAC
+    main_stream = torch.cuda.Stream(device=dev)
 
-    # ---- synthetic batch (untimed): endpoints rejection-sampled with the GPU feasibility kernel --------------------
-    robot = M.robotproperty2("M16iB")
-    r = dict(robot)
-    r["name"] = "M16iB"
-    ctx.set_robot(r, nj)
-    ctx.set_obstacles([synthetic.OBS_M16IB])
-    cfg = synthetic.batch_config_m16ib(B, lambda cand: ctx.nodes_feasible(cand)[0], horizon=H,
-                                       seed=synthetic.SEED + rank)
-    s = cfg["sys_info"]
-    ctx.set_cost(H, s["QQ"], s["lim"], s["MAX_input"])
+    # ---- contexts: one stream + one buffer set each ------------------------------------------------------------------
+    robot = dict(M.robotproperty2("M16iB"))
+    robot["name"] = "M16iB"
+    ctxs, streams = [], []
+    for c in range(NC):
+        ctx = M.Context(local_rank)
+        st = torch.cuda.Stream(device=dev)
+        ctx.set_stream(st.cuda_stream)
+        ctx.set_robot(robot, nj)
+        ctx.set_obstacles([synthetic.OBS_M16IB])
+        ctxs.append(ctx)
+        streams.append(st)
+    # ---- synthetic batches (untimed): one seeded batch per buffer set, endpoints rejection-sampled on the GPU -------------
+    cfgs = [synthetic.batch_config_m16ib(B, lambda cand: ctxs[0].nodes_feasible(cand)[0], horizon=H,
+                                         seed=synthetic.SEED + 1000 * rank + c) for c in range(NC)]
+    s = cfgs[0]["sys_info"]
     eps_o, K = float(s["epsilon_O"]), int(s["MAX_O_ITER"])
-    setup_ms = ctx.stats()["ms_setup"]
+    for ctx in ctxs:
+        ctx.set_cost(H, s["QQ"], s["lim"], s["MAX_input"])
+    setup_ms = ctxs[0].stats()["ms_setup"]
 
-    with torch.cuda.stream(stream):
-        d_in = {k: torch.from_numpy(cfg[k]).to(dev) for k in ("x0", "ff", "caug", "xref")}
-        d_out = dict(u=torch.empty((B, n), dtype=torch.float64, device=dev),
-                     x=torch.empty((B, N), dtype=torch.float64, device=dev),
-                     cost=torch.empty((B, K), dtype=torch.float64, device=dev),
-                     eu=torch.empty((B, K), dtype=torch.float64, device=dev),
-                     iters=torch.empty(B, dtype=torch.int32, device=dev),
-                     status=torch.empty(B, dtype=torch.int32, device=dev))
-        flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # 256 MB > 126 MB L2
-        gathered = torch.empty((world, B, 2), dtype=torch.float64, device=dev) if world > 1 else None
-    h_in = {k: torch.from_numpy(cfg[k]).pin_memory() for k in ("x0", "ff", "caug", "xref")}
-    h_out = dict(u=torch.empty((B, n), dtype=torch.float64).pin_memory(),
-                 x=torch.empty((B, N), dtype=torch.float64).pin_memory(),
-                 cost=torch.empty((B, K), dtype=torch.float64).pin_memory(),
-                 eu=torch.empty((B, K), dtype=torch.float64).pin_memory(),
-                 iters=torch.empty(B, dtype=torch.int32).pin_memory(),
-                 status=torch.empty(B, dtype=torch.int32).pin_memory())
+    names_in = ("x0", "ff", "caug", "xref")
 
-    def step_device(sync=False):
-        ctx.solve_batch_ptr(B, d_in["x0"].data_ptr(), d_in["ff"].data_ptr(), d_in["caug"].data_ptr(),
-                            d_in["xref"].data_ptr(), eps_o, K, d_out["u"].data_ptr(), d_out["x"].data_ptr(),
-                            d_out["cost"].data_ptr(), d_out["eu"].data_ptr(), d_out["iters"].data_ptr(),
-                            d_out["status"].data_ptr(), grad=grad_mode, device=True, sync=sync)
-        if world > 1:
-            # best-of selection: all-gather (final cost, status) of every problem, argmin over ranks (s_Parallel_rrt.m:27)
-            it = d_out["iters"].clamp(min=1).long() - 1
-            last = torch.gather(d_out["cost"], 1, it[:, None])[:, 0]
-            mine = torch.stack([last, d_out["status"].double()], dim=1)
-            dist.all_gather_into_tensor(gathered.view(-1, 2), mine)
-            cost_all = torch.where(gathered[:, :, 1] == 0, gathered[:, :, 0], torch.full_like(gathered[:, :, 0], np.inf))
-            return cost_all.argmin(dim=0)
-        return None
+    def out_set(pin):
+        mk = (lambda *sh, dt=torch.float64: torch.empty(sh, dtype=dt).pin_memory()) if pin else \
+            (lambda *sh, dt=torch.float64: torch.empty(sh, dtype=dt, device=dev))
+        return dict(u=mk(B, n), x=mk(B, N), cost=mk(B, K), eu=mk(B, K), iters=mk(B, dt=torch.int32),
+                    status=mk(B, dt=torch.int32))
 
-    def step_host():
-        ctx.solve_batch_ptr(B, h_in["x0"].data_ptr(), h_in["ff"].data_ptr(), h_in["caug"].data_ptr(),
-                            h_in["xref"].data_ptr(), eps_o, K, h_out["u"].data_ptr(), h_out["x"].data_ptr(),
-                            h_out["cost"].data_ptr(), h_out["eu"].data_ptr(), h_out["iters"].data_ptr(),
-                            h_out["status"].data_ptr(), grad=grad_mode, device=False)
+    d_in = [{k: torch.from_numpy(cfgs[c][k]).to(dev) for k in names_in} for c in range(NC)]
+    d_out = [out_set(False) for _ in range(NC)]
+    h_in = [{k: torch.from_numpy(cfgs[c][k]).pin_memory() for k in names_in} for c in range(NC)]
+    h_out = [out_set(True) for _ in range(NC)]
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # 256 MB > 126 MB L2
+    torch.cuda.synchronize(dev)
+
+    def issue(c, host):
+        i, o = (h_in[c], h_out[c]) if host else (d_in[c], d_out[c])
+        ctxs[c].solve_batch_ptr(B, i["x0"].data_ptr(), i["ff"].data_ptr(), i["caug"].data_ptr(), i["xref"].data_ptr(),
+                                eps_o, K, o["u"].data_ptr(), o["x"].data_ptr(), o["cost"].data_ptr(), o["eu"].data_ptr(),
+                                o["iters"].data_ptr(), o["status"].data_ptr(), grad=grad_mode, device=not host, sync=False)
+
+    def best_of(c):
+        """per-step exchange of the multi-GPU job: all-gather (cost, status), argmin over ranks (s_Parallel_rrt.m:27)"""
+        with torch.cuda.stream(streams[c]):
+            fc = multi_gpu.final_cost(d_out[c]["cost"], d_out[c]["iters"])
+            return multi_gpu.best_of(fc, d_out[c]["status"])[0]
+
+    def run_steps(steps, host):
+        """issue `steps` batches round-robin over the contexts; returns device ms between the first issue and the last end"""
+        t_begin = torch.cuda.Event(enable_timing=True)
+        t_end = torch.cuda.Event(enable_timing=True)
+        t_begin.record(main_stream)
+        for st in streams:
+            st.wait_event(t_begin)
+        for k in range(steps):
+            c = k % NC
+            if host and k >= NC:
+                ctxs[c].wait()  # the host buffers of this context are about to be reused
+            issue(c, host)
+            if world > 1 and not host:
+                best_of(c)
+        for c, st in enumerate(streams):
+            e = torch.cuda.Event()
+            e.record(st)
+            main_stream.wait_event(e)
+        t_end.record(main_stream)
+        torch.cuda.synchronize(dev)
+        for ctx in ctxs:
+            ctx.wait()
+        return t_begin.elapsed_time(t_end)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    def timed(fn, steps):
-        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
-        with torch.cuda.stream(stream):
-            for a, b in evs:
-                flush.zero_()        # L2 flush between timed iterations (excluded from the timed region)
-                a.record(stream)
-                fn()
-                b.record(stream)
-        torch.cuda.synchronize(dev)
-        return [a.elapsed_time(b) for a, b in evs]
-
-    # ---- warm-up --------------------------------------------------------------------------------------------------
-    with torch.cuda.stream(stream):
-        for _ in range(max(args.warmup, 3)):
-            step_device()
-        step_host()
+    # ---- warm-up -------------------------------------------------------------------------------------------------------
+    W = max(args.warmup, 3)
+    run_steps(max(W, NC), False)
+    run_steps(max(W, NC), True)
     barrier()
-
-    # ---- timed: device-resident ----------------------------------------------------------------------------------
+    # ---- timed: device-resident -------------------------------------------------------------------------------------------
     sampler = ClockSampler(local_rank)
     sampler.start()
-    time.sleep(0.15)
+    time.sleep(0.1)
+    flush.zero_()
     barrier()
-    ms_dev = timed(step_device, args.steps)
+    ms_dev = run_steps(args.steps, False)
     barrier()
-    # ---- timed: end to end through the host-pointer C ABI -----------------------------------------------------------
-    ms_e2e = timed(step_host, args.steps)
+    # ---- timed: end to end through the host-pointer C ABI -----------------------------------------------------------------
+    flush.zero_()
+    barrier()
+    ms_e2e = run_steps(args.steps, True)
     barrier()
     clocks = sampler.stop()
-
-    tot_dev = torch.tensor([sum(ms_dev), sum(ms_e2e)], dtype=torch.float64, device=dev)
+    tot = torch.tensor([ms_dev, ms_e2e], dtype=torch.float64, device=dev)
     if world > 1:
-        dist.all_reduce(tot_dev, op=dist.ReduceOp.MAX)
-    tot_dev_ms, tot_e2e_ms = float(tot_dev[0]), float(tot_dev[1])
+        dist.all_reduce(tot, op=dist.ReduceOp.MAX)
+    ms_dev, ms_e2e = float(tot[0]), float(tot[1])
 
-    # ---- instrumented pass: per-kernel CUDA events inside the library -----------------------------------------------
-    ctx.set_timing(2)
-    with torch.cuda.stream(stream):
+    # ---- one batch alone, per-tier CUDA events inside the library (timing level 2) ---------------------------------------
+    ctx0 = ctxs[0]
+    ctx0.set_timing(2)
+    lat = []
+    for _ in range(3):
         flush.zero_()
-        step_device(sync=True)
-    st = ctx.stats()
-    ctx.set_timing(1)
-    iters = d_out["iters"].cpu().numpy()
-    status = d_out["status"].cpu().numpy()
-    n_grad_launches = int(min(K, (iters + ((status & 0xFF) >= 2)).max()))
-    fp64_tf, fp64_mhz = ctx.measure_fp64_peak()
+        torch.cuda.synchronize(dev)
+        issue(0, False)
+        ctx0.wait()
+        lat.append(ctx0.stats())
+    st = min(lat, key=lambda d: d["ms_total"])
+    ctx0.set_timing(1)
+    iters = d_out[0]["iters"].cpu().numpy()
+    status = d_out[0]["status"].cpu().numpy()
+    fused = st["launches"] <= 4
+    fp64_tf, fp64_mhz = ctx0.measure_fp64_peak()
     f_wp = F_WAYPOINT_DERIVEST if args.grad == "derivest" else F_WAYPOINT_NUMJAC
     grad_flops = f_wp * st["grad_waypoints"]
-    ach_tf = grad_flops / (st["ms_grad"] * 1e-3) / 1e12 if st["ms_grad"] > 0 else 0.0
+    # stand-alone distance/gradient kernel on the same number of waypoints as the first outer iteration of the batch
+    th_all = cfgs[0]["xref"].reshape(B, H, 2 * nj)[:, :, :nj].reshape(-1, nj)
+    if args.grad == "derivest":
+        th_all = th_all[: 64 * H]
+    k1_ms = ctx0.time_dist_grad(th_all, grad=grad_mode, reps=10)
+    k1_tf = f_wp * th_all.shape[0] / (k1_ms * 1e-3) / 1e12
+    dom_ms = (st["ms_bulk"] + st["ms_heavy"]) if fused else st["ms_grad"]
+    ach_tf = grad_flops / (dom_ms * 1e-3) / 1e12 if dom_ms > 0 else 0.0
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
-    hbm_ach = HBM_BYTES_PER_PROBLEM_ITER * st["problem_iters"] / (st["ms_total"] * 1e-3) / 1e9
+    bytes_per_problem = 8.0 * ((2 * nj + n + 1 + N) + 3 * n + (n + N + 2 * K) + 1)  # inputs + v0 + outputs
+    hbm_ach = bytes_per_problem * B / (st["ms_total"] * 1e-3) / 1e9
 
     if rank == 0:
-        h2d = sum(int(h_in[k].numel() * h_in[k].element_size()) for k in h_in)
-        d2h = sum(int(h_out[k].numel() * h_out[k].element_size()) for k in h_out)
+        h2d = sum(int(t.numel() * t.element_size()) for t in h_in[0].values())
+        d2h = sum(int(t.numel() * t.element_size()) for t in h_out[0].values())
         line = {
-            "metric": "cfs_trajectories_per_sec", "value": world * B * args.steps / (tot_dev_ms * 1e-3),
-            "unit": "trajectories/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": tot_dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "batched CFS (BASELINE.json configs[2]): %d random start/goal pairs per GPU, M16iB "
-                                   "capsules, horizon %d, 1 obstacle capsule, %s gradients, run to the reference stop "
-                                   "rule (eps 0.1, <=20 outer iterations)" % (B, H, args.grad),
-                       "batch_per_gpu": B, "horizon": H, "l2": "256 MB flush between timed steps (outside the timed events)",
-                       "seed": synthetic.SEED, "parallelism": "independent problems sharded over %d GPU(s); NCCL "
-                       "all-gather of (cost,status) for best-of" % world},
-            "e2e": {"value": world * B * args.steps / (tot_e2e_ms * 1e-3), "unit": "trajectories/s",
-                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": tot_e2e_ms / args.steps,
-                    "api": "cfs_solve_batch (host pointers, pinned), H2D+solve+D2H inside the timed events"},
-            "gpu_launches": int(st["launches"]) * args.steps,
+            "metric": METRIC, "value": world * B * args.steps / (ms_dev * 1e-3), "unit": "trajectories/s", "n_gpus": world,
+            "steps": args.steps, "warmup": W, "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_text(args), "batch_per_gpu": B, "horizon": H,
+                       "l2": "%d rotating buffer sets (one seeded batch each, %.0f MB of inputs+state+outputs in total) "
+                             "> 126 MB L2; 256 MB flush before each timed region" % (NC, NC * B * (bytes_per_problem + 8 * 4 * n) / 1e6),
+                       "contexts": NC, "seed": synthetic.SEED,
+                       "parallelism": "independent problems sharded over %d GPU(s), no data-path collective; per-step NCCL "
+                                      "all-gather of (cost,status) for best-of" % world},
+            "e2e": {"value": world * B * args.steps / (ms_e2e * 1e-3), "unit": "trajectories/s",
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps,
+                    "api": "cfs_solve_batch_async + cfs_wait (host pointers, pinned): H2D + solve + D2H of every step "
+                           "inside the timed events, %d contexts in rotation" % NC},
+            "gpu_launches": int(st["launches"]) * args.steps * 2,
             "clocks": clocks,
-            "ms_per_cfs_iter": tot_dev_ms / args.steps / max(int(iters.max()), 1),
-            "problem_iters_per_sec": float(st["problem_iters"]) / (st["ms_total"] * 1e-3),
-            "roofline": {"bound": "fp64", "kernel": "k_grad_%s" % args.grad, "achieved": ach_tf, "peak": fp64_tf,
-                         "unit": "TFLOP/s", "frac": ach_tf / fp64_tf if fp64_tf else None, "traffic": None,
-                         "peak_source": "measured here by cfs_measure_fp64_peak (DFMA micro-benchmark; "
-                                        "MEASURED_PEAKS.json has no FP64 entry), implied SM clock %.0f MHz" % fp64_mhz,
-                         "algorithmic_flops_per_launch": grad_flops / max(n_grad_launches, 1),
-                         "launches": n_grad_launches, "avg_launch_ms": st["ms_grad"] / max(n_grad_launches, 1),
-                         "share_of_step": st["ms_grad"] / st["ms_total"] if st["ms_total"] else None},
-            "roofline_hbm": {"bound": "hbm", "achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s",
-                             "frac": hbm_ach / hbm_peak, "note": "14.4 KB algorithmic bytes per problem-iteration; the "
-                             "path is FP64-bound (SURVEY.md section 8d)"},
-            "breakdown_ms": {"total": st["ms_total"], "grad": st["ms_grad"], "qp_rollout": st["ms_qp"],
+            "latency_ms_single_batch": st["ms_total"],
+            "ms_per_cfs_iter": st["ms_total"] / max(int(iters.max()), 1),
+            "problem_iters_per_sec": float(st["problem_iters"]) * args.steps / (ms_dev * 1e-3),
+            "roofline": {"bound": "fp64", "kernel": "k_cfs_fused (bulk + heavy tier launches)" if fused else "k_grad",
+                         "achieved": ach_tf, "peak": fp64_tf, "unit": "TFLOP/s", "frac": ach_tf / fp64_tf if fp64_tf else None,
+                         "traffic": None,
+                         "peak_source": "measured here by cfs_measure_fp64_peak (DFMA micro-benchmark; MEASURED_PEAKS.json "
+                                        "has no FP64 entry), implied SM clock %.0f MHz" % fp64_mhz,
+                         "algorithmic_flops_per_launch": grad_flops, "avg_launch_ms": dom_ms,
+                         "note": "algorithmic FLOPs = 9680 per num_jac waypoint gradient x %d waypoint gradients "
+                                 "(SURVEY.md 8d); the fused kernel also runs the QP, roll-out and stop rule and is bound by "
+                                 "dependent-issue latency and L2 latency, not by the FP64 pipe" % st["grad_waypoints"],
+                         "share_of_step": dom_ms / st["ms_total"] if st["ms_total"] else None},
+            "roofline_k1": {"bound": "fp64", "kernel": "k_grad_%s stand-alone" % args.grad, "achieved": k1_tf, "peak": fp64_tf,
+                            "unit": "TFLOP/s", "frac": k1_tf / fp64_tf if fp64_tf else None, "waypoints": int(th_all.shape[0]),
+                            "avg_launch_ms": k1_ms},
+            "roofline_hbm": {"bound": "hbm", "achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_ach / hbm_peak,
+                             "note": "%.1f KB algorithmic bytes per problem (inputs + v0 + outputs, once per solve)" % (bytes_per_problem / 1e3)},
+            "breakdown_ms": {"single_batch_total": st["ms_total"], "fused_bulk_tier": st["ms_bulk"],
+                             "fused_heavy_tier": st["ms_heavy"], "grad_lockstep": st["ms_grad"], "qp_lockstep": st["ms_qp"],
                              "setup_once": setup_ms},
             "solve_stats": {"converged": int(((status & 0xFF) == 0).sum()), "max_iter": int(((status & 0xFF) == 1).sum()),
                             "infeasible": int(((status & 0xFF) == 2).sum()), "numerical": int(((status & 0xFF) == 3).sum()),
@@ -323,22 +368,24 @@ def main():
                             "qp_steps": int(st["qp_steps"]), "max_working_set": int(st["max_active"])},
         }
         if world == 1:
-            # bounded CPU sample of the same workload: the oracle port on all host cores, and a parity spot check
+            # bounded CPU sample of the same workload: the oracle port on all host cores, plus a parity spot check
             import oracle as O
             O.build()
-            S = min(args.cpu_sample, B)
-            P = make_oracle_problem(O, cfg, 1 if args.grad == "derivest" else 0)
+            P = make_oracle_problem(O, cfgs[0], 1 if args.grad == "derivest" else 0)
             cores = cpu_count()
+            S = B if args.grad == "numjac" else min(B, 256)
+            c0 = cfgs[0]
             t0 = time.perf_counter()
-            ref = P.solve_batch(cfg["x0"][:S], cfg["ff"][:S], cfg["caug"][:S], cfg["xref"][:S], nthreads=cores)
+            for _ in range(args.cpu_reps):
+                ref = P.solve_batch(c0["x0"][:S], c0["ff"][:S], c0["caug"][:S], c0["xref"][:S], nthreads=cores)
             dt = time.perf_counter() - t0
-            line["cpu_baseline"] = {"value": S / dt, "unit": "trajectories/s", "cores": cores, "kind": "port",
-                                    "sample": "first %d problems of the same batch, C port of the reference algorithm "
-                                              "(oracle/), OpenMP over problems" % S, "seconds": dt}
-            xg = h_out["x"].numpy()[:S]
-            ok = ((ref["status"] & 0xFF) < 2) & (ref["status"] == h_out["status"].numpy()[:S])
-            line["parity_sample"] = {"problems": S, "status_equal": bool((ref["status"] == h_out["status"].numpy()[:S]).all()),
-                                     "iters_equal": bool((ref["iters"] == h_out["iters"].numpy()[:S]).all()),
+            line["cpu_baseline"] = {"value": S * args.cpu_reps / dt, "unit": "trajectories/s", "cores": cores, "kind": "port",
+                                    "sample": "%d passes over %d problems of the same batch, C port of the reference "
+                                              "algorithm (oracle/), OpenMP over problems" % (args.cpu_reps, S), "seconds": dt}
+            xg, sg, ig = (h_out[0][k].numpy()[:S] for k in ("x", "status", "iters"))
+            ok = ((ref["status"] & 0xFF) < 2) & (ref["status"] == sg)
+            line["parity_sample"] = {"problems": S, "status_equal": bool((ref["status"] == sg).all()),
+                                     "iters_equal": bool((ref["iters"] == ig).all()),
                                      "max_abs_dx": float(np.abs(xg[ok] - ref["x"][ok]).max()) if ok.any() else None}
         print(json.dumps(line), flush=True)
     if world > 1:

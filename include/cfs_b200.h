@@ -90,6 +90,15 @@ int cfs_solve_batch(cfs_ctx *ctx, int B, int solver, int grad, const double *x0 
                     int max_outer, double alpha, double *u /*n x B*/, double *x /*2njH x B*/,
                     double *cost_hist /*max_outer x B*/, double *e_u_hist /*max_outer x B or NULL*/, int *iters /*B*/,
                     int *status /*B*/);
+/* Asynchronous form of cfs_solve_batch: enqueues H2D copies, the solve and the D2H copies on the context stream and
+ * returns.  The host buffers must stay valid (and should be pinned for the copies to overlap other contexts' kernels)
+ * until cfs_wait(ctx) returns.  One batch may be in flight per context; several contexts on one device pipeline
+ * copy(k+1) | solve(k) | copy(k-1)  -- the GPU analogue of the reference's parfor workers (s_Parallel_rrt.m:16). */
+int cfs_solve_batch_async(cfs_ctx *ctx, int B, int solver, int grad, const double *x0, const double *ff, const double *caug,
+                          const double *xref, const double *noise, double eps_outer, int max_outer, double alpha, double *u,
+                          double *x, double *cost_hist, double *e_u_hist, int *iters, int *status);
+/* Blocks until the context's stream is idle and collects the statistics of the batch in flight (if any). */
+int cfs_wait(cfs_ctx *ctx);
 /* Same, every pointer is a DEVICE pointer on ctx's device (inputs already resident in HBM); asynchronous on the
  * context stream unless sync != 0. */
 int cfs_solve_batch_device(cfs_ctx *ctx, int B, int solver, int grad, const double *x0, const double *ff,
@@ -102,6 +111,10 @@ int cfs_solve_batch_device(cfs_ctx *ctx, int B, int solver, int grad, const doub
  *   dist (n_obs x N), linkid (n_obs x N, 1-based), grad (nj x n_obs x N), flags (N: CFS_FLAG_TOUCH or 0). */
 int cfs_dist_grad(cfs_ctx *ctx, int N, int grad_mode, const double *theta /*nj x N*/, double *dist, int *linkid,
                   double *grad, int *flags);
+
+/* Times the stand-alone distance/gradient kernel (K1 / K1d) on N configurations resident in HBM: theta is uploaded once
+ * (untimed), 2 warm-up launches, then `reps` launches bracketed by CUDA events on the context stream. */
+int cfs_time_dist_grad(cfs_ctx *ctx, int N, int grad_mode, const double *theta /*nj x N*/, int reps, double *ms_per_launch);
 
 /* CFS_FANUC.get_con (Lib/CFS_FANUC.m:101-135) for ONE problem, dense and in the reference's row order
  * (per obstacle j, step i: 1 obstacle row, nj rows +Baug_w, nj rows -Baug_w).  Ainq is m x n column-major,
@@ -129,6 +142,7 @@ typedef struct {
   long long qp_steps;       /* sum of dual active-set iterations                                          */
   int launches;           /* kernels launched by the last solve                                           */
   int max_active;         /* largest working set seen                                                     */
+  double ms_bulk, ms_heavy; /* timing level 2, fused kernel: device time of its bulk / heavy tier launch        */
 } cfs_stats;
 int cfs_get_stats(const cfs_ctx *ctx, cfs_stats *out);
 /* level 1 (default): whole-solve time only; level 2: per-kernel CUDA events (ms_grad / ms_qp) */

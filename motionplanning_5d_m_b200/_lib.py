@@ -19,7 +19,7 @@ FLAG_TOUCH = 0x100
 
 # every symbol include/cfs_b200.h declares (tests check that the library exports all of them)
 SYMBOLS = ["cfs_create", "cfs_destroy", "cfs_last_error", "cfs_version", "cfs_set_stream", "cfs_set_option", "cfs_set_robot", "cfs_set_obstacles",
-           "cfs_set_cost", "cfs_solve_batch", "cfs_solve_batch_device", "cfs_dist_grad", "cfs_get_con",
+           "cfs_set_cost", "cfs_solve_batch", "cfs_solve_batch_async", "cfs_wait", "cfs_solve_batch_device", "cfs_dist_grad", "cfs_time_dist_grad", "cfs_get_con",
            "cfs_nodes_feasible", "cfs_nearest_steer", "cfs_get_stats", "cfs_set_timing", "cfs_get_iter_times", "cfs_get_problem_steps", "cfs_get_qp_profile", "cfs_measure_fp64_peak"]
 
 
@@ -31,7 +31,7 @@ class Stats(C.Structure):
     _fields_ = [("ms_setup", C.c_double), ("ms_total", C.c_double), ("ms_grad", C.c_double), ("ms_qp", C.c_double),
                 ("ms_h2d", C.c_double), ("ms_d2h", C.c_double), ("grad_waypoints", C.c_longlong),
                 ("problem_iters", C.c_longlong), ("qp_steps", C.c_longlong), ("launches", C.c_int),
-                ("max_active", C.c_int)]
+                ("max_active", C.c_int), ("ms_bulk", C.c_double), ("ms_heavy", C.c_double)]
 
 
 _lib = None
@@ -161,11 +161,15 @@ class Context:
                                                   vp(e_u_hist), vp(iters), vp(status), C.c_int(1 if sync else 0))
             self._check(rc, "cfs_solve_batch_device")
         else:
-            rc = self._lib.cfs_solve_batch(self._h, C.c_int(B), C.c_int(solver), C.c_int(grad), vp(x0), vp(ff), vp(caug),
-                                           vp(xref), vp(noise), C.c_double(eps_outer), C.c_int(max_outer),
-                                           C.c_double(alpha), vp(u), vp(x), vp(cost_hist), vp(e_u_hist), vp(iters),
-                                           vp(status))
-            self._check(rc, "cfs_solve_batch")
+            fn = self._lib.cfs_solve_batch if sync else self._lib.cfs_solve_batch_async
+            rc = fn(self._h, C.c_int(B), C.c_int(solver), C.c_int(grad), vp(x0), vp(ff), vp(caug), vp(xref), vp(noise),
+                    C.c_double(eps_outer), C.c_int(max_outer), C.c_double(alpha), vp(u), vp(x), vp(cost_hist),
+                    vp(e_u_hist), vp(iters), vp(status))
+            self._check(rc, "cfs_solve_batch" if sync else "cfs_solve_batch_async")
+
+    def wait(self):
+        """Block until the batch enqueued with sync=False has finished; collects its statistics."""
+        self._check(self._lib.cfs_wait(self._h), "cfs_wait")
 
     def dist_grad(self, theta, grad=GRAD_NUMJAC):
         """theta (N,nj) -> dist (N,nobs), linkid (N,nobs), grad (N,nobs,nj), flags (N,)"""
@@ -180,6 +184,15 @@ class Context:
                                      _dp(flags))
         self._check(rc, "cfs_dist_grad")
         return dist, lid, g, flags
+
+    def time_dist_grad(self, theta, grad=GRAD_NUMJAC, reps=10):
+        """Average device time (ms) of one stand-alone distance/gradient kernel launch over theta (N,nj) resident in HBM."""
+        theta = _f64(theta)
+        ms = C.c_double()
+        rc = self._lib.cfs_time_dist_grad(self._h, C.c_int(theta.shape[0]), C.c_int(grad), _dp(theta), C.c_int(reps),
+                                          C.byref(ms))
+        self._check(rc, "cfs_time_dist_grad")
+        return ms.value
 
     def get_con(self, x0, xcur, u, grad=GRAD_NUMJAC, margin_is_D=False):
         m = self.nobs * self.H * ((1 + 2 * self.nj) if self.has_lim else 1)

@@ -54,9 +54,16 @@ struct cfs_ctx {
   // timing
   std::vector<cudaEvent_t> ev;
   cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+  cudaEvent_t ev_h[4] = {nullptr, nullptr, nullptr, nullptr};  // H2D begin/end, D2H begin/end of the host-pointer entry
+  struct {
+    bool active = false, host = false;
+    int B = 0, max_outer = 0;
+    const int *d_iters = nullptr, *d_status = nullptr;
+  } pending;
   int timing_level = 1;
   bool use_fused = true;  // cfs_set_option("fused")
   int esc_steps = 48;     // cfs_set_option("esc_steps")
+  bool fused_last = false;
   std::vector<double> it_grad_ms, it_qp_ms;
   cfs_stats stats;
 };
@@ -212,6 +219,8 @@ extern "C" void cfs_destroy(cfs_ctx *ctx) {
   for (cudaEvent_t e : ctx->ev) cudaEventDestroy(e);
   if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);
   if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);
+  for (cudaEvent_t e : ctx->ev_h)
+    if (e) cudaEventDestroy(e);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;
 }
@@ -445,7 +454,7 @@ static int solve_device(cfs_ctx *ctx, int B, int solver, int grad, const double 
   a.slab = ptr<double>(ctx->slab);
 
   const bool detail = ctx->timing_level >= 2;
-  const size_t need_ev = detail ? (size_t)3 * max_outer + 2 : 0;
+  const size_t need_ev = detail ? (size_t)3 * max_outer + 3 : 0;
   while (ctx->ev.size() < need_ev) {
     cudaEvent_t e;
     CU(cudaEventCreate(&e));
@@ -467,12 +476,17 @@ static int solve_device(cfs_ctx *ctx, int B, int solver, int grad, const double 
     a.esc_count = cnt + 5;
     a.work_counter2 = cnt + 4;
     a.esc_steps = ctx->esc_steps;
+    if (detail) CU(cudaEventRecord(ctx->ev[0], st));
     CU(launch_fused(a, grid, 0, st)); ++launches;        // bulk tier: every problem
+    if (detail) CU(cudaEventRecord(ctx->ev[1], st));
     CU(launch_fused(a, grid_heavy, 1, st)); ++launches;  // heavy tier: the (device-side) escalation list, usually < 1 %
+    if (detail) CU(cudaEventRecord(ctx->ev[2], st));
+    ctx->fused_last = true;
     CU(cudaEventRecord(ctx->ev_b, st));
     ctx->stats.launches = launches;
     return 0;
   }
+  ctx->fused_last = false;
   CU(launch_solve_init(a, st)); ++launches;
   if (psg) {
     CU(cudaMemsetAsync(a.w, 0, sizeof(double) * (size_t)n * B, st));  // QQ*u at u = 0
@@ -541,9 +555,17 @@ static int collect_stats(cfs_ctx *ctx, int B, int max_outer, const int *d_iters,
   ctx->stats.problem_iters = pit;
   ctx->stats.grad_waypoints = gev * ctx->H * ctx->nobs;
   ctx->stats.ms_grad = ctx->stats.ms_qp = 0;
+  ctx->stats.ms_bulk = ctx->stats.ms_heavy = 0;
+  if (ctx->timing_level >= 2 && ctx->fused_last && ctx->ev.size() >= 3) {
+    float a = 0, b = 0;
+    cudaEventElapsedTime(&a, ctx->ev[0], ctx->ev[1]);
+    cudaEventElapsedTime(&b, ctx->ev[1], ctx->ev[2]);
+    ctx->stats.ms_bulk = a;
+    ctx->stats.ms_heavy = b;
+  }
   ctx->it_grad_ms.clear();
   ctx->it_qp_ms.clear();
-  if (ctx->timing_level >= 2 && ctx->ev.size() >= (size_t)3 * max_outer && ctx->stats.launches > 4) {
+  if (ctx->timing_level >= 2 && !ctx->fused_last && ctx->ev.size() >= (size_t)3 * max_outer) {
     for (int k = 0; k < max_outer; ++k) {
       float a = 0, b = 0;
       cudaEventElapsedTime(&a, ctx->ev[3 * k], ctx->ev[3 * k + 1]);
@@ -556,6 +578,8 @@ static int collect_stats(cfs_ctx *ctx, int B, int max_outer, const int *d_iters,
   }
   return 0;
 }
+
+static int finish_pending(cfs_ctx *ctx);
 
 static int check_solve_args(cfs_ctx *ctx, int B, int solver, int grad, const void *x0, const void *ff, const void *caug,
                             const void *xref, int max_outer, const void *u, const void *x, const void *cost_hist,
@@ -579,21 +603,53 @@ extern "C" int cfs_solve_batch_device(cfs_ctx *ctx, int B, int solver, int grad,
   if (rc) return rc;
   if (B == 0) return 0;
   CU(cudaSetDevice(ctx->device));
+  ctx->pending.active = false;  // device-pointer entry: statistics of an un-waited earlier batch are dropped
   rc = solve_device(ctx, B, solver, grad, x0, ff, caug, xref, noise, eps_outer, max_outer, alpha, u, x, cost_hist,
                     e_u_hist, iters, status);
   if (rc) return rc;
-  if (sync) return collect_stats(ctx, B, max_outer, iters, status);
+  ctx->pending.active = true;
+  ctx->pending.host = false;
+  ctx->pending.B = B;
+  ctx->pending.max_outer = max_outer;
+  ctx->pending.d_iters = iters;
+  ctx->pending.d_status = status;
+  if (sync) return finish_pending(ctx);
   return 0;
 }
 
-extern "C" int cfs_solve_batch(cfs_ctx *ctx, int B, int solver, int grad, const double *x0, const double *ff,
-                               const double *caug, const double *xref, const double *noise, double eps_outer,
-                               int max_outer, double alpha, double *u, double *x, double *cost_hist, double *e_u_hist,
-                               int *iters, int *status) {
+static int finish_pending(cfs_ctx *ctx) {
+  if (!ctx->pending.active) return 0;
+  ctx->pending.active = false;
+  int rc = collect_stats(ctx, ctx->pending.B, ctx->pending.max_outer, ctx->pending.d_iters, ctx->pending.d_status);
+  if (ctx->pending.host) {
+    float a = 0, b = 0;
+    cudaEventElapsedTime(&a, ctx->ev_h[0], ctx->ev_h[1]);
+    cudaEventElapsedTime(&b, ctx->ev_h[2], ctx->ev_h[3]);
+    ctx->stats.ms_h2d = a;
+    ctx->stats.ms_d2h = b;
+  }
+  return rc;
+}
+
+extern "C" int cfs_wait(cfs_ctx *ctx) {
+  if (!ctx) return CFS_E_ARG;
+  CU(cudaSetDevice(ctx->device));
+  if (!ctx->pending.active) {
+    CU(cudaStreamSynchronize(ctx->stream));
+    return 0;
+  }
+  return finish_pending(ctx);
+}
+
+extern "C" int cfs_solve_batch_async(cfs_ctx *ctx, int B, int solver, int grad, const double *x0, const double *ff,
+                                     const double *caug, const double *xref, const double *noise, double eps_outer,
+                                     int max_outer, double alpha, double *u, double *x, double *cost_hist,
+                                     double *e_u_hist, int *iters, int *status) {
   int rc = check_solve_args(ctx, B, solver, grad, x0, ff, caug, xref, max_outer, u, x, cost_hist, iters, status);
   if (rc) return rc;
   if (B == 0) return 0;
   CU(cudaSetDevice(ctx->device));
+  if (ctx->pending.active && (rc = finish_pending(ctx))) return rc;  // one batch in flight per context
   const int nj = ctx->nj, n = ctx->n, K = max_outer > 0 ? max_outer : 1;
   cudaStream_t st = ctx->stream;
   if ((rc = ensure(ctx, ctx->x0, sizeof(double) * 2 * nj * B))) return rc;
@@ -607,36 +663,45 @@ extern "C" int cfs_solve_batch(cfs_ctx *ctx, int B, int solver, int grad, const 
   if ((rc = ensure(ctx, ctx->iters, sizeof(int) * B))) return rc;
   if ((rc = ensure(ctx, ctx->status, sizeof(int) * B))) return rc;
   if (noise && (rc = ensure(ctx, ctx->noise, sizeof(double) * (size_t)n * K * B))) return rc;
-  cudaEvent_t h0, h1, h2, h3;
-  CU(cudaEventCreate(&h0)); CU(cudaEventCreate(&h1)); CU(cudaEventCreate(&h2)); CU(cudaEventCreate(&h3));
-  CU(cudaEventRecord(h0, st));
+  for (cudaEvent_t &e : ctx->ev_h)
+    if (!e) CU(cudaEventCreate(&e));
+  CU(cudaEventRecord(ctx->ev_h[0], st));
   CU(cudaMemcpyAsync(ctx->x0.p, x0, sizeof(double) * 2 * nj * B, cudaMemcpyHostToDevice, st));
   CU(cudaMemcpyAsync(ctx->ff.p, ff, sizeof(double) * (size_t)n * B, cudaMemcpyHostToDevice, st));
   CU(cudaMemcpyAsync(ctx->caug.p, caug, sizeof(double) * B, cudaMemcpyHostToDevice, st));
   CU(cudaMemcpyAsync(ctx->xref.p, xref, sizeof(double) * (size_t)2 * n * B, cudaMemcpyHostToDevice, st));
   if (noise) CU(cudaMemcpyAsync(ctx->noise.p, noise, sizeof(double) * (size_t)n * K * B, cudaMemcpyHostToDevice, st));
-  CU(cudaEventRecord(h1, st));
+  CU(cudaEventRecord(ctx->ev_h[1], st));
   rc = solve_device(ctx, B, solver, grad, ptr<double>(ctx->x0), ptr<double>(ctx->ff), ptr<double>(ctx->caug),
                     ptr<double>(ctx->xref), noise ? ptr<double>(ctx->noise) : nullptr, eps_outer, max_outer, alpha,
                     ptr<double>(ctx->u), ptr<double>(ctx->x), ptr<double>(ctx->cost), ptr<double>(ctx->eu),
                     ptr<int>(ctx->iters), ptr<int>(ctx->status));
   if (rc) return rc;
-  CU(cudaEventRecord(h2, st));
+  CU(cudaEventRecord(ctx->ev_h[2], st));
   CU(cudaMemcpyAsync(u, ctx->u.p, sizeof(double) * (size_t)n * B, cudaMemcpyDeviceToHost, st));
   CU(cudaMemcpyAsync(x, ctx->x.p, sizeof(double) * (size_t)2 * n * B, cudaMemcpyDeviceToHost, st));
   CU(cudaMemcpyAsync(cost_hist, ctx->cost.p, sizeof(double) * (size_t)max_outer * B, cudaMemcpyDeviceToHost, st));
   if (e_u_hist) CU(cudaMemcpyAsync(e_u_hist, ctx->eu.p, sizeof(double) * (size_t)max_outer * B, cudaMemcpyDeviceToHost, st));
   CU(cudaMemcpyAsync(iters, ctx->iters.p, sizeof(int) * B, cudaMemcpyDeviceToHost, st));
   CU(cudaMemcpyAsync(status, ctx->status.p, sizeof(int) * B, cudaMemcpyDeviceToHost, st));
-  CU(cudaEventRecord(h3, st));
-  rc = collect_stats(ctx, B, max_outer, ptr<int>(ctx->iters), ptr<int>(ctx->status));
-  float a = 0, b = 0;
-  cudaEventElapsedTime(&a, h0, h1);
-  cudaEventElapsedTime(&b, h2, h3);
-  ctx->stats.ms_h2d = a;
-  ctx->stats.ms_d2h = b;
-  cudaEventDestroy(h0); cudaEventDestroy(h1); cudaEventDestroy(h2); cudaEventDestroy(h3);
-  return rc;
+  CU(cudaEventRecord(ctx->ev_h[3], st));
+  ctx->pending.active = true;
+  ctx->pending.host = true;
+  ctx->pending.B = B;
+  ctx->pending.max_outer = max_outer;
+  ctx->pending.d_iters = ptr<int>(ctx->iters);
+  ctx->pending.d_status = ptr<int>(ctx->status);
+  return 0;
+}
+
+extern "C" int cfs_solve_batch(cfs_ctx *ctx, int B, int solver, int grad, const double *x0, const double *ff,
+                               const double *caug, const double *xref, const double *noise, double eps_outer,
+                               int max_outer, double alpha, double *u, double *x, double *cost_hist, double *e_u_hist,
+                               int *iters, int *status) {
+  int rc = cfs_solve_batch_async(ctx, B, solver, grad, x0, ff, caug, xref, noise, eps_outer, max_outer, alpha, u, x,
+                                 cost_hist, e_u_hist, iters, status);
+  if (rc || B == 0) return rc;
+  return cfs_wait(ctx);
 }
 
 // ---- direct kernels -------------------------------------------------------------------------------------------------
@@ -673,6 +738,41 @@ extern "C" int cfs_dist_grad(cfs_ctx *ctx, int N, int grad_mode, const double *t
   if (linkid) CU(cudaMemcpyAsync(linkid, d_lid, sizeof(int) * (size_t)O * N, cudaMemcpyDeviceToHost, st));
   if (flags) CU(cudaMemcpyAsync(flags, d_flags, sizeof(int) * (size_t)N, cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
+  return 0;
+}
+
+extern "C" int cfs_time_dist_grad(cfs_ctx *ctx, int N, int grad_mode, const double *theta, int reps, double *ms_per_launch) {
+  if (!ctx || !theta || !ms_per_launch || N <= 0 || reps <= 0) return CFS_E_ARG;
+  int rc = check_ready(ctx, false);
+  if (rc) return rc;
+  if (ctx->nobs == 0) return fail(ctx, CFS_E_STATE, "cfs_time_dist_grad: no obstacles");
+  CU(cudaSetDevice(ctx->device));
+  const int nj = ctx->nj, O = ctx->nobs;
+  cudaStream_t st = ctx->stream;
+  if ((rc = ensure(ctx, ctx->scratch_theta, sizeof(double) * (size_t)nj * N))) return rc;
+  const size_t bytes_out = (sizeof(double) * (1 + nj) + sizeof(int)) * (size_t)O * N + sizeof(int) * (size_t)N + 64;
+  if ((rc = ensure(ctx, ctx->scratch_out, bytes_out))) return rc;
+  double *d_dist = ptr<double>(ctx->scratch_out);
+  double *d_grad = d_dist + (size_t)O * N;
+  int *d_lid = reinterpret_cast<int *>(d_grad + (size_t)O * N * nj);
+  int *d_flags = d_lid + (size_t)O * N;
+  CU(cudaMemcpyAsync(ctx->scratch_theta.p, theta, sizeof(double) * (size_t)nj * N, cudaMemcpyHostToDevice, st));
+  CU(cudaMemsetAsync(d_flags, 0, sizeof(int) * N, st));
+  GradArgs g;
+  memset(&g, 0, sizeof(g));
+  g.tab = ctx->dtab; g.dv = ctx->ddv;
+  g.x = ptr<double>(ctx->scratch_theta);
+  g.ld_prob = nj; g.ld_i = 0; g.nslots = N; g.H = 1; g.nj = nj; g.nobs = O;
+  g.o_prob = O; g.o_obs = 1; g.o_i = 0;
+  g.dist = d_dist; g.linkid = d_lid; g.grad = d_grad; g.flags = d_flags;
+  for (int w = 0; w < 2; ++w) CU(grad_mode == CFS_GRAD_DERIVEST ? launch_grad_derivest(g, st) : launch_grad_numjac(g, st));
+  CU(cudaEventRecord(ctx->ev_a, st));
+  for (int r = 0; r < reps; ++r) CU(grad_mode == CFS_GRAD_DERIVEST ? launch_grad_derivest(g, st) : launch_grad_numjac(g, st));
+  CU(cudaEventRecord(ctx->ev_b, st));
+  CU(cudaStreamSynchronize(st));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, ctx->ev_a, ctx->ev_b);
+  *ms_per_launch = ms / reps;
   return 0;
 }
 
