@@ -4,6 +4,13 @@
  * A from-scratch C restatement of the reference's MATLAB algorithm; each function cites the
  * reference file:line it follows.  Compile with -ffp-contract=off so that the operation
  * order written here is the operation order executed.
+ *
+ * Pinning status.  PINNED against the reference's own known answers (tests/test_oracle.py, tests/golden/kat.json):
+ * distLinSeg doc example (distLinSeg.m:15-18), derivest(@exp,1) (derivest.m:163-174), the DERIVEST demo values
+ * (demo/derivest_demo.m:13,31,71,82), robotproperty2 constants, plus an independent numpy restatement.
+ * PARITY UNPINNED for quadprog (Optimization Toolbox, not in the reference tree, no MATLAB/Octave offline): the dense
+ * Goldfarb-Idnani solver below stands in for it; the QPs are strictly convex, so the optimum is unique.  No golden
+ * OUTPUTS of CFS/PSGCFS exist in the reference; tests/golden/cases.npz are outputs of THIS oracle (regression pins).
  */
 #include "cfs_oracle.h"
 
