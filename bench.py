@@ -45,7 +45,7 @@ def parse_args():
     ap.add_argument("--batch", type=int, default=4096)
     ap.add_argument("--horizon", type=int, default=50)
     ap.add_argument("--grad", default="numjac", choices=["numjac", "derivest"])
-    ap.add_argument("--contexts", type=int, default=4, help="library contexts (streams + buffer sets) the steps rotate over")
+    ap.add_argument("--contexts", type=int, default=8, help="library contexts (streams + buffer sets) the steps rotate over")
     ap.add_argument("--cpu-reps", type=int, default=3, help="CPU baseline: passes of the oracle over the same batch")
     return ap.parse_args()
 
