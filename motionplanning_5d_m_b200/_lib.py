@@ -136,6 +136,8 @@ class Context:
         (the C ABI's column-major 'n x B' is exactly this C-contiguous (B,n) array)."""
         x0, ff, caug, xref = _f64(x0), _f64(ff), _f64(caug), _f64(xref)
         B = x0.shape[0]
+        if not getattr(self, "n", 0):
+            raise CfsError("cost not set (cfs_set_cost)")
         n, N = self.n, 2 * self.n
         assert x0.shape == (B, 2 * self.nj) and ff.shape == (B, n) and xref.shape == (B, N) and caug.shape == (B,)
         nz = None if noise is None else _f64(noise)

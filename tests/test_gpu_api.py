@@ -1,0 +1,130 @@
+"""-m gpu : C-ABI behaviour around the hot path -- edge cases, error paths, the asynchronous entry, option switches."""
+import numpy as np
+import pytest
+
+import motionplanning_5d_m_b200 as M
+from motionplanning_5d_m_b200 import _lib
+from tests import common
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(ctx, cfg):
+    s = cfg["sys_info"]
+    r = dict(cfg["robot"])
+    r["name"] = "M16iB"
+    ctx.set_robot(r, 5)
+    ctx.set_obstacles(cfg["obs"])
+    ctx.set_cost(s["H"], s["QQ"], s["lim"], s["MAX_input"])
+    return s
+
+
+def test_empty_batch_and_single_problem(ctx, oracle):
+    cfg = common.batch_m16ib(oracle, 3, horizon=12)
+    s = _setup(ctx, cfg)
+    out = ctx.solve_batch(cfg["x0"][:0], cfg["ff"][:0], cfg["caug"][:0], cfg["xref"][:0], s["epsilon_O"], s["MAX_O_ITER"])
+    assert out["u"].shape == (0, 60) and out["status"].shape == (0,)
+    one = ctx.solve_batch(cfg["x0"][:1], cfg["ff"][:1], cfg["caug"][:1], cfg["xref"][:1], s["epsilon_O"], s["MAX_O_ITER"])
+    allb = ctx.solve_batch(cfg["x0"], cfg["ff"], cfg["caug"], cfg["xref"], s["epsilon_O"], s["MAX_O_ITER"])
+    # a problem's result does not depend on what else is in the batch (bit for bit)
+    assert np.array_equal(one["u"][0], allb["u"][0]) and np.array_equal(one["x"][0], allb["x"][0])
+    assert one["iters"][0] == allb["iters"][0] and one["status"][0] == allb["status"][0]
+
+
+def test_no_obstacles_is_the_unconstrained_or_bounded_qp(ctx, oracle):
+    """obs = {} : get_con contributes nothing; with lim and MAX_input the QP still has velocity rows and bounds."""
+    cfg = common.batch_m16ib(oracle, 4, horizon=10)
+    s = cfg["sys_info"]
+    r = dict(cfg["robot"])
+    r["name"] = "M16iB"
+    ctx.set_robot(r, 5)
+    ctx.set_obstacles([])
+    ctx.set_cost(s["H"], s["QQ"], None, None)
+    out = ctx.solve_batch(cfg["x0"], cfg["ff"], cfg["caug"], cfg["xref"], s["epsilon_O"], 3)
+    u_unc = -np.linalg.solve(s["QQ"], cfg["ff"].T).T
+    assert np.abs(out["u"] - u_unc).max() < 1e-9 * max(1.0, np.abs(u_unc).max())
+    assert ((out["status"] & 0xFF) <= 1).all()
+
+
+def test_max_outer_zero_and_one(ctx, oracle):
+    cfg = common.batch_m16ib(oracle, 5, horizon=12)
+    s = _setup(ctx, cfg)
+    P0 = common.oracle_problem(oracle, "M16iB", cfg["obs"], dict(s, MAX_O_ITER=1))
+    ref = P0.solve_batch(cfg["x0"], cfg["ff"], cfg["caug"], cfg["xref"])
+    out = ctx.solve_batch(cfg["x0"], cfg["ff"], cfg["caug"], cfg["xref"], s["epsilon_O"], 1)
+    assert (out["iters"] == ref["iters"]).all() and (out["status"] == ref["status"]).all()
+    out0 = ctx.solve_batch(cfg["x0"], cfg["ff"], cfg["caug"], cfg["xref"], s["epsilon_O"], 0)
+    assert (out0["iters"] == 0).all() and ((out0["status"] & 0xFF) == _lib.STATUS_MAX_ITER).all()
+    assert np.array_equal(out0["x"], cfg["xref"]) and not out0["u"].any()
+
+
+def test_async_entry_matches_blocking_entry(ctx, oracle):
+    import torch
+    cfg = common.batch_m16ib(oracle, 40, horizon=20)
+    s = _setup(ctx, cfg)
+    B, n, N, K = 40, 100, 200, int(s["MAX_O_ITER"])
+    ref = ctx.solve_batch(cfg["x0"], cfg["ff"], cfg["caug"], cfg["xref"], s["epsilon_O"], K)
+    hin = {k: torch.from_numpy(cfg[k]).pin_memory() for k in ("x0", "ff", "caug", "xref")}
+    mk = lambda *sh, dt=torch.float64: torch.zeros(sh, dtype=dt).pin_memory()
+    o = dict(u=mk(B, n), x=mk(B, N), cost=mk(B, K), eu=mk(B, K), iters=mk(B, dt=torch.int32), status=mk(B, dt=torch.int32))
+    ctx.solve_batch_ptr(B, hin["x0"].data_ptr(), hin["ff"].data_ptr(), hin["caug"].data_ptr(), hin["xref"].data_ptr(),
+                        s["epsilon_O"], K, o["u"].data_ptr(), o["x"].data_ptr(), o["cost"].data_ptr(), o["eu"].data_ptr(),
+                        o["iters"].data_ptr(), o["status"].data_ptr(), device=False, sync=False)
+    ctx.wait()
+    assert np.array_equal(o["u"].numpy(), ref["u"]) and np.array_equal(o["x"].numpy(), ref["x"])
+    assert np.array_equal(o["iters"].numpy(), ref["iters"]) and np.array_equal(o["status"].numpy(), ref["status"])
+    assert ctx.stats()["problem_iters"] == int(ref["iters"].sum())
+
+
+def test_escalation_threshold_does_not_change_results(ctx, oracle):
+    """The heavy tier resumes escalated problems: forcing (nearly) every QP through it must give the same answers."""
+    cfg = common.batch_m16ib(oracle, 64, horizon=30)
+    s = _setup(ctx, cfg)
+    a = ctx.solve_batch(cfg["x0"], cfg["ff"], cfg["caug"], cfg["xref"], s["epsilon_O"], s["MAX_O_ITER"])
+    ctx.set_option("esc_steps", 2)
+    b = ctx.solve_batch(cfg["x0"], cfg["ff"], cfg["caug"], cfg["xref"], s["epsilon_O"], s["MAX_O_ITER"])
+    ctx.set_option("esc_steps", 48)
+    assert (a["status"] == b["status"]).all() and (a["iters"] == b["iters"]).all()
+    ok = (a["status"] & 0xFF) < 2
+    assert np.abs(a["x"][ok] - b["x"][ok]).max() < 1e-9 and np.abs(a["u"][ok] - b["u"][ok]).max() < 1e-9
+
+
+def test_error_paths(ctx, oracle):
+    c2 = M.Context(0)
+    with pytest.raises(M.CfsError, match="robot not set"):
+        c2.dist_grad(np.zeros((1, 5)))
+    cfg = common.batch_m16ib(oracle, 2, horizon=8)
+    r = dict(cfg["robot"])
+    r["name"] = "M16iB"
+    c2.set_robot(r, 5)
+    c2.set_obstacles(cfg["obs"])
+    s = cfg["sys_info"]
+    with pytest.raises(M.CfsError, match="cost not set"):
+        c2.solve_batch(cfg["x0"], cfg["ff"], cfg["caug"], cfg["xref"], 0.1, 3)
+    bad = -np.eye(40)
+    with pytest.raises(M.CfsError, match="not positive definite"):
+        c2.set_cost(8, bad, None, None)
+    with pytest.raises(M.CfsError, match="unknown option"):
+        c2.set_option("no_such_option", 1)
+    c2.close()
+
+
+def test_many_obstacles_and_large_horizon(ctx, oracle):
+    """CFS_MAX_OBS obstacles and a horizon the fused kernel does not cover (falls back to the launch-per-iteration path)."""
+    rng = np.random.default_rng(3)
+    robot = M.robotproperty2("M16iB")
+    r = dict(robot)
+    r["name"] = "M16iB"
+    ctx.set_robot(r, 5)
+    obs = [{"l": np.array([[3.9 + 0.3 * rng.random(), 3.9 + 0.3 * rng.random()], [8.3, 8.3], [0.0, 1.5 + rng.random()]]),
+            "D": 0.05, "epsilon": 0.05} for _ in range(32)]
+    ctx.set_obstacles(obs)
+    th = common.sampling_box(rng, 200)
+    dist, lid, g, flags = ctx.dist_grad(th)
+    rr = oracle.robot("M16iB")
+    for j in (0, 13, 31):
+        o6 = oracle.obs6(obs[j]["l"])
+        dref = np.array([oracle.dist_arm(rr, t, o6)[0] for t in th])
+        assert np.abs(dist[:, j] - dref).max() < 1e-12
+    with pytest.raises(M.CfsError):
+        ctx.set_obstacles(obs + obs)  # > CFS_MAX_OBS
