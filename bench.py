@@ -30,6 +30,9 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# One hardware queue per stream: with the default of 8 connections, the copies of one context queue behind the persistent
+# kernels of another (false dependencies) and the e2e pipeline loses 40 % (measured: 2.75 -> 1.98 ms per step).
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 F_WAYPOINT_NUMJAC = 9680.0   # algorithmic FLOPs of one num_jac gradient (11 dist_arm evaluations), SURVEY.md section 8d
 F_WAYPOINT_DERIVEST = 162080.0
@@ -228,6 +231,16 @@ def main():
                                 eps_o, K, o["u"].data_ptr(), o["x"].data_ptr(), o["cost"].data_ptr(), o["eu"].data_ptr(),
                                 o["iters"].data_ptr(), o["status"].data_ptr(), grad=grad_mode, device=not host, sync=False)
 
+    h_sg = [dict(t0=torch.from_numpy(np.ascontiguousarray(cfgs[c]["theta0"])).pin_memory(),
+                 tg=torch.from_numpy(np.ascontiguousarray(cfgs[c]["thetag"])).pin_memory()) for c in range(NC)]
+
+    def issue_sg(c):
+        """start/goal pairs in (80 B per problem), problem set-up on the device, u + cost history + iters + status out"""
+        o = h_out[c]
+        ctxs[c].solve_start_goal_ptr(B, h_sg[c]["t0"].data_ptr(), h_sg[c]["tg"].data_ptr(), eps_o, K, o["u"].data_ptr(), 0,
+                                     o["cost"].data_ptr(), 0, o["iters"].data_ptr(), o["status"].data_ptr(), grad=grad_mode,
+                                     sync=False)
+
     def best_of(c):
         """per-step exchange of the multi-GPU job: all-gather (cost, status), argmin over ranks (s_Parallel_rrt.m:27)"""
         with torch.cuda.stream(streams[c]):
@@ -245,7 +258,10 @@ def main():
             c = k % NC
             if host and k >= NC:
                 ctxs[c].wait()  # the host buffers of this context are about to be reused
-            issue(c, host)
+            if host == "sg":
+                issue_sg(c)
+            else:
+                issue(c, host)
             if world > 1 and not host:
                 best_of(c)
         for c, st in enumerate(streams):
@@ -282,10 +298,19 @@ def main():
     ms_e2e = run_steps(args.steps, True)
     barrier()
     clocks = sampler.stop()
-    tot = torch.tensor([ms_dev, ms_e2e], dtype=torch.float64, device=dev)
+    # ---- e2e from start/goal pairs: the mains' problem set-up (main_FANUC.m:38-103) done on the device ---------------------
+    from motionplanning_5d_m_b200 import problem
+    for ctx in ctxs:
+        ctx.set_cost_blocks(H, problem.Q_MAIN_FANUC, problem.R_MAIN_FANUC, 50.0, s["lim"], s["MAX_input"])
+    run_steps(NC, "sg")
+    barrier()
+    ms_sg = run_steps(args.steps, "sg")
+    barrier()
+    sg_status_equal = bool((h_out[0]["status"].numpy() == d_out[0]["status"].cpu().numpy()).all())
+    tot = torch.tensor([ms_dev, ms_e2e, ms_sg], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tot, op=dist.ReduceOp.MAX)
-    ms_dev, ms_e2e = float(tot[0]), float(tot[1])
+    ms_dev, ms_e2e, ms_sg = float(tot[0]), float(tot[1]), float(tot[2])
 
     # ---- one batch alone, per-tier CUDA events inside the library (timing level 2) ---------------------------------------
     ctx0 = ctxs[0]
@@ -339,7 +364,14 @@ def main():
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps,
                     "api": "cfs_solve_batch_async + cfs_wait (host pointers, pinned): H2D + solve + D2H of every step "
                            "inside the timed events, %d contexts in rotation" % NC},
-            "gpu_launches": int(st["launches"]) * args.steps * 2,
+            "e2e_start_goal": {"value": world * B * args.steps / (ms_sg * 1e-3), "unit": "trajectories/s",
+                               "h2d_bytes_per_step": int(2 * B * nj * 8),
+                               "d2h_bytes_per_step": int(B * (n + K) * 8 + 2 * B * 4), "ms_per_step": ms_sg / args.steps,
+                               "status_equal_to_array_path": sg_status_equal,
+                               "api": "cfs_set_cost_blocks + cfs_solve_start_goal_async: start/goal pairs in, the mains' set-up "
+                                      "(straight-line reference, ff, caug: main_FANUC.m:38-103) built on the device, "
+                                      "u + cost history + iters + status out"},
+            "gpu_launches": int(st["launches"]) * args.steps * 2 + (int(st["launches"]) + 1) * args.steps,
             "clocks": clocks,
             "latency_ms_single_batch": st["ms_total"],
             "ms_per_cfs_iter": st["ms_total"] / max(int(iters.max()), 1),

@@ -79,6 +79,12 @@ int cfs_set_obstacles(cfs_ctx *ctx, const double *seg /*3x2xn_obs*/, const doubl
 int cfs_set_cost(cfs_ctx *ctx, int H, const double *QQ /*n x n, n=H*n_joints*/, const double *lim /*n_joints*/,
                  const double *max_input /*n*/);
 
+/* Same as cfs_set_cost with QQ built ON THE DEVICE from the blocks the mains assemble it from (main_FANUC.m:64-97,
+ * RRTstar_CFS.m:124-160, main_2L.m:69-92): QQ = Baug'*Qaug*Baug + r_scale*(R+R'), Qaug = blkdiag(stage_w*Q ... term_w*Q),
+ * R = blkdiag(Rblk).  Enables cfs_solve_start_goal.   */
+int cfs_set_cost_blocks(cfs_ctx *ctx, int H, const double *Q /*2nj x 2nj*/, const double *Rblk /*nj x nj*/, double r_scale,
+                        double stage_w, double term_w, const double *lim /*nj or NULL*/, const double *max_input /*n or NULL*/);
+
 /* ---- the hot path ------------------------------------------------------------------------------------- */
 /* CFS_FANUC.optimizer (Lib/CFS_FANUC.m:62-79) / PSGCFS_FANUC.optimizer (Lib/PSGCFS_FANUC.m:65-82) for B problems.
  *   x0 = sys_info.xR(:,1), ff = sys_info.ff, caug = sys_info.caug, xref = sys_info.x_, noise = the normrnd draws of
@@ -97,6 +103,15 @@ int cfs_solve_batch(cfs_ctx *ctx, int B, int solver, int grad, const double *x0 
 int cfs_solve_batch_async(cfs_ctx *ctx, int B, int solver, int grad, const double *x0, const double *ff, const double *caug,
                           const double *xref, const double *noise, double eps_outer, int max_outer, double alpha, double *u,
                           double *x, double *cost_hist, double *e_u_hist, int *iters, int *status);
+/* The mains' problem set-up + optimizer() for B start/goal pairs (main_FANUC.m:38-49: x0 = [theta0; 0], x_ = straight line
+ * in joint space, zero velocity rows; :98-103: gaug = [thetag; 0] tiled, ff, caug), built on the device: 80 B in per problem
+ * instead of 6 KB.  Needs cfs_set_cost_blocks.  x and e_u_hist may be NULL (then not copied back). */
+int cfs_solve_start_goal(cfs_ctx *ctx, int B, int solver, int grad, const double *theta0 /*nj x B*/, const double *thetag /*nj x B*/,
+                         const double *noise, double eps_outer, int max_outer, double alpha, double *u, double *x,
+                         double *cost_hist, double *e_u_hist, int *iters, int *status);
+int cfs_solve_start_goal_async(cfs_ctx *ctx, int B, int solver, int grad, const double *theta0, const double *thetag,
+                               const double *noise, double eps_outer, int max_outer, double alpha, double *u, double *x,
+                               double *cost_hist, double *e_u_hist, int *iters, int *status);
 /* Blocks until the context's stream is idle and collects the statistics of the batch in flight (if any). */
 int cfs_wait(cfs_ctx *ctx);
 /* Same, every pointer is a DEVICE pointer on ctx's device (inputs already resident in HBM); asynchronous on the

@@ -19,7 +19,7 @@ FLAG_TOUCH = 0x100
 
 # every symbol include/cfs_b200.h declares (tests check that the library exports all of them)
 SYMBOLS = ["cfs_create", "cfs_destroy", "cfs_last_error", "cfs_version", "cfs_set_stream", "cfs_set_option", "cfs_set_robot", "cfs_set_obstacles",
-           "cfs_set_cost", "cfs_solve_batch", "cfs_solve_batch_async", "cfs_wait", "cfs_solve_batch_device", "cfs_dist_grad", "cfs_time_dist_grad", "cfs_get_con",
+           "cfs_set_cost", "cfs_set_cost_blocks", "cfs_solve_start_goal", "cfs_solve_start_goal_async", "cfs_solve_batch", "cfs_solve_batch_async", "cfs_wait", "cfs_solve_batch_device", "cfs_dist_grad", "cfs_time_dist_grad", "cfs_get_con",
            "cfs_nodes_feasible", "cfs_nearest_steer", "cfs_get_stats", "cfs_set_timing", "cfs_get_iter_times", "cfs_get_problem_steps", "cfs_get_qp_profile", "cfs_measure_fp64_peak"]
 
 
@@ -128,6 +128,42 @@ class Context:
         self._check(rc, "cfs_set_cost")
         self.H, self.n = H, H * self.nj
         self.has_lim = lim is not None
+
+    def set_cost_blocks(self, H, Q, Rblk, r_scale, lim, max_input, stage_w=0.1, term_w=10000.0):
+        """QQ = Baug'QaugBaug + r_scale (R+R') built on the device from its blocks (main_FANUC.m:64-97)."""
+        Q = np.asfortranarray(Q, dtype=np.float64)
+        Rb = np.asfortranarray(Rblk, dtype=np.float64)
+        lim_ = None if lim is None else _f64(np.asarray(lim).reshape(-1))
+        mi = None if max_input is None else _f64(np.asarray(max_input).reshape(-1))
+        rc = self._lib.cfs_set_cost_blocks(self._h, C.c_int(H), _dp(Q), _dp(Rb), C.c_double(r_scale), C.c_double(stage_w),
+                                           C.c_double(term_w), _dp(lim_), _dp(mi))
+        self._check(rc, "cfs_set_cost_blocks")
+        self.H, self.n = H, H * self.nj
+        self.has_lim = lim is not None
+
+    def solve_start_goal(self, theta0, thetag, eps_outer, max_outer, solver=SOLVER_CFS, grad=GRAD_NUMJAC, noise=None,
+                         alpha=0.0, want_x=True):
+        """theta0, thetag (B,nj): the mains' problem set-up (straight-line reference, ff, caug) is built on the device."""
+        t0, tg = _f64(theta0), _f64(thetag)
+        B = t0.shape[0]
+        n, N, K = self.n, 2 * self.n, max(int(max_outer), 1)
+        out = dict(u=np.zeros((B, n)), x=np.zeros((B, N)) if want_x else None, cost_hist=np.full((B, K), np.nan),
+                   e_u_hist=np.full((B, K), np.nan), iters=np.zeros(B, dtype=np.int32), status=np.zeros(B, dtype=np.int32))
+        nz = None if noise is None else _f64(noise)
+        rc = self._lib.cfs_solve_start_goal(self._h, C.c_int(B), C.c_int(solver), C.c_int(grad), _dp(t0), _dp(tg), _dp(nz),
+                                            C.c_double(eps_outer), C.c_int(max_outer), C.c_double(alpha), _dp(out["u"]),
+                                            _dp(out["x"]), _dp(out["cost_hist"]), _dp(out["e_u_hist"]), _dp(out["iters"]),
+                                            _dp(out["status"]))
+        self._check(rc, "cfs_solve_start_goal")
+        return out
+
+    def solve_start_goal_ptr(self, B, theta0, thetag, eps_outer, max_outer, u, x, cost_hist, e_u_hist, iters, status,
+                             solver=SOLVER_CFS, grad=GRAD_NUMJAC, sync=True):
+        vp = lambda p: C.c_void_p(p) if p else None
+        fn = self._lib.cfs_solve_start_goal if sync else self._lib.cfs_solve_start_goal_async
+        rc = fn(self._h, C.c_int(B), C.c_int(solver), C.c_int(grad), vp(theta0), vp(thetag), None, C.c_double(eps_outer),
+                C.c_int(max_outer), C.c_double(0.0), vp(u), vp(x), vp(cost_hist), vp(e_u_hist), vp(iters), vp(status))
+        self._check(rc, "cfs_solve_start_goal")
 
     # ---- hot path ---------------------------------------------------------------------------------------------------
     def solve_batch(self, x0, ff, caug, xref, eps_outer, max_outer, solver=SOLVER_CFS, grad=GRAD_NUMJAC, noise=None,

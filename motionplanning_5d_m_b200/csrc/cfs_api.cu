@@ -12,6 +12,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -31,6 +32,8 @@ struct cfs_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;      // stream in use
   cudaStream_t own_stream = nullptr;  // created by cfs_create
+  cudaStream_t heavy_stream = nullptr;  // highest priority: the heavy tier must not queue behind other contexts' bulk tiers
+  cudaEvent_t ev_bulk = nullptr, ev_heavy = nullptr;
   std::string err;
   // tables
   DevTables htab;
@@ -47,6 +50,11 @@ struct cfs_ctx {
   double *dlim = nullptr, *dumax = nullptr, *dworkL = nullptr, *dworkY = nullptr;
   int *dinfo = nullptr;
   bool have_GI = false;
+  // cost blocks for the device-side problem builder (cfs_set_cost_blocks)
+  bool have_blocks = false;
+  double *dQblk = nullptr;
+  double stage_w = 0.0, term_w = 0.0;
+  DevBuf th0, thg;
   // batch buffers
   DevBuf x0, ff, caug, xref, noise, u, x, cost, eu, u0, v0, cost0, dist, grad, lid, iters, status, flags, listA, listB,
       counters, slab, scratch_theta, scratch_out, qpsteps, fupper, probsteps, psg_w, psg_cost, psg_skip;
@@ -110,6 +118,10 @@ extern "C" const char *cfs_last_error(const cfs_ctx *ctx) { return ctx ? ctx->er
 extern "C" int cfs_create(cfs_ctx **out, int device_id) {
   if (!out) return fail(nullptr, CFS_E_ARG, "cfs_create: out is NULL");
   *out = nullptr;
+  // Several contexts pipeline copy | solve | copy on their own streams; with the default of 8 hardware queues the copies of
+  // one context queue behind the persistent kernels of another.  Only effective if this is the process's first CUDA call
+  // (a MEX host), never overrides the user's setting.
+  setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev == 0)
@@ -182,6 +194,13 @@ extern "C" int cfs_create(cfs_ctx **out, int device_id) {
   }
   cudaMemcpy(ctx->ddv, &dv, sizeof(dv), cudaMemcpyHostToDevice);
   ctx->own_stream = ctx->stream;
+  {
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);  // hi is the numerically lowest = highest priority
+    if (cudaStreamCreateWithPriority(&ctx->heavy_stream, cudaStreamNonBlocking, hi) != cudaSuccess) ctx->heavy_stream = nullptr;
+    cudaEventCreateWithFlags(&ctx->ev_bulk, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ctx->ev_heavy, cudaEventDisableTiming);
+  }
   *out = ctx;
   return 0;
 }
@@ -208,8 +227,9 @@ extern "C" void cfs_destroy(cfs_ctx *ctx) {
                     &ctx->u0, &ctx->v0, &ctx->cost0, &ctx->dist, &ctx->grad, &ctx->lid, &ctx->iters, &ctx->status,
                     &ctx->flags, &ctx->listA, &ctx->listB, &ctx->counters, &ctx->slab, &ctx->scratch_theta,
                     &ctx->scratch_out, &ctx->qpsteps, &ctx->fupper, &ctx->probsteps, &ctx->psg_w, &ctx->psg_cost,
-                    &ctx->psg_skip};
+                    &ctx->psg_skip, &ctx->th0, &ctx->thg};
   for (DevBuf *b : bufs) free_buf(*b);
+  if (ctx->dQblk) cudaFree(ctx->dQblk);
   double *ds[] = {ctx->dQQraw, ctx->dQQ, ctx->dG, ctx->dgn, ctx->dGI, ctx->dgnI, ctx->dlim, ctx->dumax, ctx->dworkL, ctx->dworkY};
   for (double *d : ds)
     if (d) cudaFree(d);
@@ -222,6 +242,9 @@ extern "C" void cfs_destroy(cfs_ctx *ctx) {
   for (cudaEvent_t e : ctx->ev_h)
     if (e) cudaEventDestroy(e);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+  if (ctx->heavy_stream) cudaStreamDestroy(ctx->heavy_stream);
+  if (ctx->ev_bulk) cudaEventDestroy(ctx->ev_bulk);
+  if (ctx->ev_heavy) cudaEventDestroy(ctx->ev_heavy);
   delete ctx;
 }
 
@@ -311,6 +334,7 @@ extern "C" int cfs_set_cost(cfs_ctx *ctx, int H, const double *QQ, const double 
   ctx->dQQraw = ctx->dQQ = ctx->dG = ctx->dgn = ctx->dGI = ctx->dgnI = ctx->dlim = ctx->dumax = ctx->dworkL = ctx->dworkY = nullptr;
   ctx->have_cost = false;
   ctx->have_GI = false;
+  ctx->have_blocks = false;
   CU(cudaMalloc(&ctx->dQQ, sizeof(double) * n * n));
   CU(cudaMalloc(&ctx->dQQraw, sizeof(double) * n * n));
   CU(cudaMemcpyAsync(ctx->dQQraw, QQ, sizeof(double) * n * n, cudaMemcpyHostToDevice, ctx->stream));
@@ -351,6 +375,32 @@ extern "C" int cfs_set_cost(cfs_ctx *ctx, int H, const double *QQ, const double 
   ctx->H = H;
   ctx->n = n;
   ctx->have_cost = true;
+  return 0;
+}
+
+extern "C" int cfs_set_cost_blocks(cfs_ctx *ctx, int H, const double *Q, const double *Rblk, double r_scale,
+                                   double stage_w, double term_w, const double *lim, const double *max_input) {
+  if (!ctx) return CFS_E_ARG;
+  if (!ctx->have_robot) return fail(ctx, CFS_E_STATE, "cfs_set_cost_blocks: call cfs_set_robot first");
+  if (H < 1 || !Q || !Rblk) return fail(ctx, CFS_E_ARG, "cfs_set_cost_blocks: bad argument");
+  CU(cudaSetDevice(ctx->device));
+  const int nj = ctx->nj, n = H * nj, ns = 2 * nj;
+  if (!ctx->dQblk) CU(cudaMalloc(&ctx->dQblk, sizeof(double) * (4 * CFS_MAXL * CFS_MAXL + CFS_MAXL * CFS_MAXL)));
+  double *dR = ctx->dQblk + 4 * CFS_MAXL * CFS_MAXL, *dQQ = nullptr;
+  CU(cudaMemcpyAsync(ctx->dQblk, Q, sizeof(double) * ns * ns, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(dR, Rblk, sizeof(double) * nj * nj, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMalloc(&dQQ, sizeof(double) * (size_t)n * n));
+  cudaError_t e = launch_build_qq(H, nj, ctx->htab.dt, ctx->dQblk, dR, r_scale, stage_w, term_w, dQQ, ctx->stream);
+  std::vector<double> qq((size_t)n * n);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(qq.data(), dQQ, sizeof(double) * (size_t)n * n, cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  cudaFree(dQQ);
+  if (e != cudaSuccess) return fail(ctx, CFS_E_CUDA, "cfs_set_cost_blocks: %s", cudaGetErrorString(e));
+  int rc = cfs_set_cost(ctx, H, qq.data(), lim, max_input);  // symmetrise, factor, Gram operator
+  if (rc) return rc;
+  ctx->stage_w = stage_w;
+  ctx->term_w = term_w;
+  ctx->have_blocks = true;
   return 0;
 }
 
@@ -479,7 +529,18 @@ static int solve_device(cfs_ctx *ctx, int B, int solver, int grad, const double 
     if (detail) CU(cudaEventRecord(ctx->ev[0], st));
     CU(launch_fused(a, grid, 0, st)); ++launches;        // bulk tier: every problem
     if (detail) CU(cudaEventRecord(ctx->ev[1], st));
-    CU(launch_fused(a, grid_heavy, 1, st)); ++launches;  // heavy tier: the (device-side) escalation list, usually < 1 %
+    // heavy tier: the (device-side) escalation list, usually < 1 % of the problems.  It runs on a highest-priority stream
+    // so that, with several contexts in flight, its few CTAs (one per SM) are placed before another context's bulk tier
+    // refills the SMs.
+    if (ctx->heavy_stream && !detail) {
+      CU(cudaEventRecord(ctx->ev_bulk, st));
+      CU(cudaStreamWaitEvent(ctx->heavy_stream, ctx->ev_bulk, 0));
+      CU(launch_fused(a, grid_heavy, 1, ctx->heavy_stream)); ++launches;
+      CU(cudaEventRecord(ctx->ev_heavy, ctx->heavy_stream));
+      CU(cudaStreamWaitEvent(st, ctx->ev_heavy, 0));
+    } else {
+      CU(launch_fused(a, grid_heavy, 1, st)); ++launches;
+    }
     if (detail) CU(cudaEventRecord(ctx->ev[2], st));
     ctx->fused_last = true;
     CU(cudaEventRecord(ctx->ev_b, st));
@@ -641,13 +702,13 @@ extern "C" int cfs_wait(cfs_ctx *ctx) {
   return finish_pending(ctx);
 }
 
-extern "C" int cfs_solve_batch_async(cfs_ctx *ctx, int B, int solver, int grad, const double *x0, const double *ff,
-                                     const double *caug, const double *xref, const double *noise, double eps_outer,
-                                     int max_outer, double alpha, double *u, double *x, double *cost_hist,
-                                     double *e_u_hist, int *iters, int *status) {
-  int rc = check_solve_args(ctx, B, solver, grad, x0, ff, caug, xref, max_outer, u, x, cost_hist, iters, status);
-  if (rc) return rc;
-  if (B == 0) return 0;
+// host-pointer solve, asynchronous.  Either the reference's per-problem arrays (x0, ff, caug, xref) or, with theta0/thetag,
+// start/goal pairs from which the device builds them (main_FANUC.m:38-49,98-103).  x and e_u_hist may be NULL (not copied back).
+static int solve_host_async(cfs_ctx *ctx, int B, int solver, int grad, const double *x0, const double *ff, const double *caug,
+                            const double *xref, const double *theta0, const double *thetag, const double *noise,
+                            double eps_outer, int max_outer, double alpha, double *u, double *x, double *cost_hist,
+                            double *e_u_hist, int *iters, int *status) {
+  int rc;
   CU(cudaSetDevice(ctx->device));
   if (ctx->pending.active && (rc = finish_pending(ctx))) return rc;  // one batch in flight per context
   const int nj = ctx->nj, n = ctx->n, K = max_outer > 0 ? max_outer : 1;
@@ -666,12 +727,23 @@ extern "C" int cfs_solve_batch_async(cfs_ctx *ctx, int B, int solver, int grad, 
   for (cudaEvent_t &e : ctx->ev_h)
     if (!e) CU(cudaEventCreate(&e));
   CU(cudaEventRecord(ctx->ev_h[0], st));
-  CU(cudaMemcpyAsync(ctx->x0.p, x0, sizeof(double) * 2 * nj * B, cudaMemcpyHostToDevice, st));
-  CU(cudaMemcpyAsync(ctx->ff.p, ff, sizeof(double) * (size_t)n * B, cudaMemcpyHostToDevice, st));
-  CU(cudaMemcpyAsync(ctx->caug.p, caug, sizeof(double) * B, cudaMemcpyHostToDevice, st));
-  CU(cudaMemcpyAsync(ctx->xref.p, xref, sizeof(double) * (size_t)2 * n * B, cudaMemcpyHostToDevice, st));
+  if (theta0) {
+    if ((rc = ensure(ctx, ctx->th0, sizeof(double) * nj * B))) return rc;
+    if ((rc = ensure(ctx, ctx->thg, sizeof(double) * nj * B))) return rc;
+    CU(cudaMemcpyAsync(ctx->th0.p, theta0, sizeof(double) * nj * B, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(ctx->thg.p, thetag, sizeof(double) * nj * B, cudaMemcpyHostToDevice, st));
+  } else {
+    CU(cudaMemcpyAsync(ctx->x0.p, x0, sizeof(double) * 2 * nj * B, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(ctx->ff.p, ff, sizeof(double) * (size_t)n * B, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(ctx->caug.p, caug, sizeof(double) * B, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(ctx->xref.p, xref, sizeof(double) * (size_t)2 * n * B, cudaMemcpyHostToDevice, st));
+  }
   if (noise) CU(cudaMemcpyAsync(ctx->noise.p, noise, sizeof(double) * (size_t)n * K * B, cudaMemcpyHostToDevice, st));
   CU(cudaEventRecord(ctx->ev_h[1], st));
+  if (theta0)
+    CU(launch_build_problems(B, ctx->H, nj, ctx->htab.dt, ctx->dQblk, ctx->stage_w, ctx->term_w, ptr<double>(ctx->th0),
+                             ptr<double>(ctx->thg), ptr<double>(ctx->x0), ptr<double>(ctx->xref), ptr<double>(ctx->ff),
+                             ptr<double>(ctx->caug), st));
   rc = solve_device(ctx, B, solver, grad, ptr<double>(ctx->x0), ptr<double>(ctx->ff), ptr<double>(ctx->caug),
                     ptr<double>(ctx->xref), noise ? ptr<double>(ctx->noise) : nullptr, eps_outer, max_outer, alpha,
                     ptr<double>(ctx->u), ptr<double>(ctx->x), ptr<double>(ctx->cost), ptr<double>(ctx->eu),
@@ -679,7 +751,7 @@ extern "C" int cfs_solve_batch_async(cfs_ctx *ctx, int B, int solver, int grad, 
   if (rc) return rc;
   CU(cudaEventRecord(ctx->ev_h[2], st));
   CU(cudaMemcpyAsync(u, ctx->u.p, sizeof(double) * (size_t)n * B, cudaMemcpyDeviceToHost, st));
-  CU(cudaMemcpyAsync(x, ctx->x.p, sizeof(double) * (size_t)2 * n * B, cudaMemcpyDeviceToHost, st));
+  if (x) CU(cudaMemcpyAsync(x, ctx->x.p, sizeof(double) * (size_t)2 * n * B, cudaMemcpyDeviceToHost, st));
   CU(cudaMemcpyAsync(cost_hist, ctx->cost.p, sizeof(double) * (size_t)max_outer * B, cudaMemcpyDeviceToHost, st));
   if (e_u_hist) CU(cudaMemcpyAsync(e_u_hist, ctx->eu.p, sizeof(double) * (size_t)max_outer * B, cudaMemcpyDeviceToHost, st));
   CU(cudaMemcpyAsync(iters, ctx->iters.p, sizeof(int) * B, cudaMemcpyDeviceToHost, st));
@@ -692,6 +764,43 @@ extern "C" int cfs_solve_batch_async(cfs_ctx *ctx, int B, int solver, int grad, 
   ctx->pending.d_iters = ptr<int>(ctx->iters);
   ctx->pending.d_status = ptr<int>(ctx->status);
   return 0;
+}
+
+extern "C" int cfs_solve_batch_async(cfs_ctx *ctx, int B, int solver, int grad, const double *x0, const double *ff,
+                                     const double *caug, const double *xref, const double *noise, double eps_outer,
+                                     int max_outer, double alpha, double *u, double *x, double *cost_hist,
+                                     double *e_u_hist, int *iters, int *status) {
+  int rc = check_solve_args(ctx, B, solver, grad, x0, ff, caug, xref, max_outer, u, x, cost_hist, iters, status);
+  if (rc) return rc;
+  if (B == 0) return 0;
+  return solve_host_async(ctx, B, solver, grad, x0, ff, caug, xref, nullptr, nullptr, noise, eps_outer, max_outer, alpha, u, x,
+                          cost_hist, e_u_hist, iters, status);
+}
+
+extern "C" int cfs_solve_start_goal_async(cfs_ctx *ctx, int B, int solver, int grad, const double *theta0, const double *thetag,
+                                          const double *noise, double eps_outer, int max_outer, double alpha, double *u,
+                                          double *x, double *cost_hist, double *e_u_hist, int *iters, int *status) {
+  if (!ctx) return CFS_E_ARG;
+  int rc = check_ready(ctx, true);
+  if (rc) return rc;
+  if (!ctx->have_blocks) return fail(ctx, CFS_E_STATE, "cfs_solve_start_goal: the cost must be set with cfs_set_cost_blocks");
+  if (B < 0 || max_outer < 0 || (solver != CFS_SOLVER_CFS && solver != CFS_SOLVER_PSGCFS) ||
+      (grad != CFS_GRAD_NUMJAC && grad != CFS_GRAD_DERIVEST))
+    return fail(ctx, CFS_E_ARG, "cfs_solve_start_goal: bad argument");
+  if (B > 0 && (!theta0 || !thetag || !u || !cost_hist || !iters || !status))
+    return fail(ctx, CFS_E_ARG, "cfs_solve_start_goal: NULL buffer");
+  if (B == 0) return 0;
+  return solve_host_async(ctx, B, solver, grad, nullptr, nullptr, nullptr, nullptr, theta0, thetag, noise, eps_outer, max_outer,
+                          alpha, u, x, cost_hist, e_u_hist, iters, status);
+}
+
+extern "C" int cfs_solve_start_goal(cfs_ctx *ctx, int B, int solver, int grad, const double *theta0, const double *thetag,
+                                    const double *noise, double eps_outer, int max_outer, double alpha, double *u, double *x,
+                                    double *cost_hist, double *e_u_hist, int *iters, int *status) {
+  int rc = cfs_solve_start_goal_async(ctx, B, solver, grad, theta0, thetag, noise, eps_outer, max_outer, alpha, u, x, cost_hist,
+                                      e_u_hist, iters, status);
+  if (rc || B == 0) return rc;
+  return cfs_wait(ctx);
 }
 
 extern "C" int cfs_solve_batch(cfs_ctx *ctx, int B, int solver, int grad, const double *x0, const double *ff,

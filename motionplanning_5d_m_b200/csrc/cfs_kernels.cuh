@@ -41,6 +41,17 @@ cudaError_t setup_gram(int n, int H, int nj, double dt, const double *QQ /*devic
                        double *work_Y /*n*3n*/, double *G /*3n x 3n*/, double *gdiag /*3n*/, int *info /*device*/,
                        cudaStream_t s);
 
+// ---- problem set-up on the device ------------------------------------------------------------
+// QQ = Baug'*Qaug*Baug + r_scale*(R+R') of main_FANUC.m:64-97 from its blocks: Q (2nj x 2nj stage cost, weight stage_w on
+// steps 1..H-1 and term_w on step H), Rblk (nj x nj).  Baug's blocks are closed form ((0.5+(i-j))dt^2 I ; dt I).
+cudaError_t launch_build_qq(int H, int nj, double dt, const double *Q, const double *Rblk, double r_scale, double stage_w,
+                            double term_w, double *QQ /*n x n*/, cudaStream_t s);
+// per problem, from a start/goal pair (main_FANUC.m:38-49, 98-103): x0 = [theta0; 0], x_ = straight line in joint space
+// with zero velocity rows (step 0 dropped), gaug = [thetag; 0] tiled, ff = ((Aaug x0 - gaug)' Qaug Baug)', caug = e' Qaug e
+cudaError_t launch_build_problems(int B, int H, int nj, double dt, const double *Q, double stage_w, double term_w,
+                                  const double *theta0 /*nj x B*/, const double *thetag /*nj x B*/, double *x0 /*2nj x B*/,
+                                  double *xref /*2njH x B*/, double *ff /*n x B*/, double *caug /*B*/, cudaStream_t s);
+
 // C = alpha * op(A) * B  (column-major, A is M x K with lda (or K x M if transA), B is K x N, C is M x N)
 cudaError_t launch_dgemm(int M, int N, int K, double alpha, const double *A, int lda, bool transA, const double *B,
                          int ldb, double *C, int ldc, cudaStream_t s);

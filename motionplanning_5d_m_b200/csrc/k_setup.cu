@@ -135,6 +135,85 @@ __global__ void k_copy(size_t cnt, const double *src, double *dst) {
     dst[i] = src[i];
 }
 
+// ---- N2: cost matrix and per-problem linear terms on the device ----------------------------------------------------------
+// One thread per entry of QQ.  Column/row index (j,k): control of joint k at step j.  With b(i,j) = (0.5+(i-j))dt^2:
+//   QQ[(j1,k1),(j2,k2)] = sum_{i >= max(j1,j2)} w_i * ( b1 b2 Qtt + b1 dt Qtw + dt b2 Qwt + dt^2 Qww )[k1,k2]  + r_scale (Rblk+Rblk')[k1,k2] [j1==j2]
+__global__ void k_build_qq(int H, int nj, double dt, const double *Q, const double *Rblk, double r_scale, double stage_w,
+                           double term_w, double *QQ) {
+  const int n = H * nj, ns = 2 * nj;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n * n) return;
+  const int r = e % n, c = e / n;
+  const int j1 = r / nj, k1 = r % nj, j2 = c / nj, k2 = c % nj;
+  const double qtt = Q[k1 + ns * k2], qtw = Q[k1 + ns * (nj + k2)], qwt = Q[(nj + k1) + ns * k2], qww = Q[(nj + k1) + ns * (nj + k2)];
+  double acc = 0.0;
+  for (int i = (j1 > j2 ? j1 : j2); i < H; ++i) {
+    const double w = (i == H - 1) ? term_w : stage_w;
+    const double b1 = 0.5 * dt * dt + ((i - j1) * dt) * dt, b2 = 0.5 * dt * dt + ((i - j2) * dt) * dt;
+    acc += w * (((b1 * b2) * qtt + (b1 * dt) * qtw) + ((dt * b2) * qwt + (dt * dt) * qww));
+  }
+  if (j1 == j2) acc += r_scale * (Rblk[k1 + nj * k2] + Rblk[k2 + nj * k1]);
+  QQ[r + (size_t)n * c] = acc;
+}
+
+cudaError_t launch_build_qq(int H, int nj, double dt, const double *Q, const double *Rblk, double r_scale, double stage_w,
+                            double term_w, double *QQ, cudaStream_t s) {
+  const int n = H * nj;
+  k_build_qq<<<(n * n + 255) / 256, 256, 0, s>>>(H, nj, dt, Q, Rblk, r_scale, stage_w, term_w, QQ);
+  return cudaGetLastError();
+}
+
+// one CTA per problem; q_i = w_i Q e_i with e_i = [theta0 - thetag ; 0] (x0 has zero velocity, so Aaug x0 = x0 at every step)
+__global__ void __launch_bounds__(128) k_build_problems(int B, int H, int nj, double dt, const double *Q, double stage_w,
+                                                        double term_w, const double *theta0, const double *thetag, double *x0,
+                                                        double *xref, double *ff, double *caug) {
+  __shared__ double e[CFS_MAXL], qe_t[CFS_MAXL], qe_w[CFS_MAXL];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const int n = H * nj, ns = 2 * nj;
+  if (tid < nj) e[tid] = theta0[(size_t)b * nj + tid] - thetag[(size_t)b * nj + tid];
+  __syncthreads();
+  if (tid < ns) {  // (Q e)(tid) with e = [e_theta; 0]
+    double acc = 0.0;
+    for (int k = 0; k < nj; ++k) acc += Q[tid + ns * k] * e[k];
+    if (tid < nj) qe_t[tid] = acc; else qe_w[tid - nj] = acc;
+  }
+  __syncthreads();
+  if (tid < ns) x0[(size_t)b * ns + tid] = tid < nj ? theta0[(size_t)b * nj + tid] : 0.0;
+  // x_ : MATLAB linspace(theta0, thetag, H+1) without its first column, zero velocity rows (main_FANUC.m:38-49)
+  for (int idx = tid; idx < H * ns; idx += blockDim.x) {
+    const int i = idx / ns, k = idx % ns;
+    double v = 0.0;
+    if (k < nj) {
+      const double t0 = theta0[(size_t)b * nj + k], tg = thetag[(size_t)b * nj + k];
+      v = (i == H - 1) ? tg : t0 + ((i + 1) * (tg - t0)) / H;
+    }
+    xref[(size_t)b * H * ns + idx] = v;
+  }
+  // ff_(j,k) = sum_{i>=j} w_i ( b(i,j) (Qe)_theta(k) + dt (Qe)_omega(k) )
+  for (int idx = tid; idx < n; idx += blockDim.x) {
+    const int j = idx / nj, k = idx % nj;
+    double acc = 0.0;
+    for (int i = j; i < H; ++i) {
+      const double w = (i == H - 1) ? term_w : stage_w;
+      acc += w * ((0.5 * dt * dt + ((i - j) * dt) * dt) * qe_t[k] + dt * qe_w[k]);
+    }
+    ff[(size_t)b * n + idx] = acc;
+  }
+  if (tid == 0) {  // caug = sum_i w_i e'Qe
+    double eq = 0.0;
+    for (int k = 0; k < nj; ++k) eq += e[k] * qe_t[k];
+    caug[b] = ((H - 1) * stage_w + term_w) * eq;
+  }
+}
+
+cudaError_t launch_build_problems(int B, int H, int nj, double dt, const double *Q, double stage_w, double term_w,
+                                  const double *theta0, const double *thetag, double *x0, double *xref, double *ff,
+                                  double *caug, cudaStream_t s) {
+  if (B <= 0) return cudaSuccess;
+  k_build_problems<<<B, 128, 0, s>>>(B, H, nj, dt, Q, stage_w, term_w, theta0, thetag, x0, xref, ff, caug);
+  return cudaGetLastError();
+}
+
 cudaError_t setup_gram(int n, int H, int nj, double dt, const double *QQ, double *work_L, double *work_Y, double *G,
                        double *gdiag, int *info, cudaStream_t s) {
   (void)H;

@@ -128,3 +128,35 @@ def test_many_obstacles_and_large_horizon(ctx, oracle):
         assert np.abs(dist[:, j] - dref).max() < 1e-12
     with pytest.raises(M.CfsError):
         ctx.set_obstacles(obs + obs)  # > CFS_MAX_OBS
+
+
+def test_device_side_setup_matches_host_builder(ctx, oracle):
+    """cfs_set_cost_blocks + cfs_solve_start_goal (main_FANUC.m:38-103 on the device) against the host-built problem."""
+    from motionplanning_5d_m_b200 import problem
+    cfg = common.batch_m16ib(oracle, 48, horizon=30)
+    s = cfg["sys_info"]
+    r = dict(cfg["robot"])
+    r["name"] = "M16iB"
+    ctx.set_robot(r, 5)
+    ctx.set_obstacles(cfg["obs"])
+    ctx.set_cost(s["H"], s["QQ"], s["lim"], s["MAX_input"])
+    ref = ctx.solve_batch(cfg["x0"], cfg["ff"], cfg["caug"], cfg["xref"], s["epsilon_O"], s["MAX_O_ITER"])
+    ctx.set_cost_blocks(s["H"], problem.Q_MAIN_FANUC, problem.R_MAIN_FANUC, 50.0, s["lim"], s["MAX_input"])
+    out = ctx.solve_start_goal(cfg["theta0"], cfg["thetag"], s["epsilon_O"], s["MAX_O_ITER"])
+    assert (out["status"] == ref["status"]).all() and (out["iters"] == ref["iters"]).all()
+    ok = (ref["status"] & 0xFF) < 2
+    assert np.abs(out["x"][ok] - ref["x"][ok]).max() < 1e-6 and np.abs(out["u"][ok] - ref["u"][ok]).max() < 1e-6
+    for b in np.where(ok)[0]:
+        it = ref["iters"][b]
+        assert np.all(np.abs(out["cost_hist"][b, :it] - ref["cost_hist"][b, :it]) <= 1e-6 * np.abs(ref["cost_hist"][b, :it]))
+    # and against the oracle fed with the host-built arrays
+    P = common.oracle_problem(oracle, "M16iB", cfg["obs"], s)
+    orc = P.solve_batch(cfg["x0"], cfg["ff"], cfg["caug"], cfg["xref"], nthreads=8)
+    assert (out["status"] == orc["status"]).all() and (out["iters"] == orc["iters"]).all()
+    assert np.abs(out["x"][ok] - orc["x"][ok]).max() < 1e-6
+    # x may be skipped
+    nox = ctx.solve_start_goal(cfg["theta0"], cfg["thetag"], s["epsilon_O"], s["MAX_O_ITER"], want_x=False)
+    assert nox["x"] is None and np.array_equal(nox["u"], out["u"])
+    with pytest.raises(M.CfsError, match="cfs_set_cost_blocks"):
+        ctx.set_cost(s["H"], s["QQ"], s["lim"], s["MAX_input"])
+        ctx.solve_start_goal(cfg["theta0"], cfg["thetag"], s["epsilon_O"], s["MAX_O_ITER"])
