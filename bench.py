@@ -298,19 +298,11 @@ def main():
     ms_e2e = run_steps(args.steps, True)
     barrier()
     clocks = sampler.stop()
-    # ---- e2e from start/goal pairs: the mains' problem set-up (main_FANUC.m:38-103) done on the device ---------------------
-    from motionplanning_5d_m_b200 import problem
-    for ctx in ctxs:
-        ctx.set_cost_blocks(H, problem.Q_MAIN_FANUC, problem.R_MAIN_FANUC, 50.0, s["lim"], s["MAX_input"])
-    run_steps(NC, "sg")
-    barrier()
-    ms_sg = run_steps(args.steps, "sg")
-    barrier()
-    sg_status_equal = bool((h_out[0]["status"].numpy() == d_out[0]["status"].cpu().numpy()).all())
-    tot = torch.tensor([ms_dev, ms_e2e, ms_sg], dtype=torch.float64, device=dev)
+    e2e_out = {k: h_out[0][k].numpy().copy() for k in ("x", "status", "iters")}  # results of the array-path e2e leg
+    tot = torch.tensor([ms_dev, ms_e2e], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tot, op=dist.ReduceOp.MAX)
-    ms_dev, ms_e2e, ms_sg = float(tot[0]), float(tot[1]), float(tot[2])
+    ms_dev, ms_e2e = float(tot[0]), float(tot[1])
 
     # ---- one batch alone, per-tier CUDA events inside the library (timing level 2) ---------------------------------------
     ctx0 = ctxs[0]
@@ -336,6 +328,19 @@ def main():
         th_all = th_all[: 64 * H]
     k1_ms = ctx0.time_dist_grad(th_all, grad=grad_mode, reps=10)
     k1_tf = f_wp * th_all.shape[0] / (k1_ms * 1e-3) / 1e12
+    # ---- e2e from start/goal pairs: the mains' problem set-up (main_FANUC.m:38-103) done on the device ---------------------
+    from motionplanning_5d_m_b200 import problem
+    for ctx in ctxs:
+        ctx.set_cost_blocks(H, problem.Q_MAIN_FANUC, problem.R_MAIN_FANUC, 50.0, s["lim"], s["MAX_input"])
+    run_steps(NC, "sg")
+    barrier()
+    ms_sg = run_steps(args.steps, "sg")
+    barrier()
+    sg_status_equal = bool((h_out[0]["status"].numpy() == e2e_out["status"]).all())
+    tot_sg = torch.tensor([ms_sg], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tot_sg, op=dist.ReduceOp.MAX)
+    ms_sg = float(tot_sg[0])
     dom_ms = (st["ms_bulk"] + st["ms_heavy"]) if fused else st["ms_grad"]
     ach_tf = grad_flops / (dom_ms * 1e-3) / 1e12 if dom_ms > 0 else 0.0
     peaks = {}
@@ -414,11 +419,22 @@ def main():
             line["cpu_baseline"] = {"value": S * args.cpu_reps / dt, "unit": "trajectories/s", "cores": cores, "kind": "port",
                                     "sample": "%d passes over %d problems of the same batch, C port of the reference "
                                               "algorithm (oracle/), OpenMP over problems" % (args.cpu_reps, S), "seconds": dt}
-            xg, sg, ig = (h_out[0][k].numpy()[:S] for k in ("x", "status", "iters"))
+            xg, sg, ig = (e2e_out[k][:S] for k in ("x", "status", "iters"))
             ok = ((ref["status"] & 0xFF) < 2) & (ref["status"] == sg)
+            dxp = np.abs(xg - ref["x"]).max(axis=1)
+            dxp[~ok] = 0.0
+            # conditioning probe: the oracle's own answer when ff is perturbed by 1e-12 relative (a problem that does not
+            # converge within MAX_O_ITER can amplify that a million-fold; DESIGN.md "parity noise floor")
+            pert = P.solve_batch(c0["x0"][:S], c0["ff"][:S] * (1.0 + 1e-12), c0["caug"][:S], c0["xref"][:S], nthreads=cores)
+            sens = np.abs(pert["x"] - ref["x"]).max(axis=1)
+            well = ok & (sens < 1e-8)
             line["parity_sample"] = {"problems": S, "status_equal": bool((ref["status"] == sg).all()),
                                      "iters_equal": bool((ref["iters"] == ig).all()),
-                                     "max_abs_dx": float(np.abs(xg[ok] - ref["x"][ok]).max()) if ok.any() else None}
+                                     "max_abs_dx": float(dxp.max()) if ok.any() else None,
+                                     "max_abs_dx_well_conditioned": float(dxp[well].max()) if well.any() else None,
+                                     "ill_conditioned_problems": int((ok & ~well).sum()),
+                                     "ill_conditioned_rule": "oracle's own x moves by > 1e-8 when ff is scaled by (1 + 1e-12)",
+                                     "problems_over_1e-6": int((dxp > 1e-6).sum())}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
