@@ -203,7 +203,7 @@ __global__ void __launch_bounds__(NT, MINB) k_cfs_fused(SolveArgs a) {
 
       // ---- Solve_QP (CFS_FANUC.m:85) ----
       int q = 0, steps = 0;
-      const bool masked = qp_mask_antiparallel<NT>(s, dims);
+      const int masked = qp_mask_antiparallel<NT>(s, dims);
       const int qst = qp_solve<NT, QS, (MINB == 1), NJ>(s, dims, cost0, fupper, false, q, steps, qmax_seen, pf, tck, prof,
                                                         heavy ? 0x7fffffff : a.esc_steps, masked);
       steps_total += steps;

@@ -122,7 +122,7 @@ __global__ void __launch_bounds__(QP_THREADS, 3) k_qp(SolveArgs a) {
       for (int c = tid; c < n; c += QP_THREADS) s.v[2 * n + c] = ub[c];
       __syncthreads();
     }
-    const bool masked = !skip_solve && qp_mask_antiparallel<QP_THREADS>(s, dims);
+    const int masked = skip_solve ? 0 : qp_mask_antiparallel<QP_THREADS>(s, dims);
     const int status = qp_solve<QP_THREADS, QP_QS, true, 0>(s, dims, a.cost0[b], (has_bnd && a.fupper) ? a.fupper[b] : INFINITY, skip_solve, q, steps,
                                 qmax_seen, pf, tck, prof, 0x7fffffff, masked);
     steps_total += steps;

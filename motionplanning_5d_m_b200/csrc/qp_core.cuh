@@ -357,11 +357,14 @@ static __device__ __noinline__ void qp_refresh(const QpView &s, const QpDims &P,
 // infeasible.  The dual method finds that certificate in ~4 steps when it only sees those rows, but wanders for up to
 // hundreds of steps when it always takes the globally most violated row.  So all other obstacle rows are masked
 // (inact = 2) first: "infeasible" for a subset of the rows is infeasible for all of them; otherwise qp_solve unmasks and
-// simply continues (its working set stays a valid dual active-set state).  Returns true if a mask was set.
+// simply continues (its working set stays a valid dual active-set state).
 template <int NT>
-__device__ __forceinline__ bool qp_mask_antiparallel(const QpView &s, const QpDims &P) {
+__device__ __forceinline__ int qp_mask_antiparallel(const QpView &s, const QpDims &P) {
+  // returns the number of masking levels set: 0 none; 2: level A1 = the most anti-parallel pair only, level A2 = every
+  // pair with cos < -0.9 (inact = 2), then all rows (inact = 3)
   const int tid = threadIdx.x, OH = P.OH, H = P.H, nj = P.nj;
-  bool found = false;
+  double best = 0.0;
+  int bidx = -1;
 #pragma unroll 1
   for (int cid = tid; cid < OH; cid += NT) {
     if (wp_of(cid, H) == H - 1) continue;  // the pair (cid, cid+1) must belong to the same obstacle
@@ -373,11 +376,18 @@ __device__ __forceinline__ bool qp_mask_antiparallel(const QpView &s, const QpDi
       aa += a[k] * a[k];
       bb += b[k] * b[k];
     }
-    if (ab < 0.0 && ab * ab > 0.81 * aa * bb) found = true;  // cos < -0.9
+    if (ab < 0.0 && ab * ab > 0.81 * aa * bb) {  // cos < -0.9
+      const double cs = ab / sqrt(aa * bb);
+      if (bidx < 0 || cs < best) {
+        best = cs;
+        bidx = cid;
+      }
+    }
   }
-  if (!__syncthreads_or(found)) return false;
+  block_argmin<NT>(best, bidx, s.red);
+  if (bidx < 0) return 0;
 #pragma unroll 1
-  for (int cid = tid; cid < OH; cid += NT) s.inact[cid] = 2;
+  for (int cid = tid; cid < OH; cid += NT) s.inact[cid] = 3;
   __syncthreads();
 #pragma unroll 1
   for (int cid = tid; cid < OH; cid += NT) {
@@ -391,12 +401,17 @@ __device__ __forceinline__ bool qp_mask_antiparallel(const QpView &s, const QpDi
       bb += b[k] * b[k];
     }
     if (ab < 0.0 && ab * ab > 0.81 * aa * bb) {
-      s.inact[cid] = 0;
-      s.inact[cid + 1] = 0;
+      s.inact[cid] = 2;
+      s.inact[cid + 1] = 2;
     }
   }
   __syncthreads();
-  return true;
+  if (tid == 0) {
+    s.inact[bidx] = 0;
+    s.inact[bidx + 1] = 0;
+  }
+  __syncthreads();
+  return 2;
 }
 
 // Polish: the working-set inverse M has been rank-1 updated many times; one step of iterative refinement on
@@ -452,7 +467,7 @@ static __device__ __noinline__ void qp_polish(const QpView &s, const QpDims &P, 
 template <int NT, int QS, bool SPILL, int NJ>
 __device__ __forceinline__ int qp_solve(const QpView &s, const QpDims &P, double cost0, double fupper, bool skip_solve,
                                         int &q_out, int &steps_out, int &qmax_seen, long long *pf, long long &tck,
-                                        bool prof, int step_cap = 0x7fffffff, bool masked = false) {
+                                        bool prof, int step_cap = 0x7fffffff, int masked = 0) {
   const int tid = threadIdx.x;
   const int n = P.n, nj = NJ ? NJ : P.nj, H = P.H, OH = P.OH, has_vel = P.has_vel, has_bnd = P.has_bnd;
   double *Mgl = P.Mgl;
@@ -523,11 +538,12 @@ __device__ __forceinline__ int qp_solve(const QpView &s, const QpDims &P, double
     }
     block_argmin<NT>(best, bidx, s.red);
     PF_ADD(2);
-    if (bidx < 0 && masked) {  // phase A is feasible: unmask the other obstacle rows and carry on with the same working set
+    if (bidx < 0 && masked) {  // this phase is feasible: unmask the next level and carry on with the same working set
+      const int lvl = masked == 2 ? 2 : 3;
 #pragma unroll 1
       for (int cid = tid; cid < OH; cid += NT)
-        if (s.inact[cid] == 2) s.inact[cid] = 0;
-      masked = false;
+        if (s.inact[cid] == lvl) s.inact[cid] = 0;
+      --masked;
       __syncthreads();
       if (q == 0) {  // v is still v0: scan again without a refresh
         polished = false;
