@@ -49,7 +49,7 @@ def parse_args():
     ap.add_argument("--batch", type=int, default=4096)
     ap.add_argument("--horizon", type=int, default=50)
     ap.add_argument("--grad", default="numjac", choices=["numjac", "derivest"])
-    ap.add_argument("--contexts", type=int, default=8, help="library contexts (streams + buffer sets) the steps rotate over")
+    ap.add_argument("--contexts", type=int, default=16, help="library contexts (streams + buffer sets) the steps rotate over")
     ap.add_argument("--cpu-reps", type=int, default=3, help="CPU baseline: passes of the oracle over the same batch")
     return ap.parse_args()
 
@@ -67,6 +67,8 @@ class ClockSampler:
         self.proc = None
 
     def start(self):
+        if os.environ.get("BENCH_NO_CLOCKS"):
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "50"], stdout=subprocess.PIPE,
@@ -78,7 +80,11 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append([time.perf_counter()] + [c.strip() for c in line.split(",")])
+
+    def mark(self):
+        """start of the timed region: samples taken before it (warm-up) are only used if none fall inside it"""
+        self.t_mark = time.perf_counter()
 
     def stop(self):
         if not self.proc:
@@ -90,7 +96,9 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        inside = [r[1:] for r in self.rows if r[0] >= getattr(self, "t_mark", 0.0)]
+        window = "timed region" if inside else "warm-up + timed region (no sample fell inside the timed region)"
+        for r in (inside or [r[1:] for r in self.rows]):
             try:
                 sm.append(float(r[1]))
                 mx.append(float(r[2]))
@@ -100,7 +108,7 @@ class ClockSampler:
             except Exception:
                 pass
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
 def cpu_count():
@@ -281,18 +289,21 @@ def main():
         torch.cuda.synchronize(dev)
 
     # ---- warm-up -------------------------------------------------------------------------------------------------------
+    sampler = ClockSampler(local_rank)
+    sampler.start()  # nvidia-smi needs up to a second to deliver its first row on an 8-GPU box: started before the warm-up
     W = max(args.warmup, 3)
     run_steps(max(W, NC), False)
     run_steps(max(W, NC), True)
     barrier()
     # ---- timed: device-resident -------------------------------------------------------------------------------------------
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    time.sleep(0.1)
     flush.zero_()
     barrier()
+    sampler.mark()
     ms_dev = run_steps(args.steps, False)
     barrier()
+    # algorithmic work of the timed region: every context solved its own batch; count its gradient waypoints
+    wp_ctx = [ctxs[c].stats()["grad_waypoints"] for c in range(min(NC, args.steps))]
+    wp_timed = sum(wp_ctx[k % NC] for k in range(args.steps))
     # ---- timed: end to end through the host-pointer C ABI -----------------------------------------------------------------
     flush.zero_()
     barrier()
@@ -343,7 +354,13 @@ def main():
         dist.all_reduce(tot_sg, op=dist.ReduceOp.MAX)
     ms_sg = float(tot_sg[0])
     dom_ms = (st["ms_bulk"] + st["ms_heavy"]) if fused else st["ms_grad"]
-    ach_tf = grad_flops / (dom_ms * 1e-3) / 1e12 if dom_ms > 0 else 0.0
+    ach_single_tf = grad_flops / (dom_ms * 1e-3) / 1e12 if dom_ms > 0 else 0.0
+    share = dom_ms / st["ms_total"] if st["ms_total"] else 1.0
+    # K launches overlap on NC streams in the timed region: the duration of one launch there is the timed region / K
+    # (x the kernel's share of a step, measured on one batch alone and checked against the ncu launch list)
+    amort_ms = ms_dev / args.steps * share
+    flops_per_launch = f_wp * wp_timed / args.steps
+    ach_tf = flops_per_launch / (amort_ms * 1e-3) / 1e12
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -389,11 +406,17 @@ def main():
                                            "full, profiles/r01_prof_fused_final_raw.csv",
                          "peak_source": "measured here by cfs_measure_fp64_peak (DFMA micro-benchmark; MEASURED_PEAKS.json "
                                         "has no FP64 entry), implied SM clock %.0f MHz" % fp64_mhz,
-                         "algorithmic_flops_per_launch": grad_flops, "avg_launch_ms": dom_ms,
-                         "note": "algorithmic FLOPs = 9680 per num_jac waypoint gradient x %d waypoint gradients "
+                         "algorithmic_flops_per_launch": flops_per_launch, "avg_launch_ms": amort_ms,
+                         "avg_launch_ms_basis": "timed region / steps x share_of_step: the %d timed launches overlap on %d "
+                                                "streams, so this is the GPU time one launch costs in the timed region" % (args.steps, NC),
+                         "single_launch": {"ms": dom_ms, "achieved": ach_single_tf,
+                                           "frac": ach_single_tf / fp64_tf if fp64_tf else None,
+                                           "note": "one batch alone on an idle GPU (bulk + heavy tier, CUDA events inside "
+                                                   "the library): the tail of long problems is not overlapped"},
+                         "note": "algorithmic FLOPs = %.0f per waypoint gradient x %.0f waypoint gradients per launch "
                                  "(SURVEY.md 8d); the fused kernel also runs the QP, roll-out and stop rule and is bound by "
-                                 "dependent-issue latency and L2 latency, not by the FP64 pipe" % st["grad_waypoints"],
-                         "share_of_step": dom_ms / st["ms_total"] if st["ms_total"] else None},
+                                 "dependent-issue latency and L2 latency, not by the FP64 pipe" % (f_wp, wp_timed / args.steps),
+                         "share_of_step": share},
             "roofline_k1": {"bound": "fp64", "kernel": "k_grad_%s stand-alone" % args.grad, "achieved": k1_tf, "peak": fp64_tf,
                             "unit": "TFLOP/s", "frac": k1_tf / fp64_tf if fp64_tf else None, "waypoints": int(th_all.shape[0]),
                             "avg_launch_ms": k1_ms},

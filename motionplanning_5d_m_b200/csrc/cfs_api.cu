@@ -71,6 +71,9 @@ struct cfs_ctx {
   int timing_level = 1;
   bool use_fused = true;  // cfs_set_option("fused")
   int esc_steps = 48;     // cfs_set_option("esc_steps")
+  int heavy_grid = 0;     // cfs_set_option("heavy_grid"): cap of the heavy tier's grid (0 = one CTA per SM)
+  int bulk_grid = 0;      // cfs_set_option("bulk_grid"): cap of the bulk tier's grid (0 = every resident slot)
+  int heavy_prio = 1;     // cfs_set_option("heavy_prio"): heavy tier on the highest-priority stream
   bool fused_last = false;
   std::vector<double> it_grad_ms, it_qp_ms;
   cfs_stats stats;
@@ -500,6 +503,8 @@ static int solve_device(cfs_ctx *ctx, int B, int solver, int grad, const double 
   if (grid > B) grid = B;
   if (grid < 1) grid = 1;
   if (grid_heavy > B) grid_heavy = B;
+  if (fused && ctx->heavy_grid > 0 && grid_heavy > ctx->heavy_grid) grid_heavy = ctx->heavy_grid;
+  if (fused && ctx->bulk_grid > 0 && grid > ctx->bulk_grid) grid = ctx->bulk_grid;
   if ((rc = ensure(ctx, ctx->slab, sizeof(double) * (size_t)n * n * (grid > grid_heavy ? grid : grid_heavy)))) return rc;
   a.slab = ptr<double>(ctx->slab);
 
@@ -532,7 +537,7 @@ static int solve_device(cfs_ctx *ctx, int B, int solver, int grad, const double 
     // heavy tier: the (device-side) escalation list, usually < 1 % of the problems.  It runs on a highest-priority stream
     // so that, with several contexts in flight, its few CTAs (one per SM) are placed before another context's bulk tier
     // refills the SMs.
-    if (ctx->heavy_stream && !detail) {
+    if (ctx->heavy_stream && ctx->heavy_prio && !detail) {
       CU(cudaEventRecord(ctx->ev_bulk, st));
       CU(cudaStreamWaitEvent(ctx->heavy_stream, ctx->ev_bulk, 0));
       CU(launch_fused(a, grid_heavy, 1, ctx->heavy_stream)); ++launches;
@@ -1016,6 +1021,9 @@ extern "C" int cfs_set_option(cfs_ctx *ctx, const char *name, int value) {
     ctx->esc_steps = value > 0 ? value : 0x7fffffff;
     return 0;
   }
+  if (strcmp(name, "heavy_grid") == 0) { ctx->heavy_grid = value; return 0; }
+  if (strcmp(name, "bulk_grid") == 0) { ctx->bulk_grid = value; return 0; }
+  if (strcmp(name, "heavy_prio") == 0) { ctx->heavy_prio = value; return 0; }
   return fail(ctx, CFS_E_ARG, "cfs_set_option: unknown option '%s'", name);
 }
 
