@@ -1,12 +1,21 @@
-// cfs_numjac_cols.cuh -- the num_jac evaluations of one trajectory as H*(2NJ+1) single-chain work items, for the fused
-// persistent solver (k_fused.cu), where ONE problem's H waypoints must keep a whole CTA busy and the instruction
-// footprint must stay small (the fused kernel is instruction-fetch bound: ncu stall "no_instruction" 12 of 20 cycles
-// per issue with the one-thread-per-waypoint routine inlined).
+// cfs_numjac_cols.cuh -- the num_jac evaluations of one trajectory as single-chain work items, for the fused persistent
+// solver (k_fused.cu), where ONE problem's H waypoints must keep a whole CTA busy and the instruction footprint must stay
+// small (the fused kernel is instruction-fetch bound with the one-thread-per-waypoint routine of cfs_numjac.cuh inlined:
+// ncu stall "no_instruction" 12 of 20 cycles per issue).
 //
-// Same evaluated values as cfs_numjac.cuh (and hence as Lib/functions/num_jac.m applied to dist_arm_*): item
-// (i, col, sign) evaluates f at x with joints < col at theta - eps/2 (num_jac never resets xp, num_jac.m:13-14), joint
-// col at theta +- eps/2 and joints > col at theta; the extra item per waypoint is the base evaluation y = f(x).
-// One loop body = one link transform + endpoints + distance: ~6 KB of SASS instead of ~90 KB.
+// Same evaluated values as cfs_numjac.cuh (and hence as Lib/functions/num_jac.m applied to dist_arm_*).  num_jac never
+// resets xp (num_jac.m:13-14), so column c is evaluated with joints < c at theta - eps/2, joint c at theta +- eps/2 and
+// joints > c at theta.  Every evaluation of a waypoint is therefore a path in one small tree:
+//     chain M ("all minus"):  links 0..NJ-1 at theta - eps/2; its running transforms Mm_l are the kinematic prefix of every
+//                             column, its running minima pmin_l = min_{l' <= l} d_l' the distances of the unmoved links
+//     chain B (base, y=f(x)): links 0..NJ-1 at theta
+//     P_c  (yhi of column c): from Mm_{c-1}: link c at theta + eps/2, links > c at theta          (NJ - c link steps)
+//     N_c  (ylo of column c): from Mm_c:     links > c at theta                                    (NJ - 1 - c link steps)
+// => 2 NJ + NJ(NJ+1)/2 + NJ(NJ-1)/2 = 35 link steps per waypoint at NJ = 5 instead of 55, in two passes:
+//     pass 1: H threads, chains (M_i, B_i) side by side; M stores Mm_1..Mm_{NJ-2} and pmin_0..pmin_{NJ-1} in shared memory
+//     pass 2: NJ*H items of exactly NJ link steps each -- item (t, i) = P_t followed by N_{NJ-1-t} -- two per thread
+// One loop body = one link transform + endpoints + distance for both chains (two independent FP64 dependency chains per
+// thread): ~6 KB of SASS.
 #pragma once
 #include "cfs_geom.cuh"
 
@@ -30,48 +39,154 @@ __device__ __forceinline__ void numjac_sincos(const DevTables &tab, const double
   }
 }
 
-// Two evaluation chains side by side (two independent FP64 dependency chains per thread: the chain is latency bound),
-// each against obstacles j0, j0+1.  Chain X: waypoint iX, column colX (colX == NJ: base evaluation, all joints at theta),
-// signX 0: joint colX at +eps/2, 1: at -eps/2.  Chain B is skipped when !hasB.
+// shared-memory scratch of the gradient phase, in doubles (aliases the QP scratch span, see k_fused.cu)
+__host__ __device__ inline size_t numjac_scratch_doubles(int nj, int H, int OH) {
+  return (size_t)6 * nj * H            // scw
+         + (size_t)2 * OH * nj         // fv: f(x+), f(x-) per (obstacle, waypoint, column)
+         + (size_t)12 * (nj > 2 ? nj - 2 : 0) * H  // pm: Mm_1 .. Mm_{NJ-2}
+         + (size_t)OH * nj;            // pmin
+}
+
+struct NumjacScratch {
+  double *scw, *fv, *pm, *pmin;
+};
+__device__ __forceinline__ NumjacScratch numjac_scratch(double *base, int nj, int H, int OH) {
+  NumjacScratch w;
+  w.scw = base;
+  w.fv = w.scw + 6 * nj * H;
+  w.pm = w.fv + 2 * OH * nj;
+  w.pmin = w.pm + 12 * (nj > 2 ? nj - 2 : 0) * H;
+  return w;
+}
+
+// One work item = NJ link steps.  pass 1: type 0 = chain B, type 1 = chain M.  pass 2: type t in [0, NJ): P_t then
+// N_{NJ-1-t}.  Step s of an item: link l, sin/cos kind, whether the step starts a segment, whether it ends one.
+struct StepDesc {
+  int l, kind;
+  int start;  // 0 continue, 1 segment starts here
+  int end;    // 0 no; 1 write base distance (orhs); 2 write fv[...][col][sign]; pass-1 chain M handles its own stores
+  int col, sign;
+};
 template <int NJ>
-__device__ __forceinline__ void numjac_chain2(const DevTables &tab, const double *scw, int H, int iA, int colA, int signA,
-                                              int iB, int colB, int signB, bool hasB, int j0, int nobs, int &touched,
-                                              double dA[2], double dB[2]) {
-  dA[0] = dA[1] = dB[0] = dB[1] = INFINITY;
+__device__ __forceinline__ StepDesc step_desc(int pass, int type, int s) {
+  StepDesc d;
+  if (pass == 1) {
+    d.l = s;
+    d.kind = type ? 2 : 0;
+    d.start = (s == 0);
+    d.end = (s == NJ - 1) ? (type ? 2 : 1) : 0;
+    d.col = NJ - 1;  // chain M is also ylo of the last column
+    d.sign = 1;
+  } else {
+    const int np = NJ - type;  // link steps of P_type
+    if (s < np) {
+      d.l = type + s;
+      d.kind = (s == 0) ? 1 : 0;
+      d.start = (s == 0);
+      d.end = (s == np - 1) ? 2 : 0;
+      d.col = type;
+      d.sign = 0;
+    } else {
+      d.l = s;
+      d.kind = 0;
+      d.start = (s == np);
+      d.end = (s == NJ - 1) ? 2 : 0;
+      d.col = NJ - 1 - type;
+      d.sign = 1;
+    }
+  }
+  return d;
+}
+
+// Two items side by side against obstacles j0, j0+1.  Item X: waypoint iX, type tyX.  Chain B is skipped when !hasB.
+// Results go to w.fv / orhs_base (the base distance, margin not yet subtracted) / w.pm / w.pmin.
+template <int NJ>
+__device__ __forceinline__ void numjac_items2(const DevTables &tab, const NumjacScratch &w, int H, int pass, int iA, int tyA,
+                                              int iB, int tyB, bool hasB, int j0, int nobs, int &touched, double *dbase) {
+  const double *scw = w.scw;
   Xf MA, MB;
   double pA[6], pB[6];
+  double dA[2], dB[2];
+  dA[0] = dA[1] = dB[0] = dB[1] = INFINITY;
 #pragma unroll 1
-  for (int l = 0; l < NJ; ++l) {
-    // joints < col: theta - eps/2 ; joint col: +-eps/2 ; joints > col (and the base evaluation): theta
-    const int kA = (colA == NJ || l > colA) ? 0 : ((l < colA || signA) ? 2 : 1);
-    const int kB = (colB == NJ || l > colB) ? 0 : ((l < colB || signB) ? 2 : 1);
-    const double cA = scw[((2 * kA + 0) * NJ + l) * H + iA], sA = scw[((2 * kA + 1) * NJ + l) * H + iA];
-    const double cB = scw[((2 * kB + 0) * NJ + l) * H + iB], sB = scw[((2 * kB + 1) * NJ + l) * H + iB];
-    if (l == 0) {
-      xf_first(tab.link[0], cA, sA, MA);
-      xf_first(tab.link[0], cB, sB, MB);
-    } else {
-      xf_step_inplace(MA, tab.link[l], cA, sA);
-      xf_step_inplace(MB, tab.link[l], cB, sB);
+  for (int s = 0; s < NJ; ++s) {
+    const StepDesc a = step_desc<NJ>(pass, tyA, s), b = step_desc<NJ>(pass, tyB, s);
+    const double cA = scw[((2 * a.kind + 0) * NJ + a.l) * H + iA], sA = scw[((2 * a.kind + 1) * NJ + a.l) * H + iA];
+    const double cB = scw[((2 * b.kind + 0) * NJ + b.l) * H + iB], sB = scw[((2 * b.kind + 1) * NJ + b.l) * H + iB];
+    // ---- segment start: kinematic prefix Mm_{l-1} and the minima of the links it already passed ----
+    if (a.start && a.l > 0) {
+      if (a.l == 1) {
+        xf_first(tab.link[0], scw[((2 * 2 + 0) * NJ + 0) * H + iA], scw[((2 * 2 + 1) * NJ + 0) * H + iA], MA);
+      } else {
+        const double *src = w.pm + ((size_t)iA * (NJ - 2) + (a.l - 2)) * 12;
+#pragma unroll
+        for (int e = 0; e < 12; ++e) MA.m[e] = src[e];
+      }
+      dA[0] = w.pmin[((size_t)j0 * H + iA) * NJ + a.l - 1];
+      if (j0 + 1 < nobs) dA[1] = w.pmin[((size_t)(j0 + 1) * H + iA) * NJ + a.l - 1];
     }
-    link_endpoints(MA, tab.link[l], tab.base, pA);
-    link_endpoints(MB, tab.link[l], tab.base, pB);
+    if (b.start && b.l > 0) {
+      if (b.l == 1) {
+        xf_first(tab.link[0], scw[((2 * 2 + 0) * NJ + 0) * H + iB], scw[((2 * 2 + 1) * NJ + 0) * H + iB], MB);
+      } else {
+        const double *src = w.pm + ((size_t)iB * (NJ - 2) + (b.l - 2)) * 12;
+#pragma unroll
+        for (int e = 0; e < 12; ++e) MB.m[e] = src[e];
+      }
+      dB[0] = w.pmin[((size_t)j0 * H + iB) * NJ + b.l - 1];
+      if (j0 + 1 < nobs) dB[1] = w.pmin[((size_t)(j0 + 1) * H + iB) * NJ + b.l - 1];
+    }
+    // ---- one link step of both chains ----
+    if (a.l == 0)
+      xf_first(tab.link[0], cA, sA, MA);
+    else
+      xf_step_inplace(MA, tab.link[a.l], cA, sA);
+    if (b.l == 0)
+      xf_first(tab.link[0], cB, sB, MB);
+    else
+      xf_step_inplace(MB, tab.link[b.l], cB, sB);
+    link_endpoints(MA, tab.link[a.l], tab.base, pA);
+    link_endpoints(MB, tab.link[b.l], tab.base, pB);
 #pragma unroll 1
     for (int jj = 0; jj < 2; ++jj)
       if (j0 + jj < nobs) {
-        const double a = link_obs_dist(pA, tab.obs[j0 + jj], touched);
+        const double da = link_obs_dist(pA, tab.obs[j0 + jj], touched);
         int tb = 0;
-        const double b = link_obs_dist(pB, tab.obs[j0 + jj], tb);
+        const double db = link_obs_dist(pB, tab.obs[j0 + jj], tb);
         if (hasB) touched |= tb;
         // strict <: the first minimal link wins (dist_arm_3D_Heu_2.m:25-28)
         if (jj == 0) {
-          dA[0] = a < dA[0] ? a : dA[0];
-          dB[0] = b < dB[0] ? b : dB[0];
+          dA[0] = da < dA[0] ? da : dA[0];
+          dB[0] = db < dB[0] ? db : dB[0];
         } else {
-          dA[1] = a < dA[1] ? a : dA[1];
-          dB[1] = b < dB[1] ? b : dB[1];
+          dA[1] = da < dA[1] ? da : dA[1];
+          dB[1] = db < dB[1] ? db : dB[1];
         }
       }
+    // ---- stores ----
+#pragma unroll 1
+    for (int ch = 0; ch < (hasB ? 2 : 1); ++ch) {
+      const StepDesc &d = ch ? b : a;
+      const int i = ch ? iB : iA, ty = ch ? tyB : tyA;
+      const double d0 = ch ? dB[0] : dA[0], d1 = ch ? dB[1] : dA[1];
+      if (pass == 1 && ty == 1) {  // chain M: running minima and kinematic prefixes for pass 2
+        w.pmin[((size_t)j0 * H + i) * NJ + d.l] = d0;
+        if (j0 + 1 < nobs) w.pmin[((size_t)(j0 + 1) * H + i) * NJ + d.l] = d1;
+        if (NJ > 2 && d.l >= 1 && d.l <= NJ - 2 && j0 == 0) {
+          double *dst = w.pm + ((size_t)i * (NJ - 2) + (d.l - 1)) * 12;
+          const Xf &M = ch ? MB : MA;
+#pragma unroll
+          for (int e = 0; e < 12; ++e) dst[e] = M.m[e];
+        }
+      }
+      if (d.end == 1) {
+        dbase[j0 * H + i] = d0;
+        if (j0 + 1 < nobs) dbase[(j0 + 1) * H + i] = d1;
+      } else if (d.end == 2) {
+        w.fv[(((size_t)j0 * H + i) * NJ + d.col) * 2 + d.sign] = d0;
+        if (j0 + 1 < nobs) w.fv[(((size_t)(j0 + 1) * H + i) * NJ + d.col) * 2 + d.sign] = d1;
+      }
+    }
   }
 }
 

@@ -22,8 +22,17 @@
 
 namespace cfs {
 
+#ifdef PF_GRAD_DETAIL
+#define PF_GRAD(k) PF_ADD(k)
+#define PF_ROWS 4
+#else
+#define PF_GRAD(k) do { } while (0)
+#define PF_ROWS 0
+#endif
+
 #define FUSED_BULK_NT 128
-#define FUSED_BULK_QS QP_QS
+#define FUSED_BULK_QS 16
+#define FUSED_BULK_QZ 16  // cached directions: working sets of up to 15 rows + the candidate stay entirely in shared memory
 #define FUSED_HEAVY_NT 256
 #define FUSED_HEAVY_QS 144
 
@@ -31,10 +40,10 @@ struct FusedLayout {
   size_t qp_bytes, xs, us, tab, mbar, total;
 };
 
-__host__ __device__ inline FusedLayout fused_layout(int n, int nj, int OH, int m, int qs, int nt) {
+__host__ __device__ inline FusedLayout fused_layout(int n, int nj, int OH, int m, int qs, int nt, int qz) {
   FusedLayout L;
   size_t off[QP_NOFF];
-  L.qp_bytes = qp_smem_layout(n, nj, OH, m, off, qs, nt);
+  L.qp_bytes = qp_smem_layout(n, nj, OH, m, off, qs, nt, qz);
   size_t o = L.qp_bytes;
   L.xs = o; o += sizeof(double) * 2 * n;
   L.us = o; o += sizeof(double) * n;
@@ -45,20 +54,22 @@ __host__ __device__ inline FusedLayout fused_layout(int n, int nj, int OH, int m
   return L;
 }
 
-template <int NJ, int NT, int QS, int MINB>
+template <int NJ, int NT, int QS, int MINB, int QZ>
 __global__ void __launch_bounds__(NT, MINB) k_cfs_fused(SolveArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int n = a.n, nj = NJ, H = a.H, np = 3 * n, OH = a.nobs * H, m = OH + 4 * n, N = 2 * n;
   const int tid = threadIdx.x;
-  const FusedLayout L = fused_layout(n, nj, OH, m, QS, NT);
-  const QpView s = qp_view(smem_raw, n, nj, OH, m, QS, NT);
+  const FusedLayout L = fused_layout(n, nj, OH, m, QS, NT, QZ);
+  const QpView s = qp_view(smem_raw, n, nj, OH, m, QS, NT, QZ);
   const bool heavy = a.tier == 1;
   double *xs = reinterpret_cast<double *>(smem_raw + L.xs);  // x_  (CFS_FANUC.m:55)
   double *us = reinterpret_cast<double *>(smem_raw + L.us);  // u   (CFS_FANUC.m:56)
   DevTables &tab = *reinterpret_cast<DevTables *>(smem_raw + L.tab);
   uint64_t *mbar = reinterpret_cast<uint64_t *>(smem_raw + L.mbar);
-  double *scw = reinterpret_cast<double *>(smem_raw);  // sin/cos cache [6][NJ][H], aliases the QP scratch span
-  double *fv = scw + 6 * NJ * H;                        // f(x+), f(x-) per (obstacle, waypoint, column): [OH][NJ][2]
+  // gradient-phase scratch (sin/cos cache, f(x+-), kinematic prefixes, running minima): aliases the QP scratch span,
+  // which starts at offset 0 of the layout
+  const NumjacScratch nw = numjac_scratch(reinterpret_cast<double *>(smem_raw), NJ, H, OH);
+  double *fv = nw.fv;  // f(x+), f(x-) per (obstacle, waypoint, column): [OH][NJ][2]
 
   tma_stage(&tab, a.tab, tab_bytes(a.nobs), mbar);
   const double *__restrict__ G = a.G;
@@ -138,36 +149,38 @@ __global__ void __launch_bounds__(NT, MINB) k_cfs_fused(SolveArgs a) {
       // ---- get_con: distances + num_jac gradients of every waypoint, rows written in place (CFS_FANUC.m:110-124) ----
       PF_START();
       __syncthreads();  // the sin/cos cache aliases the previous QP's scratch
-      numjac_sincos<NJ, NT>(tab, xs, H, scw);
+      numjac_sincos<NJ, NT>(tab, xs, H, nw.scw);
       __syncthreads();
-      // H*(2NJ+1) single-chain work items: f(x+), f(x-) of every gradient column + the base evaluation of every
-      // waypoint; every thread runs two items side by side
-      {
-        const int items = H * (2 * NJ + 1);
+      PF_GRAD(1);
+      // pass 1: one thread per waypoint runs the all-minus chain M_i and the base chain B_i side by side;
+      // pass 2: NJ*H items of NJ link steps (P_t then N_{NJ-1-t} from M's stored prefixes), two per thread
 #pragma unroll 1
-        for (int eA = tid; eA < items; eA += 2 * NT) {
-          const bool hasB = eA + NT < items;
-          const int eB = hasB ? eA + NT : eA;
-          const int c2A = eA / H, iA = eA - c2A * H, c2B = eB / H, iB = eB - c2B * H;
+      for (int pass = 1; pass <= 2; ++pass) {
+        const int items = pass == 1 ? H : NJ * H;
+        const int stride = pass == 1 ? NT : 2 * NT;
 #pragma unroll 1
-          for (int j0 = 0; j0 < a.nobs; j0 += 2) {
-            double dA[2], dB[2];
-            numjac_chain2<NJ>(tab, scw, H, iA, c2A >> 1, c2A & 1, iB, c2B >> 1, c2B & 1, hasB, j0, a.nobs, touched, dA, dB);
-#pragma unroll 1
-            for (int ch = 0; ch < (hasB ? 2 : 1); ++ch) {
-              const int c2 = ch ? c2B : c2A, i = ch ? iB : iA;
-              const double d0 = ch ? dB[0] : dA[0], d1 = ch ? dB[1] : dA[1];
-              if ((c2 >> 1) == NJ) {  // base evaluation: I = distance - margin (CFS_FANUC.m:117)
-                s.orhs[j0 * H + i] = d0 - (a.margin_is_D ? tab.obs[j0].D : tab.obs[j0].eps);
-                if (j0 + 1 < a.nobs)
-                  s.orhs[(j0 + 1) * H + i] = d1 - (a.margin_is_D ? tab.obs[j0 + 1].D : tab.obs[j0 + 1].eps);
-              } else {
-                fv[((j0 * H + i) * NJ + (c2 >> 1)) * 2 + (c2 & 1)] = d0;
-                if (j0 + 1 < a.nobs) fv[(((j0 + 1) * H + i) * NJ + (c2 >> 1)) * 2 + (c2 & 1)] = d1;
-              }
-            }
+        for (int eA = tid; eA < items; eA += stride) {
+          bool hasB = true;
+          int iA = eA, tyA = 1, iB = eA, tyB = 0;
+          if (pass == 2) {
+            hasB = eA + NT < items;
+            const int eB = hasB ? eA + NT : eA;
+            tyA = eA / H;
+            iA = eA - tyA * H;
+            tyB = eB / H;
+            iB = eB - tyB * H;
           }
+#pragma unroll 1
+          for (int j0 = 0; j0 < a.nobs; j0 += 2)
+            numjac_items2<NJ>(tab, nw, H, pass, iA, tyA, iB, tyB, hasB, j0, a.nobs, touched, s.orhs);
         }
+        __syncthreads();
+        PF_GRAD(1 + pass);
+      }
+#pragma unroll 1
+      for (int cid = tid; cid < OH; cid += NT) {  // I = distance - margin (CFS_FANUC.m:117)
+        const int j = cid / H;
+        s.orhs[cid] -= a.margin_is_D ? tab.obs[j].D : tab.obs[j].eps;
       }
       __syncthreads();
 #pragma unroll 1
@@ -199,12 +212,12 @@ __global__ void __launch_bounds__(NT, MINB) k_cfs_fused(SolveArgs a) {
       }
       if (tid == 0) s.toff[0] = 0;
       __syncthreads();
-      PF_ADD(0);
+      PF_ADD(PF_ROWS);
 
       // ---- Solve_QP (CFS_FANUC.m:85) ----
       int q = 0, steps = 0;
       const int masked = qp_mask_antiparallel<NT>(s, dims);
-      const int qst = qp_solve<NT, QS, (MINB == 1), NJ>(s, dims, cost0, fupper, false, q, steps, qmax_seen, pf, tck, prof,
+      const int qst = qp_solve<NT, QS, (MINB == 1), NJ, QZ>(s, dims, cost0, fupper, false, q, steps, qmax_seen, pf, tck, prof,
                                                         heavy ? 0x7fffffff : a.esc_steps, masked);
       steps_total += steps;
       steps_prob += steps;
@@ -280,27 +293,28 @@ __global__ void __launch_bounds__(NT, MINB) k_cfs_fused(SolveArgs a) {
 
 static bool fused_supported_nj(int nj) { return nj == 2 || nj == 5; }
 
-static void tier_cfg(int tier, int &nt, int &qs) {
+static void tier_cfg(int tier, int &nt, int &qs, int &qz) {
   nt = tier ? FUSED_HEAVY_NT : FUSED_BULK_NT;
   qs = tier ? FUSED_HEAVY_QS : FUSED_BULK_QS;
+  qz = tier ? 0 : FUSED_BULK_QZ;
 }
 
 size_t fused_smem_bytes(const SolveArgs &a, int tier) {
-  int nt, qs;
-  tier_cfg(tier, nt, qs);
+  int nt, qs, qz;
+  tier_cfg(tier, nt, qs, qz);
   const int OH = a.nobs * a.H;
-  return fused_layout(a.n, a.nj, OH, OH + 4 * a.n, qs, nt).total;
+  return fused_layout(a.n, a.nj, OH, OH + 4 * a.n, qs, nt, qz).total;
 }
 
 bool fused_supported(const SolveArgs &a) {
   if (!fused_supported_nj(a.nj)) return false;
   const int OH = a.nobs * a.H;
   for (int tier = 0; tier < 2; ++tier) {
-    int nt, qs;
-    tier_cfg(tier, nt, qs);
-    // the sin/cos cache must fit into the QP scratch span it aliases, and the CTA into one SM's shared memory
+    int nt, qs, qz;
+    tier_cfg(tier, nt, qs, qz);
+    // the gradient-phase scratch must fit into the QP scratch span it aliases, and the CTA into one SM's shared memory
     (void)nt;
-    if (sizeof(double) * (6 * a.nj * a.H + 2 * (size_t)OH * a.nj) > qp_scratch_span(a.n, a.nj, OH, qs)) return false;
+    if (sizeof(double) * numjac_scratch_doubles(a.nj, a.H, OH) > qp_scratch_span(a.n, a.nj, OH, qs, qz)) return false;
     if (fused_smem_bytes(a, tier) > 227 * 1024) return false;
   }
   return true;
@@ -318,11 +332,11 @@ static int grid_of(K kernel, int nt, size_t smem, int device) {
 int fused_max_grid(const SolveArgs &a, int device, int tier) {
   const size_t smem = fused_smem_bytes(a, tier);
   if (tier == 0) {
-    if (a.nj == 2) return grid_of(k_cfs_fused<2, FUSED_BULK_NT, FUSED_BULK_QS, 3>, FUSED_BULK_NT, smem, device);
-    if (a.nj == 5) return grid_of(k_cfs_fused<5, FUSED_BULK_NT, FUSED_BULK_QS, 3>, FUSED_BULK_NT, smem, device);
+    if (a.nj == 2) return grid_of(k_cfs_fused<2, FUSED_BULK_NT, FUSED_BULK_QS, 3, FUSED_BULK_QZ>, FUSED_BULK_NT, smem, device);
+    if (a.nj == 5) return grid_of(k_cfs_fused<5, FUSED_BULK_NT, FUSED_BULK_QS, 3, FUSED_BULK_QZ>, FUSED_BULK_NT, smem, device);
   } else {
-    if (a.nj == 2) return grid_of(k_cfs_fused<2, FUSED_HEAVY_NT, FUSED_HEAVY_QS, 1>, FUSED_HEAVY_NT, smem, device);
-    if (a.nj == 5) return grid_of(k_cfs_fused<5, FUSED_HEAVY_NT, FUSED_HEAVY_QS, 1>, FUSED_HEAVY_NT, smem, device);
+    if (a.nj == 2) return grid_of(k_cfs_fused<2, FUSED_HEAVY_NT, FUSED_HEAVY_QS, 1, 0>, FUSED_HEAVY_NT, smem, device);
+    if (a.nj == 5) return grid_of(k_cfs_fused<5, FUSED_HEAVY_NT, FUSED_HEAVY_QS, 1, 0>, FUSED_HEAVY_NT, smem, device);
   }
   return 0;
 }
@@ -332,12 +346,12 @@ cudaError_t launch_fused(const SolveArgs &a_in, int grid, int tier, cudaStream_t
   a.tier = tier;
   const size_t smem = fused_smem_bytes(a, tier);
   if (tier == 0) {
-    if (a.nj == 2) k_cfs_fused<2, FUSED_BULK_NT, FUSED_BULK_QS, 3><<<grid, FUSED_BULK_NT, smem, st>>>(a);
-    else if (a.nj == 5) k_cfs_fused<5, FUSED_BULK_NT, FUSED_BULK_QS, 3><<<grid, FUSED_BULK_NT, smem, st>>>(a);
+    if (a.nj == 2) k_cfs_fused<2, FUSED_BULK_NT, FUSED_BULK_QS, 3, FUSED_BULK_QZ><<<grid, FUSED_BULK_NT, smem, st>>>(a);
+    else if (a.nj == 5) k_cfs_fused<5, FUSED_BULK_NT, FUSED_BULK_QS, 3, FUSED_BULK_QZ><<<grid, FUSED_BULK_NT, smem, st>>>(a);
     else return cudaErrorInvalidValue;
   } else {
-    if (a.nj == 2) k_cfs_fused<2, FUSED_HEAVY_NT, FUSED_HEAVY_QS, 1><<<grid, FUSED_HEAVY_NT, smem, st>>>(a);
-    else if (a.nj == 5) k_cfs_fused<5, FUSED_HEAVY_NT, FUSED_HEAVY_QS, 1><<<grid, FUSED_HEAVY_NT, smem, st>>>(a);
+    if (a.nj == 2) k_cfs_fused<2, FUSED_HEAVY_NT, FUSED_HEAVY_QS, 1, 0><<<grid, FUSED_HEAVY_NT, smem, st>>>(a);
+    else if (a.nj == 5) k_cfs_fused<5, FUSED_HEAVY_NT, FUSED_HEAVY_QS, 1, 0><<<grid, FUSED_HEAVY_NT, smem, st>>>(a);
     else return cudaErrorInvalidValue;
   }
   return cudaGetLastError();

@@ -34,34 +34,43 @@ struct QpView {  // decoded shared-memory layout
   double *gns;     // 3n      G_ii of every primitive row (per kernel)
   double *ums;     // n       MAX_input (per kernel)
   double *pscr;    // QP_THREADS  partial sums of the polish residual
+  double *zc;      // QZ*n   cached directions z_w = QQ^-1 c_w' of the working-set members + the candidate (bulk tier)
+  int *zslot;      // QZ+1   physical slot of member w; zslot[q] is the candidate's slot
+  double *yp;      // 2n     B_theta z_p | B_omega z_p of the candidate (cached mode)
 };
 
-#define QP_NOFF 23
+#define QP_NOFF 26
+// qz > 0: "cached" layout of the fused bulk tier -- the working set holds at most qz-1 rows, every member's direction
+// z_w (n doubles) stays in shared memory, and the flat term lists of the G-based refresh are not needed.
 __host__ __device__ inline size_t qp_smem_layout(int n, int nj, int OH, int m, size_t *off /*[QP_NOFF]*/, int qs = QP_QS,
-                                                  int nt = QP_THREADS) {
+                                                  int nt = QP_THREADS, int qz = 0) {
   size_t o = 0;
   const int np = 3 * n;
-  const int tmax = nj * OH + n + 2;
-  // [Msm | v | tcoef | twgt | lam | r | g] first and contiguous: all of it is dead while the fused kernel runs its
-  // gradient phase, which aliases its sin/cos cache onto this span (qp_scratch_span()).
+  const int tmax = qz ? 0 : nj * OH + n + 2;
+  const int nw = qz ? qz + 2 : n + 2;  // capacity of the per-member arrays
+  // [zc | Msm | v | tcoef | twgt | lam | r | g] first and contiguous: all of it is dead while the fused kernel runs its
+  // gradient phase, which aliases its scratch onto this span (qp_scratch_span()).
+  off[23] = o; o += sizeof(double) * (size_t)qz * n;
+  off[25] = o; o += sizeof(double) * (size_t)(qz ? 2 * n : 0);
   off[10] = o; o += sizeof(double) * qs * qs;
   off[0] = o; o += sizeof(double) * np;
   off[8] = o; o += sizeof(double) * tmax;
   off[9] = o; o += sizeof(double) * tmax;
-  off[4] = o; o += sizeof(double) * (n + 2);
-  off[5] = o; o += sizeof(double) * (n + 2);
-  off[6] = o; o += sizeof(double) * (n + 2);
+  off[4] = o; o += sizeof(double) * nw;
+  off[5] = o; o += sizeof(double) * nw;
+  off[6] = o; o += sizeof(double) * nw;
   off[1] = o; o += sizeof(double) * (size_t)OH * nj;
   off[2] = o; o += sizeof(double) * OH;
   off[3] = o; o += sizeof(double) * OH;
   off[7] = o; o += sizeof(double) * 64;
   off[11] = o; o += sizeof(double) * 8;
   off[12] = o; o += sizeof(double) * 8;
-  off[13] = o; o += sizeof(int) * (n + 2);
-  off[14] = o; o += sizeof(int) * (n + 4);
+  off[13] = o; o += sizeof(int) * nw;
+  off[14] = o; o += sizeof(int) * (nw + 2);
   off[15] = o; o += sizeof(int) * tmax;
   off[16] = o; o += sizeof(int) * tmax;
   off[17] = o; o += sizeof(int) * 8;
+  off[24] = o; o += sizeof(int) * (size_t)(qz ? qz + 2 : 0);
   off[18] = o; o += (size_t)((m + 15) / 16) * 16;
   o = (o + 15) / 16 * 16;
   off[19] = o; o += sizeof(double) * np;
@@ -71,16 +80,20 @@ __host__ __device__ inline size_t qp_smem_layout(int n, int nj, int OH, int m, s
   return (o + 15) / 16 * 16;
 }
 
-__host__ __device__ inline size_t qp_scratch_span(int n, int nj, int OH, int qs = QP_QS) {  // bytes of the leading dead-during-gradient span
-  const int tmax = nj * OH + n + 2;
-  return sizeof(double) * ((size_t)qs * qs + 3 * n + 2 * (size_t)tmax + 3 * (size_t)(n + 2));
+__host__ __device__ inline size_t qp_scratch_span(int n, int nj, int OH, int qs = QP_QS, int qz = 0) {  // bytes of the leading dead-during-gradient span
+  const int tmax = qz ? 0 : nj * OH + n + 2;
+  const int nw = qz ? qz + 2 : n + 2;
+  return sizeof(double) * ((size_t)qz * n + (size_t)(qz ? 2 * n : 0) + (size_t)qs * qs + 3 * n + 2 * (size_t)tmax + 3 * (size_t)nw);
 }
 
 __device__ __forceinline__ QpView qp_view(unsigned char *smem_raw, int n, int nj, int OH, int m, int qs = QP_QS,
-                                          int nt = QP_THREADS) {
+                                          int nt = QP_THREADS, int qz = 0) {
   QpView s;
   size_t off[QP_NOFF];
-  qp_smem_layout(n, nj, OH, m, off, qs, nt);
+  qp_smem_layout(n, nj, OH, m, off, qs, nt, qz);
+  s.zc = reinterpret_cast<double *>(smem_raw + off[23]);
+  s.zslot = reinterpret_cast<int *>(smem_raw + off[24]);
+  s.yp = reinterpret_cast<double *>(smem_raw + off[25]);
   s.v = reinterpret_cast<double *>(smem_raw + off[0]);
   s.ocoef = reinterpret_cast<double *>(smem_raw + off[1]);
   s.orhs = reinterpret_cast<double *>(smem_raw + off[2]);
@@ -243,6 +256,11 @@ static __device__ __noinline__ double block_sum(double val, double *red) {
   return __shfl_sync(0xffffffffu, s, 0);
 }
 
+#ifdef PF_GRAD_DETAIL  // dev build: slots 0-4 = gradient sub-phases, every QP phase lands in slot 5
+#define QPF(k) 5
+#else
+#define QPF(k) k
+#endif
 #define PF_START() do { if (prof && tid == 0) tck = clock64(); } while (0)
 #define PF_ADD(k) do { if (prof && tid == 0) { const long long now_ = clock64(); pf[k] += now_ - tck; tck = now_; } } while (0)
 
@@ -349,6 +367,120 @@ static __device__ __noinline__ void qp_refresh(const QpView &s, const QpDims &P,
     s.v[n + e] = aw;
   }
   __syncthreads();
+}
+
+// ---- cached-direction mode (fused bulk tier) ------------------------------------------------------------------------
+// Every working-set member w keeps z_w = QQ^-1 c_w' (n doubles, one pass over <= nj rows of G when the row becomes the
+// candidate) in shared memory.  Then nothing inside a dual step touches L2 any more:
+//   primal recovery   u = u0 - sum_w lambda_w z_w,  B_theta u and B_omega u in closed form
+//   sigma, g_w        e_p'(P z_p), e_w'(P z_p): closed-form partial sums over the candidate's direction
+
+// B_theta u and B_omega u of the control vector u (n entries, [waypoint][joint]) by warp-level prefix sums: one warp per
+// joint, two consecutive waypoints per lane.  With S1_i = sum_{j<=i} u_j:
+//   (B_omega u)_i = dt S1_i,   (B_theta u)_i = sum_{j<=i} (0.5 + (i-j)) dt^2 u_j = dt^2 (0.5 S1_i + sum_{j<i} S1_j)
+template <int NT>
+static __device__ __noinline__ void prims_from_controls(const double *u, double *vth, double *vom, int H, int nj, double dt) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const double dt2 = dt * dt;
+#pragma unroll 1
+  for (int k = warp; k < nj; k += NT / 32) {
+    double carry1 = 0.0, carry2 = 0.0;
+#pragma unroll 1
+    for (int base = 0; base < H; base += 64) {
+      const int i0 = base + 2 * lane, i1 = i0 + 1;
+      const double a0 = i0 < H ? u[i0 * nj + k] : 0.0, a1 = i1 < H ? u[i1 * nj + k] : 0.0;
+      const double pr = a0 + a1;
+      double inc = pr;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const double t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+      }
+      const double s0 = carry1 + ((inc - pr) + a0), s1 = carry1 + inc;  // S1 at i0, i1
+      const double rr = s0 + s1;
+      double inc2 = rr;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const double t = __shfl_up_sync(0xffffffffu, inc2, o);
+        if (lane >= o) inc2 += t;
+      }
+      const double t0 = carry2 + (inc2 - rr), t1 = t0 + s0;  // sum_{j<i} S1_j at i0, i1
+      if (i0 < H) {
+        vth[i0 * nj + k] = dt2 * (0.5 * s0 + t0);
+        vom[i0 * nj + k] = dt * s0;
+      }
+      if (i1 < H) {
+        vth[i1 * nj + k] = dt2 * (0.5 * s1 + t1);
+        vom[i1 * nj + k] = dt * s1;
+      }
+      carry1 = __shfl_sync(0xffffffffu, s1, 31);
+      carry2 += __shfl_sync(0xffffffffu, inc2, 31);
+    }
+  }
+}
+
+template <int NT>
+static __device__ __noinline__ void qp_refresh_cached(const QpView &s, const QpDims &P, int q) {
+  const int n = P.n;
+#pragma unroll 1
+  for (int c = threadIdx.x; c < n; c += NT) {
+    double acc = 0.0;
+#pragma unroll 4
+    for (int w = 0; w < q; ++w) acc += s.lam[w] * s.zc[(size_t)s.zslot[w] * n + c];
+    s.v[2 * n + c] = s.v0s[2 * n + c] - acc;
+  }
+  __syncthreads();
+  prims_from_controls<NT>(s.v + 2 * n, s.v, s.v + n, P.H, P.nj, P.dt);
+  __syncthreads();
+}
+
+// e_cid' y for y = P z given as (yth | yom | z)
+static __device__ __forceinline__ double row_dot_prims(int cid, const double *yth, const double *yom, const double *z,
+                                                       const QpDims &P, const double *ocoef) {
+  if (cid < P.OH) {
+    const double *c = ocoef + (size_t)cid * P.nj, *y = yth + wp_of(cid, P.H) * P.nj;
+    double acc = 0.0;
+#pragma unroll 1
+    for (int k = 0; k < P.nj; ++k) acc += c[k] * y[k];
+    return acc;
+  }
+  const int e = cid - P.OH, pr = e >> 1;
+  const double val = pr < P.n ? yom[pr] : z[pr - P.n];
+  return (e & 1) ? -val : val;
+}
+
+// candidate p: z_p = QQ^-1 c_p' into the candidate slot (one pass over <= nj rows of G), y_p = P z_p by prefix sums, then
+// sigma = c_p QQ^-1 c_p' = e_p'y_p and g_w = c_w QQ^-1 c_p' = e_w'y_p for every member
+template <int NT>
+static __device__ __noinline__ double qp_candidate_cached(const QpView &s, const QpDims &P, int p, int q) {
+  const int tid = threadIdx.x, n = P.n;
+  const Desc dp = decode(p, P, s.ocoef);
+  double *zp = s.zc + (size_t)s.zslot[q] * n;
+  const double *__restrict__ Gu = P.G + (size_t)dp.row0 * P.np + 2 * n;  // control block of the candidate's primitive rows
+#pragma unroll 1
+  for (int c = tid; c < n; c += NT) {
+    double acc = 0.0;
+    if (dp.nterm == 1) {
+      acc = dp.coef * Gu[c];
+    } else {
+#pragma unroll 1
+      for (int k = 0; k < dp.nterm; ++k) acc += dp.cv[k] * Gu[(size_t)k * P.np + c];
+    }
+    zp[c] = acc;
+  }
+  __syncthreads();
+  prims_from_controls<NT>(zp, s.yp, s.yp + n, P.H, P.nj, P.dt);
+  __syncthreads();
+#pragma unroll 1
+  for (int w = tid; w <= q; w += NT) {
+    const double val = row_dot_prims(w < q ? s.act[w] : p, s.yp, s.yp + n, zp, P, s.ocoef);
+    if (w < q)
+      s.g[w] = val;
+    else
+      s.red[40] = val;
+  }
+  __syncthreads();
+  return s.red[40];
 }
 
 // Phase A of every QP: if two CONSECUTIVE obstacle rows have (almost) opposite coefficient vectors -- the gradient flips
@@ -464,7 +596,7 @@ static __device__ __noinline__ void qp_polish(const QpView &s, const QpDims &P, 
 // optimum (controls in s.v[2n..3n)), s.lam / s.act / q the multipliers and the working set.
 // status: 0 optimal, 2 infeasible, 3 numerical, 4 escalate (step_cap exceeded / working set outgrew QS and !SPILL).
 // Must be called by all NT threads of the CTA.  NJ: compile-time joint count (0 = use P.nj).
-template <int NT, int QS, bool SPILL, int NJ>
+template <int NT, int QS, bool SPILL, int NJ, int QZ = 0>
 __device__ __forceinline__ int qp_solve(const QpView &s, const QpDims &P, double cost0, double fupper, bool skip_solve,
                                         int &q_out, int &steps_out, int &qmax_seen, long long *pf, long long &tck,
                                         bool prof, int step_cap = 0x7fffffff, int masked = 0) {
@@ -472,15 +604,25 @@ __device__ __forceinline__ int qp_solve(const QpView &s, const QpDims &P, double
   const int n = P.n, nj = NJ ? NJ : P.nj, H = P.H, OH = P.OH, has_vel = P.has_vel, has_bnd = P.has_bnd;
   double *Mgl = P.Mgl;
   const int ldg = P.ldg;
+  constexpr bool CACHED = QZ > 0;
   int q = 0, status = skip_solve ? 0 : -1, steps = 0;
   bool in_smem = true, polished = false;
+  if (CACHED) {
+    if (tid <= QZ) s.zslot[tid] = tid;
+    __syncthreads();
+  }
   double fval = cost0;
   const int max_steps = 20 * (P.m + n) + 100;
   while (status < 0) {
     double *M = (SPILL && !in_smem) ? Mgl : s.Msm;  // column-major, leading dimension ldm
     const int ldm = (SPILL && !in_smem) ? ldg : QS;
-    if (q > 0) qp_refresh<NT, (SPILL ? 32 : 8)>(s, P, q);
-    PF_ADD(1);
+    if (q > 0) {
+      if (CACHED)
+        qp_refresh_cached<NT>(s, P, q);
+      else
+        qp_refresh<NT, (SPILL ? 32 : 8)>(s, P, q);
+    }
+    PF_ADD(QPF(1));
     pf[7] += 1;
     // (1) most violated inactive row, normalised by its QQ^-1 norm: minimise -slack^2/sigma over the violated rows
     double best = 0.0;
@@ -537,7 +679,7 @@ __device__ __forceinline__ int qp_solve(const QpView &s, const QpDims &P, double
       }
     }
     block_argmin<NT>(best, bidx, s.red);
-    PF_ADD(2);
+    PF_ADD(QPF(2));
     if (bidx < 0 && masked) {  // this phase is feasible: unmask the next level and carry on with the same working set
       const int lvl = masked == 2 ? 2 : 3;
 #pragma unroll 1
@@ -563,7 +705,13 @@ __device__ __forceinline__ int qp_solve(const QpView &s, const QpDims &P, double
     const int p = bidx;
     // sigma = c_p QQ^-1 c_p': one G entry for a primitive row, an nj x nj bilinear form (one load per thread) otherwise
     double sigma;
-    if (p < OH) {
+    if (CACHED) {
+      if (q > QZ - 1) {  // no slot left for the candidate's direction: the heavy tier redoes this iteration
+        status = 4;
+        break;
+      }
+      sigma = qp_candidate_cached<NT>(s, P, p, q);
+    } else if (p < OH) {
       double part = 0.0;
       if (tid < nj * nj) {
         const int k = tid / nj, l2 = tid - k * nj, r0 = wp_of(p, H) * nj;
@@ -586,9 +734,11 @@ __device__ __forceinline__ int qp_solve(const QpView &s, const QpDims &P, double
         break;
       }
       // g_w = c_w QQ^-1 c_p'
+      if (!CACHED) {
 #pragma unroll 1
-      for (int w = tid; w < q; w += NT) s.g[w] = gram(s.act[w], p, P, s.ocoef);
-      __syncthreads();
+        for (int w = tid; w < q; w += NT) s.g[w] = gram(s.act[w], p, P, s.ocoef);
+        __syncthreads();
+      }
       // r = Minv g ;  delta = sigma - g'r  (z'n+ in Goldfarb-Idnani's notation) ; t1 = largest dual step keeping lambda >= 0
       double part = 0.0, t1 = INFINITY;
       int l = -1;
@@ -663,7 +813,7 @@ __device__ __forceinline__ int qp_solve(const QpView &s, const QpDims &P, double
       for (int w = tid; w < q; w += NT) s.lam[w] -= t * s.r[w];
       lam_p += t;
       __syncthreads();
-      PF_ADD(3);
+      PF_ADD(QPF(3));
       if (full) {
         if (in_smem && q + 1 > QS) {
           if (!SPILL) {
@@ -697,37 +847,40 @@ __device__ __forceinline__ int qp_solve(const QpView &s, const QpDims &P, double
             Mw[r + (size_t)ldw * c] = val;
           }
         }
-        const Desc dp = decode(p, P, s.ocoef);
-        const int t0 = s.toff[q];
-        if (tid < dp.nterm) {
-          s.trow[t0 + tid] = dp.row0 + tid;
-          s.tcoef[t0 + tid] = dp.cv ? dp.cv[tid] : dp.coef;
-          s.towner[t0 + tid] = q;
+        if (!CACHED) {
+          const Desc dp = decode(p, P, s.ocoef);
+          const int t0 = s.toff[q];
+          if (tid < dp.nterm) {
+            s.trow[t0 + tid] = dp.row0 + tid;
+            s.tcoef[t0 + tid] = dp.cv ? dp.cv[tid] : dp.coef;
+            s.towner[t0 + tid] = q;
+          }
+          if (tid == 0) s.toff[q + 1] = t0 + dp.nterm;
         }
         if (tid == 0) {
           s.act[q] = p;
           s.lam[q] = lam_p;
           s.inact[p] = 1;
-          s.toff[q + 1] = t0 + dp.nterm;
         }
         ++q;
         if (q > qmax_seen) qmax_seen = q;
         __syncthreads();
-        PF_ADD(4);
+        PF_ADD(QPF(4));
         break;
       }
       // drop working-set member l: M <- M - M(:,l) M(l,:)/M(l,l), then move the last member into slot l
       {
         const int last = q - 1;
+        double *col = CACHED ? s.pscr : s.g;  // cached mode keeps g (it only depends on (w, p))
 #pragma unroll 1
-        for (int w = tid; w < q; w += NT) s.g[w] = M[w + (size_t)ldm * l];
+        for (int w = tid; w < q; w += NT) col[w] = M[w + (size_t)ldm * l];
         __syncthreads();
-        const double ip = 1.0 / s.g[l];
+        const double ip = 1.0 / col[l];
 #pragma unroll 1
         for (int c = tid >> 5; c < q; c += NT / 32) {
-          const double gc = s.g[c] * ip;
+          const double gc = col[c] * ip;
 #pragma unroll 4
-          for (int r = tid & 31; r < q; r += 32) M[r + (size_t)ldm * c] -= s.g[r] * gc;
+          for (int r = tid & 31; r < q; r += 32) M[r + (size_t)ldm * c] -= col[r] * gc;
         }
         __syncthreads();
         if (l != last) {
@@ -741,27 +894,38 @@ __device__ __forceinline__ int qp_solve(const QpView &s, const QpDims &P, double
           s.inact[s.act[l]] = 0;
           s.act[l] = s.act[last];
           s.lam[l] = s.lam[last];
-          int o = 0;  // rebuild the term offsets (drops are rare)
-          for (int w = 0; w < last; ++w) {
-            s.toff[w] = o;
-            o += (s.act[w] < OH) ? nj : 1;
+          if (CACHED) {
+            // member `last` moves to l, the candidate's slot follows the shrinking working set, l's slot becomes free
+            s.g[l] = s.g[last];
+            const int freed = s.zslot[l];
+            s.zslot[l] = s.zslot[last];
+            s.zslot[last] = s.zslot[q];
+            s.zslot[q] = freed;
+          } else {
+            int o = 0;  // rebuild the term offsets (drops are rare)
+            for (int w = 0; w < last; ++w) {
+              s.toff[w] = o;
+              o += (s.act[w] < OH) ? nj : 1;
+            }
+            s.toff[last] = o;
           }
-          s.toff[last] = o;
         }
         --q;
         __syncthreads();
+        if (!CACHED) {
 #pragma unroll 1
-        for (int w = tid; w < q; w += NT) {
-          const Desc d = decode(s.act[w], P, s.ocoef);
-          const int t0 = s.toff[w];
-          for (int k = 0; k < d.nterm; ++k) {
-            s.trow[t0 + k] = d.row0 + k;
-            s.tcoef[t0 + k] = d.cv ? d.cv[k] : d.coef;
-            s.towner[t0 + k] = w;
+          for (int w = tid; w < q; w += NT) {
+            const Desc d = decode(s.act[w], P, s.ocoef);
+            const int t0 = s.toff[w];
+            for (int k = 0; k < d.nterm; ++k) {
+              s.trow[t0 + k] = d.row0 + k;
+              s.tcoef[t0 + k] = d.cv ? d.cv[k] : d.coef;
+              s.towner[t0 + k] = w;
+            }
           }
+          __syncthreads();
         }
-        __syncthreads();
-        PF_ADD(4);
+        PF_ADD(QPF(4));
       }
     }
   }

@@ -77,7 +77,9 @@ def test_async_entry_matches_blocking_entry(ctx, oracle):
 
 
 def test_escalation_threshold_does_not_change_results(ctx, oracle):
-    """The heavy tier resumes escalated problems: forcing (nearly) every QP through it must give the same answers."""
+    """The heavy tier resumes escalated problems: forcing (nearly) every QP through it must give the same answers.
+    The two tiers recover the primal point by different (mathematically identical) routes -- cached directions and prefix
+    sums in the bulk tier, the Gram operator in the heavy tier -- so they agree to the parity tolerance, not bit for bit."""
     cfg = common.batch_m16ib(oracle, 64, horizon=30)
     s = _setup(ctx, cfg)
     a = ctx.solve_batch(cfg["x0"], cfg["ff"], cfg["caug"], cfg["xref"], s["epsilon_O"], s["MAX_O_ITER"])
@@ -86,7 +88,8 @@ def test_escalation_threshold_does_not_change_results(ctx, oracle):
     ctx.set_option("esc_steps", 48)
     assert (a["status"] == b["status"]).all() and (a["iters"] == b["iters"]).all()
     ok = (a["status"] & 0xFF) < 2
-    assert np.abs(a["x"][ok] - b["x"][ok]).max() < 1e-9 and np.abs(a["u"][ok] - b["u"][ok]).max() < 1e-9
+    dx, du = np.abs(a["x"][ok] - b["x"][ok]).max(), np.abs(a["u"][ok] - b["u"][ok]).max()
+    assert dx < 1e-6 and du < 1e-6, (dx, du)
 
 
 def test_error_paths(ctx, oracle):
