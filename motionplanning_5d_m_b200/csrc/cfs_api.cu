@@ -317,7 +317,7 @@ extern "C" int cfs_set_obstacles(cfs_ctx *ctx, const double *seg, const double *
     o.D2 = D2;
     o.D = D ? D[j] : 0.0;
     o.eps = eps ? eps[j] : 0.0;
-    o.pad_ = 0.0;
+    o.rD2 = D2 != 0.0 ? 1.0 / D2 : 0.0;
   }
   t.nobs = n_obs;
   ctx->nobs = n_obs;

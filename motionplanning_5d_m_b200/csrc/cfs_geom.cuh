@@ -115,6 +115,14 @@ __device__ __forceinline__ void link_endpoints(const Xf &M, const LinkTab &L, co
                       M.m[4 * a + 3]) + base[a];
 }
 
+// x / D2 for the obstacle constant D2 with its correctly rounded reciprocal r: q0 = RN(x r), rem = x - q0 D2 (exact, FMA),
+// q = RN(q0 + rem r) is the correctly rounded quotient (Markstein's theorem; x, D2 are far from over/underflow here)
+__device__ __forceinline__ double div_by_const(double x, double d, double r) {
+  const double q0 = x * r;
+  const double rem = fma(-q0, d, x);
+  return fma(rem, r, q0);
+}
+
 __device__ __forceinline__ double fixbound(double v) {  // distLinSeg.m:93-101
   return v < 0.0 ? 0.0 : (v > 1.0 ? 1.0 : v);
 }
@@ -123,7 +131,17 @@ __device__ __forceinline__ double fixbound(double v) {  // distLinSeg.m:93-101
 //   if |dis| < 1e-4: dis = -norm(P1 - link_end)       (dist_arm_3D_200i_2.m:22-24, dist_link_Heu.m:19-21)
 // The branch-deciding quantity den = D1*D2 - R^2 is formed with explicit round-to-nearest mul/sub (no FMA
 // contraction) so that the parallel-lines test (distLinSeg.m:55) sees the same value as MATLAB's arithmetic.
-__device__ __forceinline__ double link_obs_dist(const double p[6], const ObsTab &o, int &touched) {
+//
+// link_obs_key returns the signed square of that distance: key = |v|^2 for an ordinary link, -|w|^2 for a touching one.
+// sqrt is monotone and correctly rounded, so min over links of the distances == key_to_dist(min over links of the keys)
+// bit for bit, and one evaluation of dist_arm needs ONE square root instead of one per link (35 -> 11 per num_jac
+// waypoint).  CFS_TOUCH_KEY = 1e-08 (0x1.5798ee2308c3ap-27) is the smallest double whose square root is >= 1e-4, so
+// "key < CFS_TOUCH_KEY" is exactly the reference's "abs(dis) < 1e-4".  (Only difference: when two links' distances round
+// to the same double from different squares, the first-minimal-link rule may name the other link; the value is the same.)
+#define CFS_TOUCH_KEY 1e-08
+__device__ __forceinline__ double key_to_dist(double k) { return k >= 0.0 ? sqrt(k) : -sqrt(-k); }
+
+__device__ __forceinline__ double link_obs_key(const double p[6], const ObsTab &o, int &touched) {
   const double d1x = p[3] - p[0], d1y = p[4] - p[1], d1z = p[5] - p[2];
   const double d12x = o.s[0] - p[0], d12y = o.s[1] - p[1], d12z = o.s[2] - p[2];
   const double d2x = o.d2[0], d2y = o.d2[1], d2z = o.d2[2];
@@ -140,14 +158,14 @@ __device__ __forceinline__ double link_obs_dist(const double p[6], const ObsTab 
       t = fixbound(S1 / D1);
     } else if (D2 != 0.0) {
       t = 0.0;
-      u = fixbound(-S2 / D2);
+      u = fixbound(div_by_const(-S2, D2, o.rD2));
     } else {
       t = 0.0;
       u = 0.0;
     }
   } else if (den == 0.0) {
     t = 0.0;
-    u = -S2 / D2;
+    u = div_by_const(-S2, D2, o.rD2);
     const double uf = fixbound(u);
     if (uf != u) {
       t = fixbound((uf * R + S1) / D1);
@@ -155,7 +173,7 @@ __device__ __forceinline__ double link_obs_dist(const double p[6], const ObsTab 
     }
   } else {
     t = fixbound((S1 * D2 - S2 * R) / den);
-    u = (t * R - S2) / D2;
+    u = div_by_const(t * R - S2, D2, o.rD2);
     const double uf = fixbound(u);
     if (uf != u) {
       t = fixbound((uf * R + S1) / D1);
@@ -163,13 +181,17 @@ __device__ __forceinline__ double link_obs_dist(const double p[6], const ObsTab 
     }
   }
   const double vx = (d1x * t - d2x * u) - d12x, vy = (d1y * t - d2y * u) - d12y, vz = (d1z * t - d2z * u) - d12z;
-  double dis = sqrt((vx * vx + vy * vy) + vz * vz);
-  if (fabs(dis) < CFS_TOUCH_TOL) {
+  double key = (vx * vx + vy * vy) + vz * vz;
+  if (key < CFS_TOUCH_KEY) {
     const double wx = (p[0] + d1x * t) - p[3], wy = (p[1] + d1y * t) - p[4], wz = (p[2] + d1z * t) - p[5];
-    dis = -sqrt((wx * wx + wy * wy) + wz * wz);
+    key = -((wx * wx + wy * wy) + wz * wz);
     touched = 1;
   }
-  return dis;
+  return key;
+}
+
+__device__ __forceinline__ double link_obs_dist(const double p[6], const ObsTab &o, int &touched) {
+  return key_to_dist(link_obs_key(p, o, touched));
 }
 
 }  // namespace cfs

@@ -25,17 +25,18 @@ namespace cfs {
 //   scw[((2*kind + 0)*NJ + k)*H + i] = cos,  scw[((2*kind + 1)*NJ + k)*H + i] = sin
 template <int NJ, int NT>
 __device__ __forceinline__ void numjac_sincos(const DevTables &tab, const double *xs, int H, double *scw) {
-  const double hh = CFS_NUMJAC_EPS / 2;  // num_jac.m:11,13
 #pragma unroll 1
-  for (int e = threadIdx.x; e < 3 * H * NJ; e += NT) {
-    const int kind = e / (H * NJ), r = e - kind * (H * NJ);
-    const int i = r / NJ, k = r - i * NJ;
-    const double th = xs[i * 2 * NJ + k];
-    const double arg = (kind == 0 ? th : (kind == 1 ? th + hh : th - hh)) + tab.link[k].th_off;
+  for (int e = threadIdx.x; e < H * NJ; e += NT) {
+    const int i = e / NJ, k = e - i * NJ;
     double s, c;
-    sincos(arg, &s, &c);
-    scw[((2 * kind + 0) * NJ + k) * H + i] = c;
-    scw[((2 * kind + 1) * NJ + k) * H + i] = s;
+    sincos(xs[i * 2 * NJ + k] + tab.link[k].th_off, &s, &c);
+    const double cc = c * CFS_NUMJAC_COSH, ss = s * CFS_NUMJAC_COSH;  // angle addition, see cfs_types.cuh
+    scw[(0 * NJ + k) * H + i] = c;
+    scw[(1 * NJ + k) * H + i] = s;
+    scw[(2 * NJ + k) * H + i] = fma(-s, CFS_NUMJAC_SINH, cc);  // cos(theta + eps/2)   (num_jac.m:11)
+    scw[(3 * NJ + k) * H + i] = fma(c, CFS_NUMJAC_SINH, ss);   // sin(theta + eps/2)
+    scw[(4 * NJ + k) * H + i] = fma(s, CFS_NUMJAC_SINH, cc);   // cos(theta - eps/2)   (num_jac.m:13)
+    scw[(5 * NJ + k) * H + i] = fma(-c, CFS_NUMJAC_SINH, ss);  // sin(theta - eps/2)
   }
 }
 
@@ -150,9 +151,9 @@ __device__ __forceinline__ void numjac_items2(const DevTables &tab, const Numjac
 #pragma unroll 1
     for (int jj = 0; jj < 2; ++jj)
       if (j0 + jj < nobs) {
-        const double da = link_obs_dist(pA, tab.obs[j0 + jj], touched);
+        const double da = link_obs_key(pA, tab.obs[j0 + jj], touched);  // keys (signed squares), see cfs_geom.cuh
         int tb = 0;
-        const double db = link_obs_dist(pB, tab.obs[j0 + jj], tb);
+        const double db = link_obs_key(pB, tab.obs[j0 + jj], tb);
         if (hasB) touched |= tb;
         // strict <: the first minimal link wins (dist_arm_3D_Heu_2.m:25-28)
         if (jj == 0) {
@@ -179,12 +180,15 @@ __device__ __forceinline__ void numjac_items2(const DevTables &tab, const Numjac
           for (int e = 0; e < 12; ++e) dst[e] = M.m[e];
         }
       }
-      if (d.end == 1) {
-        dbase[j0 * H + i] = d0;
-        if (j0 + 1 < nobs) dbase[(j0 + 1) * H + i] = d1;
-      } else if (d.end == 2) {
-        w.fv[(((size_t)j0 * H + i) * NJ + d.col) * 2 + d.sign] = d0;
-        if (j0 + 1 < nobs) w.fv[(((size_t)(j0 + 1) * H + i) * NJ + d.col) * 2 + d.sign] = d1;
+      if (d.end) {  // one evaluation of dist_arm is complete: the only square roots of the chain
+        const double e0 = key_to_dist(d0), e1 = key_to_dist(d1);
+        if (d.end == 1) {
+          dbase[j0 * H + i] = e0;
+          if (j0 + 1 < nobs) dbase[(j0 + 1) * H + i] = e1;
+        } else {
+          w.fv[(((size_t)j0 * H + i) * NJ + d.col) * 2 + d.sign] = e0;
+          if (j0 + 1 < nobs) w.fv[(((size_t)(j0 + 1) * H + i) * NJ + d.col) * 2 + d.sign] = e1;
+        }
       }
     }
   }

@@ -19,16 +19,22 @@
 
 namespace cfs {
 
+#ifndef GRAD_MINB
+#define GRAD_MINB 4  // 4 x 128 threads per SM: <= 128 registers per thread
+#endif
 
 // ============================================================================================================
 // K1: num_jac
 // ============================================================================================================
 template <int NJ, int OC>
-__global__ void __launch_bounds__(GRAD_THREADS) k_grad_numjac(GradArgs a) {
+__global__ void __launch_bounds__(GRAD_THREADS, GRAD_MINB) k_grad_numjac(GradArgs a) {
   __shared__ alignas(128) DevTables tab;
   __shared__ alignas(8) uint64_t mbar;
-  // sin/cos cache: [6 kinds][NJ][thread]; kinds: c0,s0 (theta), cp,sp (theta+eps/2), cm,sm (theta-eps/2)
-  __shared__ double sc[6][NJ][GRAD_THREADS];
+  // dynamic shared memory: sin/cos cache [6 kinds][NJ][thread] (kinds: c0,s0 (theta), cp,sp (theta+eps/2), cm,sm
+  // (theta-eps/2)) followed by the running "all minus" kinematic prefix [12][thread] of every thread's waypoint
+  extern __shared__ __align__(16) double k1_dyn[];
+  double (*sc)[NJ][GRAD_THREADS] = reinterpret_cast<double (*)[NJ][GRAD_THREADS]>(k1_dyn);
+  double (*pmS)[GRAD_THREADS] = reinterpret_cast<double (*)[GRAD_THREADS]>(k1_dyn + 6 * NJ * GRAD_THREADS);
 
   const int count = a.count ? *a.count : a.nslots;
   const long long total = (long long)count * a.H;
@@ -53,7 +59,7 @@ __global__ void __launch_bounds__(GRAD_THREADS) k_grad_numjac(GradArgs a) {
       if (a.linkid) a.linkid[idx(j)] = lid;
     }
   } out{a, prob, i};
-  numjac_waypoint<NJ, OC, GRAD_THREADS>(tab, sc, tid, thp, a.nobs, touched, out);
+  numjac_waypoint<NJ, OC, GRAD_THREADS>(tab, sc, pmS, tid, thp, a.nobs, touched, out);
   if (touched && a.flags) atomicOr(&a.flags[prob], 0x100);
 }
 
@@ -62,10 +68,14 @@ static cudaError_t launch_numjac_nj(const GradArgs &a, cudaStream_t s) {
   const long long total = (long long)a.nslots * a.H;
   if (total <= 0) return cudaSuccess;
   const int grid = (int)((total + GRAD_THREADS - 1) / GRAD_THREADS);
-  if (a.nobs <= 1)
-    k_grad_numjac<NJ, 1><<<grid, GRAD_THREADS, 0, s>>>(a);
-  else
-    k_grad_numjac<NJ, 2><<<grid, GRAD_THREADS, 0, s>>>(a);
+  const size_t dyn = sizeof(double) * (6 * NJ + 12) * GRAD_THREADS;
+  if (a.nobs <= 1) {
+    if (dyn > 48 * 1024) cudaFuncSetAttribute(k_grad_numjac<NJ, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+    k_grad_numjac<NJ, 1><<<grid, GRAD_THREADS, dyn, s>>>(a);
+  } else {
+    if (dyn > 48 * 1024) cudaFuncSetAttribute(k_grad_numjac<NJ, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+    k_grad_numjac<NJ, 2><<<grid, GRAD_THREADS, dyn, s>>>(a);
+  }
   return cudaGetLastError();
 }
 
