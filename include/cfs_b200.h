@@ -112,6 +112,19 @@ int cfs_solve_start_goal(cfs_ctx *ctx, int B, int solver, int grad, const double
 int cfs_solve_start_goal_async(cfs_ctx *ctx, int B, int solver, int grad, const double *theta0, const double *thetag,
                                const double *noise, double eps_outer, int max_outer, double alpha, double *u, double *x,
                                double *cost_hist, double *e_u_hist, int *iters, int *status);
+/* RRT*-CFS glue (RRTstar_CFS.m:96-119), on the device: every route (nj x W waypoints, dt apart) is
+ * resampled to H+1 points with cubicpolytraj's default boundary conditions (zero velocity at every waypoint:
+ * q = q_k + (3s^2 - 2s^3)(q_{k+1} - q_k) on segment k), x0 = [sample_1; 0], xg = sample_{H+1}, x_ = [sample_i; 0] (i = 2..H+1),
+ * ff / caug as in cfs_solve_start_goal, then optimizer().  Needs cfs_set_cost_blocks.  (cubicpolytraj is Robotics System
+ * Toolbox code, not part of the reference tree: parity unpinned, see DESIGN.md.) */
+int cfs_solve_routes(cfs_ctx *ctx, int B, int W, int solver, int grad, const double *routes /*nj x W x B*/, const double *noise,
+                     double eps_outer, int max_outer, double alpha, double *u, double *x, double *cost_hist, double *e_u_hist,
+                     int *iters, int *status);
+int cfs_solve_routes_async(cfs_ctx *ctx, int B, int W, int solver, int grad, const double *routes, const double *noise,
+                           double eps_outer, int max_outer, double alpha, double *u, double *x, double *cost_hist,
+                           double *e_u_hist, int *iters, int *status);
+/* The resampling step alone: sampled (nj x (H+1) x B) = cubicpolytraj(route, (0:W-1)*dt, linspace(0,(W-1)*dt,H+1)). */
+int cfs_resample_routes(cfs_ctx *ctx, int B, int W, int H, const double *routes /*nj x W x B*/, double *sampled);
 /* Blocks until the context's stream is idle and collects the statistics of the batch in flight (if any). */
 int cfs_wait(cfs_ctx *ctx);
 /* Same, every pointer is a DEVICE pointer on ctx's device (inputs already resident in HBM); asynchronous on the

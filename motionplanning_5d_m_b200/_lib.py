@@ -19,7 +19,7 @@ FLAG_TOUCH = 0x100
 
 # every symbol include/cfs_b200.h declares (tests check that the library exports all of them)
 SYMBOLS = ["cfs_create", "cfs_destroy", "cfs_last_error", "cfs_version", "cfs_set_stream", "cfs_set_option", "cfs_set_robot", "cfs_set_obstacles",
-           "cfs_set_cost", "cfs_set_cost_blocks", "cfs_solve_start_goal", "cfs_solve_start_goal_async", "cfs_solve_batch", "cfs_solve_batch_async", "cfs_wait", "cfs_solve_batch_device", "cfs_dist_grad", "cfs_time_dist_grad", "cfs_get_con",
+           "cfs_set_cost", "cfs_set_cost_blocks", "cfs_solve_start_goal", "cfs_solve_start_goal_async", "cfs_solve_routes", "cfs_solve_routes_async", "cfs_resample_routes", "cfs_solve_batch", "cfs_solve_batch_async", "cfs_wait", "cfs_solve_batch_device", "cfs_dist_grad", "cfs_time_dist_grad", "cfs_get_con",
            "cfs_nodes_feasible", "cfs_nearest_steer", "cfs_get_stats", "cfs_set_timing", "cfs_get_iter_times", "cfs_get_problem_steps", "cfs_get_qp_profile", "cfs_measure_fp64_peak"]
 
 
@@ -155,6 +155,31 @@ class Context:
                                             _dp(out["x"]), _dp(out["cost_hist"]), _dp(out["e_u_hist"]), _dp(out["iters"]),
                                             _dp(out["status"]))
         self._check(rc, "cfs_solve_start_goal")
+        return out
+
+    def solve_routes(self, routes, eps_outer, max_outer, solver=SOLVER_CFS, grad=GRAD_NUMJAC, noise=None, alpha=0.0):
+        """routes (B, W, nj): RRT routes; resampling (cubicpolytraj, RRTstar_CFS.m:96-100) and the CFS stage set-up
+        (:106-163) run on the device, then optimizer()."""
+        r = _f64(routes)
+        B, W = r.shape[0], r.shape[1]
+        n, N, K = self.n, 2 * self.n, max(int(max_outer), 1)
+        out = dict(u=np.zeros((B, n)), x=np.zeros((B, N)), cost_hist=np.full((B, K), np.nan), e_u_hist=np.full((B, K), np.nan),
+                   iters=np.zeros(B, dtype=np.int32), status=np.zeros(B, dtype=np.int32))
+        nz = None if noise is None else _f64(noise)
+        rc = self._lib.cfs_solve_routes(self._h, C.c_int(B), C.c_int(W), C.c_int(solver), C.c_int(grad), _dp(r), _dp(nz),
+                                        C.c_double(eps_outer), C.c_int(max_outer), C.c_double(alpha), _dp(out["u"]),
+                                        _dp(out["x"]), _dp(out["cost_hist"]), _dp(out["e_u_hist"]), _dp(out["iters"]),
+                                        _dp(out["status"]))
+        self._check(rc, "cfs_solve_routes")
+        return out
+
+    def resample_routes(self, routes, H):
+        """routes (B, W, nj) -> (B, H+1, nj): cubicpolytraj(route, (0:W-1)*dt, linspace(0,(W-1)*dt,H+1)) on the device."""
+        r = _f64(routes)
+        B, W = r.shape[0], r.shape[1]
+        out = np.zeros((B, H + 1, self.nj))
+        self._check(self._lib.cfs_resample_routes(self._h, C.c_int(B), C.c_int(W), C.c_int(H), _dp(r), _dp(out)),
+                    "cfs_resample_routes")
         return out
 
     def solve_start_goal_ptr(self, B, theta0, thetag, eps_outer, max_outer, u, x, cost_hist, e_u_hist, iters, status,

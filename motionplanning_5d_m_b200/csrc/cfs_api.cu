@@ -57,7 +57,7 @@ struct cfs_ctx {
   DevBuf th0, thg;
   // batch buffers
   DevBuf x0, ff, caug, xref, noise, u, x, cost, eu, u0, v0, cost0, dist, grad, lid, iters, status, flags, listA, listB,
-      counters, slab, scratch_theta, scratch_out, qpsteps, fupper, probsteps, psg_w, psg_cost, psg_skip;
+      counters, slab, scratch_theta, scratch_out, qpsteps, fupper, probsteps, psg_w, psg_cost, psg_skip, routes;
   int slab_grid = 0, slab_ld = 0;
   // timing
   std::vector<cudaEvent_t> ev;
@@ -229,7 +229,7 @@ extern "C" void cfs_destroy(cfs_ctx *ctx) {
   DevBuf *bufs[] = {&ctx->x0, &ctx->ff, &ctx->caug, &ctx->xref, &ctx->noise, &ctx->u, &ctx->x, &ctx->cost, &ctx->eu,
                     &ctx->u0, &ctx->v0, &ctx->cost0, &ctx->dist, &ctx->grad, &ctx->lid, &ctx->iters, &ctx->status,
                     &ctx->flags, &ctx->listA, &ctx->listB, &ctx->counters, &ctx->slab, &ctx->scratch_theta,
-                    &ctx->scratch_out, &ctx->qpsteps, &ctx->fupper, &ctx->probsteps, &ctx->psg_w, &ctx->psg_cost,
+                    &ctx->scratch_out, &ctx->qpsteps, &ctx->fupper, &ctx->probsteps, &ctx->routes, &ctx->psg_w, &ctx->psg_cost,
                     &ctx->psg_skip, &ctx->th0, &ctx->thg};
   for (DevBuf *b : bufs) free_buf(*b);
   if (ctx->dQblk) cudaFree(ctx->dQblk);
@@ -712,7 +712,7 @@ extern "C" int cfs_wait(cfs_ctx *ctx) {
 static int solve_host_async(cfs_ctx *ctx, int B, int solver, int grad, const double *x0, const double *ff, const double *caug,
                             const double *xref, const double *theta0, const double *thetag, const double *noise,
                             double eps_outer, int max_outer, double alpha, double *u, double *x, double *cost_hist,
-                            double *e_u_hist, int *iters, int *status) {
+                            double *e_u_hist, int *iters, int *status, const double *routes = nullptr, int W = 0) {
   int rc;
   CU(cudaSetDevice(ctx->device));
   if (ctx->pending.active && (rc = finish_pending(ctx))) return rc;  // one batch in flight per context
@@ -732,7 +732,12 @@ static int solve_host_async(cfs_ctx *ctx, int B, int solver, int grad, const dou
   for (cudaEvent_t &e : ctx->ev_h)
     if (!e) CU(cudaEventCreate(&e));
   CU(cudaEventRecord(ctx->ev_h[0], st));
-  if (theta0) {
+  if (routes) {
+    if ((rc = ensure(ctx, ctx->th0, sizeof(double) * nj * B))) return rc;
+    if ((rc = ensure(ctx, ctx->thg, sizeof(double) * nj * B))) return rc;
+    if ((rc = ensure(ctx, ctx->routes, sizeof(double) * (size_t)nj * W * B))) return rc;
+    CU(cudaMemcpyAsync(ctx->routes.p, routes, sizeof(double) * (size_t)nj * W * B, cudaMemcpyHostToDevice, st));
+  } else if (theta0) {
     if ((rc = ensure(ctx, ctx->th0, sizeof(double) * nj * B))) return rc;
     if ((rc = ensure(ctx, ctx->thg, sizeof(double) * nj * B))) return rc;
     CU(cudaMemcpyAsync(ctx->th0.p, theta0, sizeof(double) * nj * B, cudaMemcpyHostToDevice, st));
@@ -745,10 +750,17 @@ static int solve_host_async(cfs_ctx *ctx, int B, int solver, int grad, const dou
   }
   if (noise) CU(cudaMemcpyAsync(ctx->noise.p, noise, sizeof(double) * (size_t)n * K * B, cudaMemcpyHostToDevice, st));
   CU(cudaEventRecord(ctx->ev_h[1], st));
-  if (theta0)
+  if (routes) {  // N1: cubicpolytraj resampling, then the same problem set-up around that reference
+    CU(launch_resample_routes(B, W, ctx->H, nj, ctx->htab.dt, ptr<double>(ctx->routes), ptr<double>(ctx->th0),
+                              ptr<double>(ctx->thg), ptr<double>(ctx->xref), st));
+    CU(launch_build_problems(B, ctx->H, nj, ctx->htab.dt, ctx->dQblk, ctx->stage_w, ctx->term_w, ptr<double>(ctx->th0),
+                             ptr<double>(ctx->thg), ptr<double>(ctx->x0), nullptr, ptr<double>(ctx->ff),
+                             ptr<double>(ctx->caug), st));
+  } else if (theta0) {
     CU(launch_build_problems(B, ctx->H, nj, ctx->htab.dt, ctx->dQblk, ctx->stage_w, ctx->term_w, ptr<double>(ctx->th0),
                              ptr<double>(ctx->thg), ptr<double>(ctx->x0), ptr<double>(ctx->xref), ptr<double>(ctx->ff),
                              ptr<double>(ctx->caug), st));
+  }
   rc = solve_device(ctx, B, solver, grad, ptr<double>(ctx->x0), ptr<double>(ctx->ff), ptr<double>(ctx->caug),
                     ptr<double>(ctx->xref), noise ? ptr<double>(ctx->noise) : nullptr, eps_outer, max_outer, alpha,
                     ptr<double>(ctx->u), ptr<double>(ctx->x), ptr<double>(ctx->cost), ptr<double>(ctx->eu),
@@ -797,6 +809,58 @@ extern "C" int cfs_solve_start_goal_async(cfs_ctx *ctx, int B, int solver, int g
   if (B == 0) return 0;
   return solve_host_async(ctx, B, solver, grad, nullptr, nullptr, nullptr, nullptr, theta0, thetag, noise, eps_outer, max_outer,
                           alpha, u, x, cost_hist, e_u_hist, iters, status);
+}
+
+extern "C" int cfs_solve_routes_async(cfs_ctx *ctx, int B, int W, int solver, int grad, const double *routes, const double *noise,
+                                      double eps_outer, int max_outer, double alpha, double *u, double *x, double *cost_hist,
+                                      double *e_u_hist, int *iters, int *status) {
+  if (!ctx) return CFS_E_ARG;
+  int rc = check_ready(ctx, true);
+  if (rc) return rc;
+  if (!ctx->have_blocks) return fail(ctx, CFS_E_STATE, "cfs_solve_routes: the cost must be set with cfs_set_cost_blocks");
+  if (B < 0 || W < 2 || max_outer < 0 || (solver != CFS_SOLVER_CFS && solver != CFS_SOLVER_PSGCFS) ||
+      (grad != CFS_GRAD_NUMJAC && grad != CFS_GRAD_DERIVEST))
+    return fail(ctx, CFS_E_ARG, "cfs_solve_routes: bad argument");
+  if (B > 0 && (!routes || !u || !cost_hist || !iters || !status)) return fail(ctx, CFS_E_ARG, "cfs_solve_routes: NULL buffer");
+  if (B == 0) return 0;
+  return solve_host_async(ctx, B, solver, grad, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, noise, eps_outer, max_outer,
+                          alpha, u, x, cost_hist, e_u_hist, iters, status, routes, W);
+}
+
+extern "C" int cfs_solve_routes(cfs_ctx *ctx, int B, int W, int solver, int grad, const double *routes, const double *noise,
+                                double eps_outer, int max_outer, double alpha, double *u, double *x, double *cost_hist,
+                                double *e_u_hist, int *iters, int *status) {
+  int rc = cfs_solve_routes_async(ctx, B, W, solver, grad, routes, noise, eps_outer, max_outer, alpha, u, x, cost_hist, e_u_hist,
+                                  iters, status);
+  if (rc || B == 0) return rc;
+  return cfs_wait(ctx);
+}
+
+extern "C" int cfs_resample_routes(cfs_ctx *ctx, int B, int W, int H, const double *routes, double *sampled) {
+  if (!ctx) return CFS_E_ARG;
+  int rc = check_ready(ctx, false);
+  if (rc) return rc;
+  if (B < 0 || W < 2 || H < 1 || (B > 0 && (!routes || !sampled))) return fail(ctx, CFS_E_ARG, "cfs_resample_routes: bad argument");
+  if (B == 0) return 0;
+  CU(cudaSetDevice(ctx->device));
+  const int nj = ctx->nj;
+  cudaStream_t st = ctx->stream;
+  if ((rc = ensure(ctx, ctx->routes, sizeof(double) * (size_t)nj * W * B))) return rc;
+  if ((rc = ensure(ctx, ctx->th0, sizeof(double) * nj * B))) return rc;
+  if ((rc = ensure(ctx, ctx->thg, sizeof(double) * nj * B))) return rc;
+  if ((rc = ensure(ctx, ctx->scratch_out, sizeof(double) * (size_t)2 * nj * H * B))) return rc;
+  CU(cudaMemcpyAsync(ctx->routes.p, routes, sizeof(double) * (size_t)nj * W * B, cudaMemcpyHostToDevice, st));
+  CU(launch_resample_routes(B, W, H, nj, ctx->htab.dt, ptr<double>(ctx->routes), ptr<double>(ctx->th0), ptr<double>(ctx->thg),
+                            ptr<double>(ctx->scratch_out), st));
+  // sampled (nj x (H+1) x B): column 0 = theta0, columns 1..H = the theta rows of x_
+  CU(cudaMemcpy2DAsync(sampled, sizeof(double) * nj * (H + 1), ctx->th0.p, sizeof(double) * nj, sizeof(double) * nj, B,
+                       cudaMemcpyDeviceToHost, st));
+  for (int i = 0; i < H; ++i)
+    CU(cudaMemcpy2DAsync(sampled + (size_t)nj * (i + 1), sizeof(double) * nj * (H + 1),
+                         ptr<double>(ctx->scratch_out) + (size_t)2 * nj * i, sizeof(double) * 2 * nj * H, sizeof(double) * nj, B,
+                         cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  return 0;
 }
 
 extern "C" int cfs_solve_start_goal(cfs_ctx *ctx, int B, int solver, int grad, const double *theta0, const double *thetag,

@@ -52,6 +52,12 @@ cudaError_t launch_build_problems(int B, int H, int nj, double dt, const double 
                                   const double *theta0 /*nj x B*/, const double *thetag /*nj x B*/, double *x0 /*2nj x B*/,
                                   double *xref /*2njH x B*/, double *ff /*n x B*/, double *caug /*B*/, cudaStream_t s);
 
+// RRT route (nj x W waypoints dt apart) -> H+1 samples of cubicpolytraj with zero waypoint velocities (RRTstar_CFS.m:96-100):
+// theta0 / thetag = first / last sample, xref = [sample_i; 0], i = 1..H.  launch_build_problems with xref == nullptr then
+// adds x0, ff, caug without touching that reference.
+cudaError_t launch_resample_routes(int B, int W, int H, int nj, double dt, const double *routes /*nj x W x B*/, double *theta0,
+                                   double *thetag, double *xref, cudaStream_t s);
+
 // C = alpha * op(A) * B  (column-major, A is M x K with lda (or K x M if transA), B is K x N, C is M x N)
 cudaError_t launch_dgemm(int M, int N, int K, double alpha, const double *A, int lda, bool transA, const double *B,
                          int ldb, double *C, int ldc, cudaStream_t s);

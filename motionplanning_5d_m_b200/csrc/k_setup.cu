@@ -166,7 +166,8 @@ cudaError_t launch_build_qq(int H, int nj, double dt, const double *Q, const dou
 // one CTA per problem; q_i = w_i Q e_i with e_i = [theta0 - thetag ; 0] (x0 has zero velocity, so Aaug x0 = x0 at every step)
 __global__ void __launch_bounds__(128) k_build_problems(int B, int H, int nj, double dt, const double *Q, double stage_w,
                                                         double term_w, const double *theta0, const double *thetag, double *x0,
-                                                        double *xref, double *ff, double *caug) {
+                                                        double *xref /*nullptr: keep the caller's reference*/, double *ff,
+                                                        double *caug) {
   __shared__ double e[CFS_MAXL], qe_t[CFS_MAXL], qe_w[CFS_MAXL];
   const int b = blockIdx.x, tid = threadIdx.x;
   const int n = H * nj, ns = 2 * nj;
@@ -180,7 +181,7 @@ __global__ void __launch_bounds__(128) k_build_problems(int B, int H, int nj, do
   __syncthreads();
   if (tid < ns) x0[(size_t)b * ns + tid] = tid < nj ? theta0[(size_t)b * nj + tid] : 0.0;
   // x_ : MATLAB linspace(theta0, thetag, H+1) without its first column, zero velocity rows (main_FANUC.m:38-49)
-  for (int idx = tid; idx < H * ns; idx += blockDim.x) {
+  for (int idx = tid; xref && idx < H * ns; idx += blockDim.x) {
     const int i = idx / ns, k = idx % ns;
     double v = 0.0;
     if (k < nj) {
@@ -211,6 +212,43 @@ cudaError_t launch_build_problems(int B, int H, int nj, double dt, const double 
                                   double *caug, cudaStream_t s) {
   if (B <= 0) return cudaSuccess;
   k_build_problems<<<B, 128, 0, s>>>(B, H, nj, dt, Q, stage_w, term_w, theta0, thetag, x0, xref, ff, caug);
+  return cudaGetLastError();
+}
+
+// RRT route -> CFS reference (RRTstar_CFS.m:96-100):
+//   wpTimes = (0:W-1)*dt; trajTimes = linspace(0, wpTimes(end), H+1); sampled = cubicpolytraj(route, wpTimes, trajTimes)
+// with the toolbox defaults (zero velocity at every waypoint): on segment k, q = q_k + (3 s^2 - 2 s^3)(q_{k+1} - q_k),
+// s = (t - t_k)/(t_{k+1} - t_k).  One CTA per route; outputs theta0 = sampled(:,1), thetag = sampled(:,H+1) and
+// x_ = [sampled(:,i); 0] for i = 2..H+1 (RRTstar_CFS.m:106-119).
+__global__ void __launch_bounds__(128) k_resample_routes(int B, int W, int H, int nj, double dt, const double *routes /*nj x W x B*/,
+                                                         double *theta0, double *thetag, double *xref) {
+  const int b = blockIdx.x, ns = 2 * nj;
+  const double *wp = routes + (size_t)b * nj * W;
+  const double t_end = (W - 1) * dt;
+  for (int idx = threadIdx.x; idx < (H + 1) * nj; idx += blockDim.x) {
+    const int i = idx / nj, k = idx - i * nj;
+    // MATLAB linspace: d1 + (0:n1)*(d2-d1)/n1 with the last point set to d2 exactly
+    const double t = (i == H) ? t_end : (i * t_end) / H;
+    int seg = 0;  // last waypoint time <= t, clipped to a valid segment
+    while (seg < W - 2 && (seg + 1) * dt <= t) ++seg;
+    const double t0 = seg * dt, t1 = (seg + 1) * dt;
+    const double sn = (t - t0) / (t1 - t0);
+    const double blend = 3.0 * sn * sn - 2.0 * sn * sn * sn;
+    const double q0 = wp[k + nj * seg], q1 = wp[k + nj * (seg + 1)];
+    const double q = q0 + blend * (q1 - q0);
+    if (i == 0) theta0[(size_t)b * nj + k] = q;
+    if (i == H) thetag[(size_t)b * nj + k] = q;
+    if (i > 0) {
+      xref[(size_t)b * H * ns + (size_t)(i - 1) * ns + k] = q;
+      xref[(size_t)b * H * ns + (size_t)(i - 1) * ns + nj + k] = 0.0;
+    }
+  }
+}
+
+cudaError_t launch_resample_routes(int B, int W, int H, int nj, double dt, const double *routes, double *theta0, double *thetag,
+                                   double *xref, cudaStream_t s) {
+  if (B <= 0) return cudaSuccess;
+  k_resample_routes<<<B, 128, 0, s>>>(B, W, H, nj, dt, routes, theta0, thetag, xref);
   return cudaGetLastError();
 }
 

@@ -163,3 +163,45 @@ def test_device_side_setup_matches_host_builder(ctx, oracle):
     with pytest.raises(M.CfsError, match="cfs_set_cost_blocks"):
         ctx.set_cost(s["H"], s["QQ"], s["lim"], s["MAX_input"])
         ctx.solve_start_goal(cfg["theta0"], cfg["thetag"], s["epsilon_O"], s["MAX_O_ITER"])
+
+
+def test_device_route_resampling_and_solve_routes(ctx, oracle):
+    """cubicpolytraj resampling (RRTstar_CFS.m:96-100) + the CFS stage set-up on the device, against the host
+    restatement problem.cubicpolytraj, the golden rrtstar_cfs case (shipped route data/200i_xori.mat) and the oracle on
+    perturbed routes."""
+    from motionplanning_5d_m_b200 import problem
+    from tests.test_oracle import check_against_golden
+    inp = common.golden("inputs.npz")
+    route = np.asarray(inp["route_wp"], dtype=np.float64)            # (5, 16)
+    ROBOT, robot, obs, s = common.rrtstar_route_config(route)
+    r = dict(robot)
+    r["name"] = ROBOT
+    ctx.set_robot(r, 5)
+    ctx.set_obstacles(obs)
+    H = s["H"]
+    rng = np.random.default_rng(11)
+    routes = np.stack([route.T] + [route.T + 0.02 * rng.standard_normal(route.T.shape) * np.linspace(0, 1, 16)[:, None] *
+                                   np.linspace(1, 0, 16)[:, None] * 4 for _ in range(7)])    # (8, W, 5), same end points
+    # resampling alone (also with a horizon that does not divide the route, and W = 2)
+    for Hs, rt in ((H, routes), (23, routes[:3]), (7, routes[:2, :2])):
+        got = ctx.resample_routes(rt, Hs)
+        W = rt.shape[1]
+        for b in range(rt.shape[0]):
+            ref = problem.cubicpolytraj(rt[b].T, np.arange(W) * 0.5, np.linspace(0, (W - 1) * 0.5, Hs + 1))
+            assert np.abs(got[b].T - ref).max() < 1e-12
+    assert np.array_equal(ctx.resample_routes(routes, H)[:, 0], routes[:, 0]) and \
+        np.array_equal(ctx.resample_routes(routes, H)[:, -1], routes[:, -1])
+    # solve: device glue against the golden case and against the oracle on host-built arrays
+    ctx.set_cost_blocks(H, problem.Q_RRTSTAR, problem.R_MAIN_FANUC, 10.0, s["lim"], s["MAX_input"])
+    out = ctx.solve_routes(routes, s["epsilon_O"], s["MAX_O_ITER"])
+    check_against_golden("rrtstar_cfs", {k: v[:1] for k, v in out.items()}, common.golden("cases.npz"))
+    for b in range(routes.shape[0]):
+        _, _, _, sb = common.rrtstar_route_config(routes[b].T)
+        P = common.oracle_problem(oracle, ROBOT, obs, sb)
+        orc = P.solve_batch(sb["xR"][:, 0][None], sb["ff"][None], np.array([sb["caug"]]), sb["x_"][None])
+        assert int(out["status"][b]) == int(orc["status"][0]) and int(out["iters"][b]) == int(orc["iters"][0])
+        if (int(orc["status"][0]) & 0xFF) < 2:
+            assert np.abs(out["x"][b] - orc["x"][0]).max() < 1e-6
+            it = int(orc["iters"][0])
+            assert np.all(np.abs(out["cost_hist"][b, :it] - orc["cost_hist"][0, :it]) <= 1e-6 * np.abs(orc["cost_hist"][0, :it]))
+    assert ctx.solve_routes(routes[:0], s["epsilon_O"], s["MAX_O_ITER"])["u"].shape == (0, H * 5)
