@@ -43,7 +43,7 @@ FUSED_DRAM_BYTES_PER_LAUNCH = 44.82e6 + 13.84e6  # ncu capture of one 4096 x H=5
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--steps", type=int, default=64)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=4096)
@@ -148,7 +148,10 @@ def run_reference(args, rank):
     cores = cpu_count()
     cfg = oracle_batch(args, O)
     P = make_oracle_problem(O, cfg, 1 if args.grad == "derivest" else 0)
-    S = args.batch if args.grad == "numjac" else min(args.batch, 256)  # bounded sample per step
+    # bounded sample per step: the first S problems of the seeded batch, sized so that K steps take about a minute on
+    # 16 host cores (the port solves ~1.2 k num_jac / ~0.6 k DERIVEST trajectories per second)
+    budget = 65536 if args.grad == "numjac" else 16384
+    S = min(args.batch, max(64, budget // max(args.steps, 1)))
     run = lambda: P.solve_batch(cfg["x0"][:S], cfg["ff"][:S], cfg["caug"][:S], cfg["xref"][:S], nthreads=cores)
     for _ in range(min(args.warmup, 1)):
         run()
@@ -337,7 +340,7 @@ def main():
     # stand-alone distance/gradient kernel on the same number of waypoints as the first outer iteration of the batch
     th_all = cfgs[0]["xref"].reshape(B, H, 2 * nj)[:, :, :nj].reshape(-1, nj)
     if args.grad == "derivest":
-        th_all = th_all[: 64 * H]
+        th_all = th_all[: 1024 * H]  # 51 200 waypoints x 5 joints = 2000 CTAs: fills the GPU, 3 ms per launch
     k1_ms = ctx0.time_dist_grad(th_all, grad=grad_mode, reps=10)
     k1_tf = f_wp * th_all.shape[0] / (k1_ms * 1e-3) / 1e12
     # ---- e2e from start/goal pairs: the mains' problem set-up (main_FANUC.m:38-103) done on the device ---------------------
