@@ -333,7 +333,7 @@ def main():
     ctx0.set_timing(1)
     iters = d_out[0]["iters"].cpu().numpy()
     status = d_out[0]["status"].cpu().numpy()
-    fused = st["launches"] <= 4
+    fused = st["launches"] <= 6
     fp64_tf, fp64_mhz = ctx0.measure_fp64_peak()
     f_wp = F_WAYPOINT_DERIVEST if args.grad == "derivest" else F_WAYPOINT_NUMJAC
     grad_flops = f_wp * st["grad_waypoints"]

@@ -74,6 +74,7 @@ struct cfs_ctx {
   int heavy_grid = 0;     // cfs_set_option("heavy_grid"): cap of the heavy tier's grid (0 = one CTA per SM)
   int bulk_grid = 0;      // cfs_set_option("bulk_grid"): cap of the bulk tier's grid (0 = every resident slot)
   int heavy_prio = 1;     // cfs_set_option("heavy_prio"): heavy tier on the highest-priority stream
+  int lpt = 1;            // cfs_set_option("lpt"): fused solver pulls the problems longest-expected-first
   bool fused_last = false;
   std::vector<double> it_grad_ms, it_qp_ms;
   cfs_stats stats;
@@ -531,6 +532,11 @@ static int solve_device(cfs_ctx *ctx, int B, int solver, int grad, const double 
     a.esc_count = cnt + 5;
     a.work_counter2 = cnt + 4;
     a.esc_steps = ctx->esc_steps;
+    if (ctx->lpt && O > 0 && B > 1) {  // listB / flags are free in the fused path: work order + its scratch
+      CU(launch_work_order(ctx->dtab, nj, O, B, H, xref, a.margin_is_D, ptr<int>(ctx->flags), ptr<int>(ctx->listB), st));
+      launches += 2;
+      a.order = ptr<int>(ctx->listB);
+    }
     if (detail) CU(cudaEventRecord(ctx->ev[0], st));
     CU(launch_fused(a, grid, 0, st)); ++launches;        // bulk tier: every problem
     if (detail) CU(cudaEventRecord(ctx->ev[1], st));
@@ -1088,6 +1094,7 @@ extern "C" int cfs_set_option(cfs_ctx *ctx, const char *name, int value) {
   if (strcmp(name, "heavy_grid") == 0) { ctx->heavy_grid = value; return 0; }
   if (strcmp(name, "bulk_grid") == 0) { ctx->bulk_grid = value; return 0; }
   if (strcmp(name, "heavy_prio") == 0) { ctx->heavy_prio = value; return 0; }
+  if (strcmp(name, "lpt") == 0) { ctx->lpt = value; return 0; }
   return fail(ctx, CFS_E_ARG, "cfs_set_option: unknown option '%s'", name);
 }
 

@@ -34,6 +34,11 @@ cudaError_t launch_nodes_feasible(const DevTables *tab, int nj, int nobs, int N,
 cudaError_t launch_nearest_steer(int nj, int n_nodes, const double *nodes, int S, const double *samples,
                                  const double *ratial, double step, int *parent, double *newnode, cudaStream_t s);
 
+// work order of the fused solver (longest expected problems first): order[] = problems by descending number of reference
+// waypoints inside an obstacle margin; count[] is scratch (B ints each)
+cudaError_t launch_work_order(const DevTables *tab, int nj, int nobs, int B, int H, const double *xref, int margin_is_D,
+                              int *count, int *order, cudaStream_t s);
+
 // ---- set-up: shared Gram operator G = P QQ^{-1} P' ----------------------------------------------------------
 // P = [B_theta; B_omega; I] (3n x n): the primitives every constraint row of CFS_FANUC.get_con is built from.
 // hessian_is_identity: PSGCFS projection (PSGCFS_FANUC.m:117) -> G = P P'.
@@ -100,6 +105,7 @@ struct SolveArgs {
   double *cost_old, *cost_new;  // B     EVAL.cost_old / cost_new (EVAL.m:29, PSGCFS_FANUC.m:66,76,90)
   int *skip;                  // B       stop_inner() was already true: no PSG step this outer iteration (PSGCFS_FANUC.m:88,136-142)
   // fused kernel tiers (k_fused.cu)
+  const int *order;           // bulk tier: problem of work-queue slot k (nullptr: slot k = problem k)
   int tier;                   // 0 bulk (all B problems), 1 heavy (the escalation list)
   int *esc_list, *esc_count;  // problems the bulk tier handed over (working set outgrew shared memory / step cap)
   int *work_counter2;         // work queue of the heavy tier

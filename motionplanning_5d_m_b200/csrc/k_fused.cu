@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(NT, MINB) k_cfs_fused(SolveArgs a) {
     __syncthreads();
     const int slot = s.ctl[0];
     if (slot >= count) break;
-    const int b = heavy ? a.esc_list[slot] : slot;
+    const int b = heavy ? a.esc_list[slot] : (a.order ? a.order[slot] : slot);
     const double *x0 = a.x0 + (size_t)b * 2 * nj;
     const double *v0 = a.v0 + (size_t)b * np;
 

@@ -297,6 +297,74 @@ __global__ void __launch_bounds__(GRAD_THREADS) k_nodes_feasible(const DevTables
   if (dmin) dmin[t] = dm;
 }
 
+// ---- work order of the fused solver: longest expected problems first ------------------------------------------------------
+// A problem whose reference line passes inside an obstacle margin needs several CFS iterations (or a long infeasibility
+// certificate); one that stays clear converges in two.  count[b] = number of (waypoint, obstacle) pairs of x_ with
+// distance < margin; k_order_desc then lists the problems by descending count (counting sort, one CTA), and the persistent
+// CTAs of k_cfs_fused pull them in that order: the long problems start first instead of wherever the batch put them.
+// The order only changes WHEN a problem is solved, never its result (every problem is solved independently).
+__global__ void __launch_bounds__(GRAD_THREADS) k_difficulty(const DevTables *gtab, int nj, int nobs, int B, int H,
+                                                            const double *xref, int margin_is_D, int *count) {
+  __shared__ alignas(128) DevTables tab;
+  __shared__ alignas(8) uint64_t mbar;
+  tma_stage(&tab, gtab, tab_bytes(nobs), &mbar);
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)B * H) return;
+  const int b = (int)(t / H);
+  const double *th = xref + t * 2 * nj;
+  Xf M;
+  double p[6];
+  int touched = 0, viol = 0;
+  double dm[CFS_MAX_OBS];
+  for (int j = 0; j < nobs; ++j) dm[j] = INFINITY;
+  for (int l = 0; l < nj; ++l) {
+    double sn, cs;
+    sincos(th[l] + tab.link[l].th_off, &sn, &cs);
+    if (l == 0)
+      xf_first(tab.link[0], cs, sn, M);
+    else
+      xf_step_inplace(M, tab.link[l], cs, sn);
+    link_endpoints(M, tab.link[l], tab.base, p);
+    for (int j = 0; j < nobs; ++j) {
+      const double k = link_obs_key(p, tab.obs[j], touched);
+      dm[j] = k < dm[j] ? k : dm[j];
+    }
+  }
+  for (int j = 0; j < nobs; ++j) viol += key_to_dist(dm[j]) < (margin_is_D ? tab.obs[j].D : tab.obs[j].eps) ? 1 : 0;
+  if (viol) atomicAdd(&count[b], viol);
+}
+
+__global__ void __launch_bounds__(1024) k_order_desc(int B, int max_count, const int *count, int *order) {
+  extern __shared__ int hist[];  // max_count + 2
+  for (int e = threadIdx.x; e <= max_count + 1; e += blockDim.x) hist[e] = 0;
+  __syncthreads();
+  for (int b = threadIdx.x; b < B; b += blockDim.x) atomicAdd(&hist[min(count[b], max_count)], 1);
+  __syncthreads();
+  if (threadIdx.x == 0) {  // start offset of every bucket, largest count first
+    int o = 0;
+    for (int c = max_count; c >= 0; --c) {
+      const int h = hist[c];
+      hist[c] = o;
+      o += h;
+    }
+  }
+  __syncthreads();
+  for (int b = threadIdx.x; b < B; b += blockDim.x) order[atomicAdd(&hist[min(count[b], max_count)], 1)] = b;
+}
+
+cudaError_t launch_work_order(const DevTables *tab, int nj, int nobs, int B, int H, const double *xref, int margin_is_D,
+                              int *count, int *order, cudaStream_t s) {
+  if (B <= 0) return cudaSuccess;
+  cudaError_t e = cudaMemsetAsync(count, 0, sizeof(int) * B, s);
+  if (e != cudaSuccess) return e;
+  const long long total = (long long)B * H;
+  k_difficulty<<<(int)((total + GRAD_THREADS - 1) / GRAD_THREADS), GRAD_THREADS, 0, s>>>(tab, nj, nobs, B, H, xref, margin_is_D,
+                                                                                       count);
+  const int max_count = H * nobs;
+  k_order_desc<<<1, 1024, sizeof(int) * (max_count + 2), s>>>(B, max_count, count, order);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_nodes_feasible(const DevTables *tab, int nj, int nobs, int N, const double *theta,
                                   unsigned char *feasible, double *dmin, cudaStream_t s) {
   if (N <= 0) return cudaSuccess;

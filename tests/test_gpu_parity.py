@@ -154,7 +154,7 @@ def test_batch_m16ib_solve_parity(ctx, oracle, fused):
     ctx.set_option("fused", 1)
     assert ((ref["status"] & 0xFF) == 2).any() and ((ref["status"] & 0xFF) == 0).any()
     _compare_solve(out, ref)
-    assert ctx.stats()["launches"] == (4 if fused else 44)
+    assert ctx.stats()["launches"] == (6 if fused else 44)
 
 
 def test_psgcfs_main_fanuc_parity(ctx, oracle):
