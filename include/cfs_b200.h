@@ -157,6 +157,19 @@ int cfs_nodes_feasible(cfs_ctx *ctx, int N, const double *theta /*nj x N*/, unsi
  * parent[s] = argmin_i ||(nodes(:,i)-sample(:,s)).*ratial|| (first minimum, 0-based), newnode = parent + (sample-parent)*step/||parent-sample||. */
 int cfs_nearest_steer(cfs_ctx *ctx, int n_nodes, const double *nodes /*nj x n_nodes*/, int S, const double *samples /*nj x S*/,
                       const double *ratial /*nj*/, double step, int *parent /*S*/, double *newnode /*nj x S*/);
+/* RRT_FANUC.find_route (Lib/RRT_FANUC.m:63-207: getNode / getRandNode / feasible / addNode / arrangeNode / goal_reached) for
+ * S independent seeds at once -- the parfor over num_seed workers of Lib/functions/s_Parallel_rrt.m:16-25 -- one CTA per seed,
+ * trees in shared memory.  star != 0: 'RRT*' (re-parenting), else 'RRT'.  MATLAB's rand stream is an
+ * input: rnd (nrnd x S) is consumed per seed in the reference's order (pp = rand; rand(nstate,1) when pp < bi).
+ *   x0 / goal / goal_th: nj x S (sys_info.x0, goalxyz, sys_info.goal_th); region_g, region_s, sample_off, ratial: nj; bi = 0.5,
+ *   max_iter = 400 in the reference (RRT_FANUC.m:37-38).  Obstacles and their D come from cfs_set_obstacles.
+ *   routes: nj x (max_iter+2) x S, the first route_len[s] columns are self.route; route_len = size(route,2) = routeL
+ *   (-1: rnd exhausted); n_nodes = node_num; fail = self.fail; rnd_used = numbers consumed.  tree_* (nj x (max_iter+2) x S,
+ *   (max_iter+2) x S; all three or none) receive all_nodes(2:end,:), all_nodes(1,:) and total_dis; ms_kernel may be NULL. */
+int cfs_rrt_find_routes(cfs_ctx *ctx, int S, int star, const double *x0, const double *goal, const double *goal_th,
+                        const double *region_g, const double *region_s, const double *sample_off, const double *ratial,
+                        double bi, int max_iter, const double *rnd, int nrnd, double *routes, int *route_len, int *n_nodes,
+                        int *fail, int *rnd_used, double *tree_nodes, int *tree_parent, double *tree_total, double *ms_kernel);
 
 /* ---- introspection (profiling / bench) ---------------------------------------------------------------- */
 typedef struct {

@@ -20,7 +20,7 @@ FLAG_TOUCH = 0x100
 # every symbol include/cfs_b200.h declares (tests check that the library exports all of them)
 SYMBOLS = ["cfs_create", "cfs_destroy", "cfs_last_error", "cfs_version", "cfs_set_stream", "cfs_set_option", "cfs_set_robot", "cfs_set_obstacles",
            "cfs_set_cost", "cfs_set_cost_blocks", "cfs_solve_start_goal", "cfs_solve_start_goal_async", "cfs_solve_routes", "cfs_solve_routes_async", "cfs_resample_routes", "cfs_solve_batch", "cfs_solve_batch_async", "cfs_wait", "cfs_solve_batch_device", "cfs_dist_grad", "cfs_time_dist_grad", "cfs_get_con",
-           "cfs_nodes_feasible", "cfs_nearest_steer", "cfs_get_stats", "cfs_set_timing", "cfs_get_iter_times", "cfs_get_problem_steps", "cfs_get_qp_profile", "cfs_measure_fp64_peak"]
+           "cfs_nodes_feasible", "cfs_nearest_steer", "cfs_rrt_find_routes", "cfs_get_stats", "cfs_set_timing", "cfs_get_iter_times", "cfs_get_problem_steps", "cfs_get_qp_profile", "cfs_measure_fp64_peak"]
 
 
 class CfsError(RuntimeError):
@@ -284,6 +284,29 @@ class Context:
                                          _dp(_f64(ratial)), C.c_double(step), _dp(parent), _dp(new))
         self._check(rc, "cfs_nearest_steer")
         return parent, new
+
+    def rrt_find_routes(self, x0, goal, goal_th, region_g, region_s, sample_off, ratial, rnd, bi=0.5, max_iter=400, star=True,
+                        want_tree=False):
+        """RRT_FANUC.find_route for S seeds: x0, goal, goal_th (S,nj); rnd (S,nrnd) uniform numbers consumed in MATLAB's
+        order.  Returns dict(routes [list of (len,nj)], route_len, n_nodes, fail, rnd_used, ms [, nodes, parent, total_dis])."""
+        x0, goal, goal_th, rnd = _f64(x0), _f64(goal), _f64(goal_th), _f64(rnd)
+        S, nj, cap = x0.shape[0], self.nj, max_iter + 2
+        routes = np.zeros((S, cap, nj))
+        ln, nn, fl, ru = (np.zeros(S, dtype=np.int32) for _ in range(4))
+        tn = np.zeros((S, cap, nj)) if want_tree else None
+        tp = np.zeros((S, cap), dtype=np.int32) if want_tree else None
+        tt = np.zeros((S, cap)) if want_tree else None
+        ms = C.c_double(0.0)
+        rc = self._lib.cfs_rrt_find_routes(self._h, C.c_int(S), C.c_int(1 if star else 0), _dp(x0), _dp(goal), _dp(goal_th),
+                                           _dp(_f64(region_g)), _dp(_f64(region_s)), _dp(_f64(sample_off)), _dp(_f64(ratial)),
+                                           C.c_double(bi), C.c_int(max_iter), _dp(rnd), C.c_int(rnd.shape[1]), _dp(routes),
+                                           _dp(ln), _dp(nn), _dp(fl), _dp(ru), _dp(tn), _dp(tp), _dp(tt), C.byref(ms))
+        self._check(rc, "cfs_rrt_find_routes")
+        out = dict(routes=[routes[s, :max(ln[s], 0)].copy() for s in range(S)], route_len=ln, n_nodes=nn, fail=fl.astype(bool),
+                   rnd_used=ru, ms=ms.value)
+        if want_tree:
+            out.update(nodes=tn, parent=tp, total_dis=tt)
+        return out
 
     def stats(self):
         s = Stats()

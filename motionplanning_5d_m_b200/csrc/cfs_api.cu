@@ -1046,6 +1046,71 @@ extern "C" int cfs_nearest_steer(cfs_ctx *ctx, int n_nodes, const double *nodes,
   return 0;
 }
 
+extern "C" int cfs_rrt_find_routes(cfs_ctx *ctx, int S, int star, const double *x0, const double *goal, const double *goal_th,
+                                   const double *region_g, const double *region_s, const double *sample_off,
+                                   const double *ratial, double bi, int max_iter, const double *rnd, int nrnd, double *routes,
+                                   int *route_len, int *n_nodes, int *fail_out, int *rnd_used, double *tree_nodes,
+                                   int *tree_parent, double *tree_total, double *ms_kernel) {
+  if (!ctx) return CFS_E_ARG;
+  int rc = check_ready(ctx, false);
+  if (rc) return rc;
+  if (S < 0 || max_iter < 1 || nrnd < 1 ||
+      (S > 0 && (!x0 || !goal || !goal_th || !region_g || !region_s || !sample_off || !ratial || !rnd || !routes || !route_len ||
+                 !n_nodes || !fail_out || !rnd_used)))
+    return fail(ctx, CFS_E_ARG, "cfs_rrt_find_routes: bad argument");
+  if (S == 0) return 0;
+  CU(cudaSetDevice(ctx->device));
+  const int nj = ctx->nj, cap = max_iter + 2;
+  cudaStream_t st = ctx->stream;
+  const size_t n_in = (size_t)3 * nj * S + 4 * (size_t)nj + (size_t)nrnd * S;
+  if ((rc = ensure(ctx, ctx->routes, sizeof(double) * n_in))) return rc;
+  const bool tree = tree_nodes && tree_parent && tree_total;
+  const size_t out_d = (size_t)nj * cap * S + (tree ? (size_t)nj * cap * S + (size_t)cap * S : 0);
+  const size_t out_i = (size_t)4 * S + (tree ? (size_t)cap * S : 0);
+  if ((rc = ensure(ctx, ctx->scratch_out, sizeof(double) * out_d + sizeof(int) * out_i + 64))) return rc;
+  double *d_in = ptr<double>(ctx->routes);
+  double *d_x0 = d_in, *d_goal = d_x0 + (size_t)nj * S, *d_gth = d_goal + (size_t)nj * S, *d_rg = d_gth + (size_t)nj * S;
+  double *d_rs = d_rg + nj, *d_off = d_rs + nj, *d_rat = d_off + nj, *d_rnd = d_rat + nj;
+  double *d_routes = ptr<double>(ctx->scratch_out);
+  double *d_tn = tree ? d_routes + (size_t)nj * cap * S : nullptr, *d_tt = tree ? d_tn + (size_t)nj * cap * S : nullptr;
+  int *d_int = reinterpret_cast<int *>(d_routes + out_d);
+  int *d_len = d_int, *d_nn = d_len + S, *d_fail = d_nn + S, *d_used = d_fail + S, *d_tp = tree ? d_used + S : nullptr;
+  CU(cudaMemcpyAsync(d_x0, x0, sizeof(double) * nj * S, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(d_goal, goal, sizeof(double) * nj * S, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(d_gth, goal_th, sizeof(double) * nj * S, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(d_rg, region_g, sizeof(double) * nj, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(d_rs, region_s, sizeof(double) * nj, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(d_off, sample_off, sizeof(double) * nj, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(d_rat, ratial, sizeof(double) * nj, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(d_rnd, rnd, sizeof(double) * (size_t)nrnd * S, cudaMemcpyHostToDevice, st));
+  RrtArgs a;
+  memset(&a, 0, sizeof(a));
+  a.tab = ctx->dtab; a.nj = nj; a.nobs = ctx->nobs; a.star = star; a.max_iter = max_iter; a.nrnd = nrnd; a.bi = bi;
+  a.x0 = d_x0; a.goal = d_goal; a.goal_th = d_gth; a.region_g = d_rg; a.region_s = d_rs; a.sample_off = d_off; a.ratial = d_rat;
+  a.rnd = d_rnd; a.routes = d_routes; a.route_len = d_len; a.n_nodes = d_nn; a.fail = d_fail; a.rnd_used = d_used;
+  a.tree_nodes = d_tn; a.tree_total = d_tt; a.tree_parent = d_tp;
+  CU(cudaEventRecord(ctx->ev_a, st));
+  CU(launch_rrt_find_routes(a, S, st));
+  CU(cudaEventRecord(ctx->ev_b, st));
+  CU(cudaMemcpyAsync(routes, d_routes, sizeof(double) * (size_t)nj * cap * S, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(route_len, d_len, sizeof(int) * S, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(n_nodes, d_nn, sizeof(int) * S, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(fail_out, d_fail, sizeof(int) * S, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(rnd_used, d_used, sizeof(int) * S, cudaMemcpyDeviceToHost, st));
+  if (tree) {
+    CU(cudaMemcpyAsync(tree_nodes, d_tn, sizeof(double) * (size_t)nj * cap * S, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(tree_total, d_tt, sizeof(double) * (size_t)cap * S, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(tree_parent, d_tp, sizeof(int) * (size_t)cap * S, cudaMemcpyDeviceToHost, st));
+  }
+  CU(cudaStreamSynchronize(st));
+  if (ms_kernel) {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ctx->ev_a, ctx->ev_b);
+    *ms_kernel = ms;
+  }
+  return 0;
+}
+
 extern "C" int cfs_get_stats(const cfs_ctx *ctx, cfs_stats *out) {
   if (!ctx || !out) return CFS_E_ARG;
   *out = ctx->stats;

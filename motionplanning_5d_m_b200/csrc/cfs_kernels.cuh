@@ -39,6 +39,21 @@ cudaError_t launch_nearest_steer(int nj, int n_nodes, const double *nodes, int S
 cudaError_t launch_work_order(const DevTables *tab, int nj, int nobs, int B, int H, const double *xref, int margin_is_D,
                               int *count, int *order, cudaStream_t s);
 
+// ---- batched RRT / RRT* tree growth, one CTA per seed (k_rrt.cu) -------------------------------------------------------------
+struct RrtArgs {
+  const DevTables *tab;
+  int nj, nobs, star, max_iter, nrnd;
+  double bi;
+  const double *x0, *goal, *goal_th;                          // nj x S
+  const double *region_g, *region_s, *sample_off, *ratial;    // nj
+  const double *rnd;                                          // nrnd x S uniform numbers, consumed in MATLAB's order
+  double *routes;                                             // nj x (max_iter+2) x S
+  int *route_len, *n_nodes, *fail, *rnd_used;                 // S   (route_len = -1: random stream exhausted)
+  double *tree_nodes, *tree_total;                            // optional: nj x (max_iter+2) x S, (max_iter+2) x S
+  int *tree_parent;                                           // optional: (max_iter+2) x S
+};
+cudaError_t launch_rrt_find_routes(const RrtArgs &a, int S, cudaStream_t s);
+
 // ---- set-up: shared Gram operator G = P QQ^{-1} P' ----------------------------------------------------------
 // P = [B_theta; B_omega; I] (3n x n): the primitives every constraint row of CFS_FANUC.get_con is built from.
 // hessian_is_identity: PSGCFS projection (PSGCFS_FANUC.m:117) -> G = P P'.

@@ -224,3 +224,28 @@ def rrt_nearest(nodes, sample, ratial):
     lib().orc_rrt_nearest.restype = C.c_int
     p = lib().orc_rrt_nearest(C.c_int(nj), C.c_int(nn), _p(nodes), _p(_f64(sample)), _p(_f64(ratial)), _p(d))
     return p, d
+
+
+def rrt_find_route(r, obs_list, D, x0, goal, region_g, region_s, sample_off, goal_th, ratial, rnd, bi=0.5, max_iter=400,
+                   star=True):
+    """RRT_FANUC.find_route (Lib/RRT_FANUC.m:63-207) with the uniform random stream `rnd` consumed in MATLAB's order.
+    Returns dict(route (len, nj), n_nodes, fail, rnd_used, nodes, parent, total_dis) or None if rnd ran out."""
+    o = _f64(np.concatenate([obs6(o) for o in obs_list]))
+    nj = r.nj
+    cap = max_iter + 2
+    nodes = np.zeros((cap, nj))
+    parent = np.zeros(cap, dtype=np.int32)
+    tot = np.zeros(cap)
+    route = np.zeros((cap, nj))
+    nn, fl, ru = C.c_int(0), C.c_int(0), C.c_int(0)
+    rnd = _f64(rnd)
+    f = lib().orc_rrt_find_route
+    f.restype = C.c_int
+    ln = f(C.byref(r), C.c_int(len(obs_list)), _p(o), _p(_f64(D)), _p(_f64(x0)), _p(_f64(goal)), _p(_f64(region_g)),
+           _p(_f64(region_s)), _p(_f64(sample_off)), _p(_f64(goal_th)), _p(_f64(ratial)), C.c_double(bi), C.c_int(max_iter),
+           C.c_int(1 if star else 0), _p(rnd), C.c_int(rnd.size), C.c_int(cap), _p(nodes), _p(parent), _p(tot), _p(route),
+           C.byref(nn), C.byref(fl), C.byref(ru))
+    if ln < 0:
+        return None
+    return dict(route=route[:ln].copy(), n_nodes=nn.value, fail=bool(fl.value), rnd_used=ru.value, nodes=nodes[:nn.value].copy(),
+                parent=parent[:nn.value].copy(), total_dis=tot[:nn.value].copy())

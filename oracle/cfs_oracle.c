@@ -1056,3 +1056,86 @@ int orc_rrt_nearest(int nj, int nnodes, const double *nodes, const double *sampl
   }
   return parent;
 }
+
+/* ------------------------------------------------------------------------------------------
+ * RRT_FANUC.find_route (Lib/RRT_FANUC.m:63-93) with getNode/getRandNode (:97-131), arrangeNode (:134-142),
+ * addNode (:184-190) and goal_reached (:193-207).  MATLAB's rand stream is an INPUT: rnd[] is consumed in the
+ * reference's order -- pp = rand (:108), then rand(nstate,1) if pp < bi (:111).
+ *   star = 1: 'RRT*' (arrangeNode after every addNode), 0: 'RRT'
+ *   nodes (nj x cap), parent (1-based column index, -1 for the root), total_dis: the tree; cap >= max_iter + 1
+ *   route (nj x cap): the root-to-last-node path (:86-91); returns its length (size(route,2) = routeL of
+ *   s_Parallel_rrt.m:21); *fail: node_num > MAX_ITER (:201-205); *rnd_used: numbers consumed.
+ * Returns -1 when the random stream is exhausted before the search ends.
+ * ---------------------------------------------------------------------------------------- */
+int orc_rrt_find_route(const orc_robot *r, int nobs, const double *obs, const double *D, const double *x0,
+                       const double *goal, const double *region_g, const double *region_s, const double *sample_off,
+                       const double *goal_th, const double *ratial, double bi, int max_iter, int star,
+                       const double *rnd, int nrnd, int cap, double *nodes, int *parent, double *total_dis,
+                       double *route, int *n_nodes, int *fail, int *rnd_used) {
+  const int nj = r->nj;
+  double *to_dis = (double *)malloc(sizeof(double) * (size_t)cap);
+  double newn[ORC_MAXL], sample[ORC_MAXL];
+  int node_num = 1, cur = 0, par = 0 /* [] in MATLAB: the loop below never ran */, reached = 0, touched = 0;
+  *fail = 0;
+  for (int k = 0; k < nj; ++k) nodes[k] = newn[k] = x0[k];
+  parent[0] = -1;
+  total_dis[0] = 0.0;
+  for (;;) {
+    /* goal_reached (:193-207): both comparisons must hold for every joint */
+    int in = 1;
+    for (int k = 0; k < nj; ++k)
+      if (!((goal[k] - region_g[k]) < newn[k] && newn[k] < (goal[k] + region_g[k]))) in = 0;
+    reached = in;
+    if (node_num > max_iter) {
+      *fail = 1;
+      reached = 1;
+    }
+    if (reached) break;
+    /* getNode (:97-104) */
+    for (;;) {
+      if (cur >= nrnd) { free(to_dis); return -1; }
+      const double pp = rnd[cur++];
+      if (pp < bi) {
+        if (cur + nj > nrnd) { free(to_dis); return -1; }
+        for (int k = 0; k < nj; ++k) sample[k] = (rnd[cur + k] - 0.5) * region_s[k] * 2 + sample_off[k];
+        cur += nj;
+      } else {
+        for (int k = 0; k < nj; ++k) sample[k] = goal_th[k];
+      }
+      par = 1 + orc_rrt_nearest(nj, node_num, nodes, sample, ratial, to_dis);
+      const double *pn = nodes + (size_t)(par - 1) * nj;
+      double ss = 0.0;
+      for (int k = 0; k < nj; ++k) ss += (pn[k] - sample[k]) * (pn[k] - sample[k]);
+      const double nrm = sqrt(ss);
+      for (int k = 0; k < nj; ++k) newn[k] = pn[k] + (sample[k] - pn[k]) * 0.1 / nrm; /* :129 */
+      if (orc_rrt_feasible(r, newn, nobs, obs, D, NULL, &touched)) break;
+    }
+    /* addNode (:184-190) */
+    for (int k = 0; k < nj; ++k) nodes[(size_t)node_num * nj + k] = newn[k];
+    parent[node_num] = par;
+    total_dis[node_num] = total_dis[par - 1] + to_dis[par - 1];
+    ++node_num;
+    /* arrangeNode (:134-142): nodes closer than 0.2 to the SAMPLE are re-parented to the new node when that is shorter */
+    if (star)
+      for (int i = 0; i < node_num - 1; ++i)
+        if (to_dis[i] < 0.2 && total_dis[i] > (total_dis[node_num - 1] + to_dis[i])) {
+          parent[i] = node_num;
+          total_dis[i] = total_dis[node_num - 1] + to_dis[i];
+        }
+  }
+  free(to_dis);
+  /* route (:86-91) */
+  int len = 1, p = par, guard = 0;
+  while (p > 0 && guard++ <= node_num) { ++len; p = parent[p - 1]; }
+  int pos = len - 1;
+  for (int k = 0; k < nj; ++k) route[(size_t)pos * nj + k] = newn[k];
+  p = par; guard = 0;
+  while (p > 0 && guard++ <= node_num) {
+    --pos;
+    for (int k = 0; k < nj; ++k) route[(size_t)pos * nj + k] = nodes[(size_t)(p - 1) * nj + k];
+    p = parent[p - 1];
+  }
+  *n_nodes = node_num;
+  *rnd_used = cur;
+  return len;
+}

@@ -127,6 +127,13 @@ int  orc_rrt_feasible(const orc_robot *r, const double *theta, int nobs, const d
 int  orc_rrt_nearest(int nj, int nnodes, const double *nodes /* nj x nnodes */, const double *sample,
                      const double *ratial, double *dists /* nnodes or NULL */);
 
+/* RRT_FANUC.find_route (RRT_FANUC.m:63-207) driven by a caller-supplied uniform random stream; see cfs_oracle.c */
+int  orc_rrt_find_route(const orc_robot *r, int nobs, const double *obs, const double *D, const double *x0,
+                        const double *goal, const double *region_g, const double *region_s, const double *sample_off,
+                        const double *goal_th, const double *ratial, double bi, int max_iter, int star,
+                        const double *rnd, int nrnd, int cap, double *nodes, int *parent, double *total_dis,
+                        double *route, int *n_nodes, int *fail, int *rnd_used);
+
 #ifdef __cplusplus
 }
 #endif

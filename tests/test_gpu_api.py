@@ -205,3 +205,82 @@ def test_device_route_resampling_and_solve_routes(ctx, oracle):
             it = int(orc["iters"][0])
             assert np.all(np.abs(out["cost_hist"][b, :it] - orc["cost_hist"][0, :it]) <= 1e-6 * np.abs(orc["cost_hist"][0, :it]))
     assert ctx.solve_routes(routes[:0], s["epsilon_O"], s["MAX_O_ITER"])["u"].shape == (0, H * 5)
+
+
+def test_batched_rrt_tree_growth_matches_the_restatement(ctx, oracle):
+    """RRT_FANUC.find_route for many seeds at once (one CTA per seed) against the C restatement fed with the same
+    uniform random streams: RRTstar_CFS.m's scene (M200i, two obstacles, :29-55), RRT* and RRT, plus a seed whose stream runs dry."""
+    O = oracle
+    ROBOT, robot, obs, s = common.rrtstar_cfs_config(np.zeros((5, 41)))
+    r = dict(robot)
+    r["name"] = ROBOT
+    ctx.set_robot(r, 5)
+    ctx.set_obstacles(obs)
+    x0 = np.array([0.421, 0, -0.0092, -0.0010, -1.5786])                       # RRTstar_CFS.m:30
+    goal = np.array([-1.4090, 0.8873, 0.4008, 0.0, 0.4430])                    # :33
+    region_g = np.array([np.pi / 20, np.pi / 20, np.pi / 10, np.pi / 2, np.pi / 2])
+    region_s = np.array([np.pi / 2, np.pi / 2, np.pi / 2, np.pi / 1.5, np.pi / 1.5])
+    ratial, off = np.array([1, 1, 0.5, 0.1, 0.1]), np.zeros(5)
+    S, R = 48, 12000
+    rnd = np.random.default_rng(2026).random((S, R))
+    rnd[S - 1, 40:] = 0.99      # this seed only ever samples the goal after 40 numbers: it stalls against the obstacle ...
+    X0, G = np.tile(x0, (S, 1)), np.tile(goal, (S, 1))
+    X0[1] = goal                 # ... and this one starts inside the goal box: route = x0, no sample drawn
+    rob = O.robot(ROBOT)
+    for star in (True, False):
+        out = ctx.rrt_find_routes(X0, G, G, region_g, region_s, off, ratial, rnd, star=star, want_tree=True)
+        assert out["route_len"][1] == 1 and out["rnd_used"][1] == 0 and np.array_equal(out["routes"][1][0], goal)
+        n_ok = 0
+        for k in range(S):
+            ref = O.rrt_find_route(rob, [o["l"] for o in obs], [o["D"] for o in obs], X0[k], G[k], region_g, region_s, off, G[k],
+                                   ratial, rnd[k], star=star)
+            if ref is None:
+                assert out["route_len"][k] == -1
+                continue
+            n_ok += 1
+            assert out["route_len"][k] == len(ref["route"]) and out["n_nodes"][k] == ref["n_nodes"]
+            assert bool(out["fail"][k]) == ref["fail"] and out["rnd_used"][k] == ref["rnd_used"]
+            nn = ref["n_nodes"]
+            assert np.array_equal(out["parent"][k, :nn], ref["parent"])
+            assert np.abs(out["nodes"][k, :nn] - ref["nodes"]).max() < 1e-13
+            assert np.abs(out["total_dis"][k, :nn] - ref["total_dis"]).max() < 1e-12
+            assert np.abs(out["routes"][k] - ref["route"]).max() < 1e-13
+        assert n_ok >= S - 2
+        found = ~out["fail"] & (out["route_len"] > 0)
+        assert found.any() and out["fail"].any()
+        # s_Parallel_rrt.m:27: [~, id] = min(routeL) over the seeds that found a path
+        rl = np.where(found, out["route_len"], 1000)
+        assert rl.min() == min(len(rt) for rt, f in zip(out["routes"], found) if f)
+
+
+def test_rrt_to_cfs_pipeline_on_the_device(ctx, oracle):
+    """RRTstar_CFS.m end to end (s_Parallel_rrt -> min(routeL) -> cubicpolytraj -> CFS_FANUC.optimizer) with every stage on
+    the GPU, checked stage by stage against the CPU restatements."""
+    from motionplanning_5d_m_b200 import problem
+    O = oracle
+    ROBOT, robot, obs, s = common.rrtstar_cfs_config(np.zeros((5, 41)))
+    r = dict(robot)
+    r["name"] = ROBOT
+    ctx.set_robot(r, 5)
+    ctx.set_obstacles(obs)
+    x0 = np.array([0.421, 0, -0.0092, -0.0010, -1.5786])
+    goal = np.array([-1.4090, 0.8873, 0.4008, 0.0, 0.4430])
+    region_g = np.array([np.pi / 20, np.pi / 20, np.pi / 10, np.pi / 2, np.pi / 2])
+    region_s = np.array([np.pi / 2, np.pi / 2, np.pi / 2, np.pi / 1.5, np.pi / 1.5])
+    S = 32
+    rnd = np.random.default_rng(77).random((S, 12000))
+    out = ctx.rrt_find_routes(np.tile(x0, (S, 1)), np.tile(goal, (S, 1)), np.tile(goal, (S, 1)), region_g, region_s, np.zeros(5),
+                              np.array([1, 1, 0.5, 0.1, 0.1]), rnd, star=False)       # s_Parallel_rrt.m:16 uses 'RRT'
+    rl = np.where(out["fail"] | (out["route_len"] < 0), 1000, out["route_len"])       # s_Parallel_rrt.m:14,21
+    best = int(np.argmin(rl))                                                          # :27
+    assert rl[best] < 1000
+    route = out["routes"][best]                                                        # (W, 5)
+    H = s["H"]
+    ctx.set_cost_blocks(H, problem.Q_RRTSTAR, problem.R_MAIN_FANUC, 10.0, s["lim"], s["MAX_input"])
+    sol = ctx.solve_routes(route[None], s["epsilon_O"], s["MAX_O_ITER"])
+    _, _, _, sb = common.rrtstar_route_config(route.T)
+    P = common.oracle_problem(O, ROBOT, obs, sb)
+    orc = P.solve_batch(sb["xR"][:, 0][None], sb["ff"][None], np.array([sb["caug"]]), sb["x_"][None])
+    assert int(sol["status"][0]) == int(orc["status"][0]) and int(sol["iters"][0]) == int(orc["iters"][0])
+    if (int(orc["status"][0]) & 0xFF) < 2:
+        assert np.abs(sol["x"][0] - orc["x"][0]).max() < 1e-6
