@@ -218,3 +218,43 @@ def test_cubicpolytraj_restatement():
     eps = 1e-6  # zero velocity at interior waypoints
     qa = problem.cubicpolytraj(wp, t, np.array([0.5 - eps, 0.5 + eps]))
     assert np.abs(qa[:, 1] - qa[:, 0]).max() < 1e-10
+
+
+def test_rrt_find_route_restatement_properties(oracle):
+    """orc_rrt_find_route (RRT_FANUC.m:63-207): structural properties of the tree the reference grows -- every edge is a 0.1 rad
+    step from its (original) parent towards a sample (:129), every node passes RRT_FANUC.feasible (:146-181), the route walks
+    the parents from the root to the last node (:86-91), the goal box holds unless the search failed (:193-207), RRT and RRT*
+    grow the same nodes, and RRT* never lengthens a path to a node (:134-142)."""
+    O = oracle
+    ROBOT, robot, obs, s = common.rrtstar_cfs_config(np.zeros((5, 41)))
+    r = O.robot(ROBOT)
+    x0 = np.array([0.421, 0, -0.0092, -0.0010, -1.5786])
+    goal = np.array([-1.4090, 0.8873, 0.4008, 0.0, 0.4430])
+    region_g = np.array([np.pi / 20, np.pi / 20, np.pi / 10, np.pi / 2, np.pi / 2])
+    region_s = np.array([np.pi / 2, np.pi / 2, np.pi / 2, np.pi / 1.5, np.pi / 1.5])
+    ratial, off = np.array([1, 1, 0.5, 0.1, 0.1]), np.zeros(5)
+    seg, D = [o["l"] for o in obs], [o["D"] for o in obs]
+    found = 0
+    for seed in range(8):
+        rnd = np.random.default_rng(seed).random(12000)
+        a = O.rrt_find_route(r, seg, D, x0, goal, region_g, region_s, off, goal, ratial, rnd, star=False)
+        b = O.rrt_find_route(r, seg, D, x0, goal, region_g, region_s, off, goal, ratial, rnd, star=True)
+        assert a is not None and b is not None
+        assert np.array_equal(a["nodes"], b["nodes"]) and a["rnd_used"] == b["rnd_used"] and a["fail"] == b["fail"]
+        assert (b["total_dis"] <= a["total_dis"] + 1e-12).all()
+        n = a["n_nodes"]
+        assert a["parent"][0] == -1 and ((a["parent"][1:] >= 1) & (a["parent"][1:] <= np.arange(1, n))).all()
+        step = np.linalg.norm(a["nodes"][1:] - a["nodes"][a["parent"][1:] - 1], axis=1)
+        assert np.abs(step - 0.1).max() < 1e-12
+        assert all(O.rrt_feasible(r, th, seg, D)[0] for th in a["nodes"][1:])
+        assert np.array_equal(a["route"][0], x0) and np.array_equal(a["route"][-1], a["nodes"][-1])
+        if not a["fail"]:
+            found += 1
+            last = a["route"][-1]
+            assert ((goal - region_g < last) & (last < goal + region_g)).all() and n <= 400
+        else:
+            assert n == 401
+    assert found >= 3
+    assert O.rrt_find_route(r, seg, D, x0, goal, region_g, region_s, off, goal, ratial, np.full(10, 0.3)) is None   # stream too short
+    one = O.rrt_find_route(r, seg, D, goal, goal, region_g, region_s, off, goal, ratial, np.zeros(1))              # starts in the goal box
+    assert len(one["route"]) == 1 and one["rnd_used"] == 0 and not one["fail"]
