@@ -94,171 +94,247 @@ cudaError_t launch_grad_numjac(const GradArgs &a, cudaStream_t s) {
 // K1d: DERIVEST gradients of dist_link(linkid)
 //   one thread per (problem, waypoint, obstacle, joint s)
 // ============================================================================================================
+#ifndef K1D_MINB
+#define K1D_MINB 3
+#endif
+// "e precedes c" in MATLAB's ascending sort of der_romb (derivest.m:442): smaller value first, NaNs last, stable
+__device__ __forceinline__ bool dv_precedes(double ve, int e, double vc, int c) {
+  const bool lt = ve < vc || (isnan(vc) && !isnan(ve));
+  const bool eq = (ve == vc) || (isnan(vc) && isnan(ve));
+  return lt || (eq && e < c);
+}
+
+// K1d, two phases inside one CTA of 128 (waypoint, obstacle) pairs:
+//   phase 1  one thread per pair: sin/cos of the joints, base evaluation (distance, linkid: M16iB/main_CFS.m:229), and the
+//            CTA-wide list of work items (pair, joint s) with s < linkid -- dist_link(linkid) does not depend on joints
+//            >= linkid, so every f_del of those joints is exactly 0 and derivest returns 0 (45 % of the reference line's
+//            waypoints have linkid 1: a thread-per-joint mapping leaves half of the lanes idle);
+//   phase 2  one thread per work item, dense lanes: the 26 x 2 evaluations f(x0 +- h*delta_k) (derivest.m:366-371) with both
+//            signs side by side (two independent dependency chains), then der_init / rombextrap / trimmed selection.
+// Register diet (234 -> 168 registers, 2 -> 3 CTAs/SM): the 23 derivative estimates, the 19 Romberg extrapolants and their
+// error estimates live in shared-memory columns of the thread (der_init overwrites f_del in place, der_romb overwrites
+// der_init in place), and the trimmed-sort selection finds the two smallest / two largest extrapolants by four argmin passes
+// instead of ranking all 19.  Every evaluated value and every operation order is unchanged.
 template <int NJ>
-__global__ void __launch_bounds__(GRAD_THREADS) k_grad_derivest(GradArgs a) {
+__global__ void __launch_bounds__(GRAD_THREADS, K1D_MINB) k_grad_derivest(GradArgs a, int pairs_per_cta) {
   __shared__ alignas(128) DevTables tab;
   __shared__ alignas(128) DerivestTab dv;
   __shared__ alignas(8) uint64_t mbar;
-  __shared__ double fdel_s[DV_NDEL][GRAD_THREADS];
+  __shared__ int lid_s[GRAD_THREADS], off_s[GRAD_THREADS + 1], wsum[GRAD_THREADS / 32];
+  __shared__ long long o_s[GRAD_THREADS];
+  __shared__ unsigned short items[GRAD_THREADS * NJ];
+  extern __shared__ __align__(16) double k1d_dyn[];
+  double (*fdel_s)[GRAD_THREADS] = reinterpret_cast<double (*)[GRAD_THREADS]>(k1d_dyn);  // f_del -> der_init -> der_romb
+  double (*err_s)[GRAD_THREADS] = fdel_s + DV_NDEL;                                      // errest of every extrapolant
+  double (*cs_s)[GRAD_THREADS] = err_s + DV_NEST;                                        // cos (rows 0..NJ-1), sin (NJ..2NJ-1)
+  double (*th_s)[GRAD_THREADS] = cs_s + 2 * NJ;                                          // joint angles of the pair
 
   const int count = a.count ? *a.count : a.nslots;
-  const long long total = (long long)count * a.H * a.nobs * NJ;
-  if ((long long)blockIdx.x * blockDim.x >= total) return;
+  const long long total = (long long)count * a.H * a.nobs;  // pairs
+  if ((long long)blockIdx.x * pairs_per_cta >= total) return;
   tma_stage(&tab, a.tab, tab_bytes(a.nobs), &mbar);
   for (int w = threadIdx.x; w < (int)(sizeof(DerivestTab) / sizeof(double)); w += blockDim.x)
     reinterpret_cast<double *>(&dv)[w] = reinterpret_cast<const double *>(a.dv)[w];
   __syncthreads();
-  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= total) return;
   const int tid = threadIdx.x;
-  const int s = (int)(t % NJ);
-  long long rest = t / NJ;
-  const int j = (int)(rest % a.nobs);
-  rest /= a.nobs;
-  const int i = (int)(rest % a.H);
-  const int slot = (int)(rest / a.H);
-  const int prob = a.list ? a.list[slot] : slot;
-  const double *thp = a.x + prob * a.ld_prob + i * a.ld_i;
-  const ObsTab &ob = tab.obs[j];
-
-  double th[NJ], c0[NJ], s0[NJ];
-#pragma unroll
-  for (int k = 0; k < NJ; ++k) {
-    th[k] = thp[k];
-    sincos(th[k] + tab.link[k].th_off, &s0[k], &c0[k]);
-  }
-  int touched = 0;
-  // base evaluation: distance, linkid (M16iB/main_CFS.m:229) and the kinematic prefix of joint s
-  Xf M, Mn, Ps;
+  // pairs_per_cta <= 128 pairs per CTA: small launches (late outer iterations) use fewer pairs per CTA so that phase 2 is one
+  // round of items instead of up to NJ
+  const long long t = (long long)blockIdx.x * pairs_per_cta + tid;
+  int touched = 0, lid = 0, prob = -1;
+  Xf M;
   double p[6];
-  double dbase = INFINITY;
-  int lid = 0;
-#pragma unroll
-  for (int l = 0; l < NJ; ++l) {
-    if (l == s) Ps = M;  // product of links < s (unused when s == 0)
-    if (l == 0) {
-      xf_first(tab.link[0], c0[0], s0[0], M);
-    } else {
-      xf_step(M, tab.link[l], c0[l], s0[l], Mn);
-      M = Mn;
+  // ---- phase 1 ----
+  if (tid < pairs_per_cta && t < total) {
+    const int j = (int)(t % a.nobs);
+    long long rest = t / a.nobs;
+    const int i = (int)(rest % a.H);
+    const int slot = (int)(rest / a.H);
+    prob = a.list ? a.list[slot] : slot;
+    const double *thp = a.x + prob * a.ld_prob + i * a.ld_i;
+    double dbase = INFINITY;
+#pragma unroll 1
+    for (int l = 0; l < NJ; ++l) {
+      const double thl = thp[l];
+      double sn, cs;
+      sincos(thl + tab.link[l].th_off, &sn, &cs);
+      th_s[l][tid] = thl;
+      cs_s[l][tid] = cs;
+      cs_s[NJ + l][tid] = sn;
+      if (l == 0)
+        xf_first(tab.link[0], cs, sn, M);
+      else
+        xf_step_inplace(M, tab.link[l], cs, sn);
+      link_endpoints(M, tab.link[l], tab.base, p);
+      const double d = link_obs_dist(p, tab.obs[j], touched);
+      if (d < dbase) {
+        dbase = d;
+        lid = l + 1;
+      }
     }
-    link_endpoints(M, tab.link[l], tab.base, p);
-    const double d = link_obs_dist(p, ob, touched);
-    if (d < dbase) {
-      dbase = d;
-      lid = l + 1;
-    }
-  }
-  const long long o = prob * a.o_prob + (long long)j * a.o_obs + i * a.o_i;
-  if (s == 0) {
+    const long long o = prob * a.o_prob + (long long)j * a.o_obs + i * a.o_i;
+    o_s[tid] = o;
     a.dist[o] = dbase;
     if (a.linkid) a.linkid[o] = lid;
+    for (int k = lid; k < NJ; ++k) a.grad[o * NJ + k] = 0.0;
   }
-  double der = 0.0;
-  if (s < lid) {  // dist_link(linkid) does not depend on joints > linkid: every f_del is exactly 0 there
-    double ths = 0.0, offs = 0.0;
+  lid_s[tid] = lid;
+  // exclusive scan of the item counts over the CTA
+  {
+    int inc = lid;
 #pragma unroll
-    for (int k = 0; k < NJ; ++k)
-      if (k == s) {
-        ths = th[k];
-        offs = tab.link[k].th_off;
-      }
+    for (int d = 1; d < 32; d <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, inc, d);
+      if ((tid & 31) >= d) inc += v;
+    }
+    if ((tid & 31) == 31) wsum[tid >> 5] = inc;
+    __syncthreads();
+    int base = 0;
+    for (int w = 0; w < (tid >> 5); ++w) base += wsum[w];
+    off_s[tid] = base + inc - lid;
+    if (tid == GRAD_THREADS - 1) off_s[GRAD_THREADS] = base + inc;
+  }
+  __syncthreads();
+  for (int k = 0; k < lid; ++k) items[off_s[tid] + k] = (unsigned short)(tid * 8 + k);
+  __syncthreads();
+  const int nitems = off_s[GRAD_THREADS];
+  // ---- phase 2 ----
+#pragma unroll 1
+  for (int it = tid; it < nitems; it += GRAD_THREADS) {
+    const int pr = items[it] >> 3, s = items[it] & 7, lidp = lid_s[pr];
+    const long long tp = (long long)blockIdx.x * pairs_per_cta + pr;
+    const ObsTab &ob = tab.obs[(int)(tp % a.nobs)];
+    const double ths = th_s[s][pr], offs = tab.link[s].th_off;
+    Xf Ps, MB;  // Ps: product of links < s (unused when s == 0)
+#pragma unroll 1
+    for (int l = 0; l < s; ++l) {
+      if (l == 0)
+        xf_first(tab.link[0], cs_s[0][pr], cs_s[NJ][pr], Ps);
+      else
+        xf_step_inplace(Ps, tab.link[l], cs_s[l][pr], cs_s[NJ + l][pr]);
+    }
     const double h = ths > 0.02 ? ths : 0.02;  // par.NominalStep = max(x0,0.02)  derivest.m:229
 #pragma unroll 1
     for (int kk = 0; kk < DV_NDEL; ++kk) {
-      double f[2];
-#pragma unroll 1
-      for (int sg = 0; sg < 2; ++sg) {
-        const double xs = sg == 0 ? ths + h * dv.delta[kk] : ths - h * dv.delta[kk];  // derivest.m:369-370
-        double sn, cs;
-        sincos(xs + offs, &sn, &cs);
-        if (s == 0)
-          xf_first(tab.link[0], cs, sn, M);
-        else
-          xf_step(Ps, tab.link[s], cs, sn, M);
-#pragma unroll
-        for (int l = 1; l < NJ; ++l)
-          if (l > s && l < lid) {
-            xf_step(M, tab.link[l], c0[l], s0[l], Mn);
-            M = Mn;
-          }
-        link_endpoints(M, tab.link[lid - 1], tab.base, p);
-        f[sg] = link_obs_dist(p, ob, touched);
+      const double step = h * dv.delta[kk];
+      double snA, csA, snB, csB;
+      sincos((ths + step) + offs, &snA, &csA);  // derivest.m:369
+      sincos((ths - step) + offs, &snB, &csB);  // derivest.m:370
+      if (s == 0) {
+        xf_first(tab.link[0], csA, snA, M);
+        xf_first(tab.link[0], csB, snB, MB);
+      } else {
+        xf_step(Ps, tab.link[s], csA, snA, M);
+        xf_step(Ps, tab.link[s], csB, snB, MB);
       }
-      fdel_s[kk][tid] = (f[0] - f[1]) / 2;  // odd transformation, derivest.m:376
+#pragma unroll 1
+      for (int l = s + 1; l < lidp; ++l) {
+        const double cl = cs_s[l][pr], sl = cs_s[NJ + l][pr];
+        xf_step_inplace(M, tab.link[l], cl, sl);
+        xf_step_inplace(MB, tab.link[l], cl, sl);
+      }
+      double pB[6];
+      link_endpoints(M, tab.link[lidp - 1], tab.base, p);
+      link_endpoints(MB, tab.link[lidp - 1], tab.base, pB);
+      const double fA = link_obs_dist(p, ob, touched);
+      const double fB = link_obs_dist(pB, ob, touched);
+      fdel_s[kk][tid] = (fA - fB) / 2;  // odd transformation, derivest.m:376
     }
-    // der_init (derivest.m:415-418)
-    double dinit[DV_NE];
-#pragma unroll
+    // der_init (derivest.m:415-418), in place: entry e only reads entries e and e+1
+#pragma unroll 1
     for (int e = 0; e < DV_NE; ++e)
-      dinit[e] = (fdel_s[e][tid] * dv.fdarule[0] + fdel_s[e + 1][tid] * dv.fdarule[1]) / (h * dv.delta[e]);
-    // rombextrap (derivest.m:512-526)
-    double dr[DV_NEST], er[DV_NEST];
-#pragma unroll
+      fdel_s[e][tid] = (fdel_s[e][tid] * dv.fdarule[0] + fdel_s[e + 1][tid] * dv.fdarule[1]) / (h * dv.delta[e]);
+    // rombextrap (derivest.m:512-526), in place: extrapolant c reads der_init entries c..c+3 and replaces entry c
+#pragma unroll 1
     for (int c = 0; c < DV_NEST; ++c) {
-      double qtr[3], coef[3];
+      double di[4], qtr[3], coef[3];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) di[r] = fdel_s[c + r][tid];
 #pragma unroll
       for (int cc = 0; cc < 3; ++cc) {
         double acc = 0.0;
 #pragma unroll
-        for (int r = 0; r < 4; ++r) acc += dv.q[r][cc] * dinit[r + c];
+        for (int r = 0; r < 4; ++r) acc += dv.q[r][cc] * di[r];
         qtr[cc] = acc;
       }
       coef[2] = qtr[2] / dv.rr[2][2];
       coef[1] = (qtr[1] - dv.rr[1][2] * coef[2]) / dv.rr[1][1];
       coef[0] = ((qtr[0] - dv.rr[0][1] * coef[1]) - dv.rr[0][2] * coef[2]) / dv.rr[0][0];
-      dr[c] = coef[0];
       double ss = 0.0;
 #pragma unroll
       for (int r = 0; r < 4; ++r) {
-        const double res =
-            dinit[r + c] - ((dv.rmat[r][0] * coef[0] + dv.rmat[r][1] * coef[1]) + dv.rmat[r][2] * coef[2]);
+        const double res = di[r] - ((dv.rmat[r][0] * coef[0] + dv.rmat[r][1] * coef[1]) + dv.rmat[r][2] * coef[2]);
         ss += res * res;
       }
-      er[c] = sqrt(ss) * dv.errfac;
+      fdel_s[c][tid] = coef[0];
+      err_s[c][tid] = sqrt(ss) * dv.errfac;
     }
-    // sort ascending (stable), drop ranks {1,2,nest-1,nest}, take the minimum error (derivest.m:442-462).
-    // Done by rank counting: no data-dependent indexing, everything stays in registers.
-    double best_err = INFINITY;
-    int best_rank = DV_NEST;
-    bool have = false;
-#pragma unroll
-    for (int c = 0; c < DV_NEST; ++c) {
-      int rank = 0;
-#pragma unroll
-      for (int e = 0; e < DV_NEST; ++e) {
-        const bool lt = dr[e] < dr[c] || (isnan(dr[c]) && !isnan(dr[e]));
-        const bool eq = (dr[e] == dr[c]) || (isnan(dr[c]) && isnan(dr[e]));
-        rank += (lt || (eq && e < c)) ? 1 : 0;
-      }
-      if (rank >= 2 && rank < DV_NEST - 2) {
-        // min() returns the first minimum in sorted order -> smallest rank on ties
-        if (!have || er[c] < best_err || (er[c] == best_err && rank < best_rank)) {
-          best_err = er[c];
-          best_rank = rank;
-          der = dr[c];
-          have = true;
+    // sort ascending (stable), drop ranks {1,2,nest-1,nest}, take the minimum error (derivest.m:442-462): the dropped
+    // extrapolants are the two that precede all others and the two that all others precede
+    int drop[4] = {-1, -1, -1, -1};
+#pragma unroll 1
+    for (int pass = 0; pass < 4; ++pass) {
+      int bi = -1;
+      double bv = 0.0;
+#pragma unroll 1
+      for (int c = 0; c < DV_NEST; ++c) {
+        if (c == drop[0] || c == drop[1] || c == drop[2] || c == drop[3]) continue;
+        const double v = fdel_s[c][tid];
+        const bool better = bi < 0 || (pass < 2 ? dv_precedes(v, c, bv, bi) : dv_precedes(bv, bi, v, c));
+        if (better) {
+          bv = v;
+          bi = c;
         }
       }
+      if (pass == 0) drop[0] = bi; else if (pass == 1) drop[1] = bi; else if (pass == 2) drop[2] = bi; else drop[3] = bi;
+    }
+    double best_err = INFINITY, best_val = 0.0;
+    int best_c = -1;
+#pragma unroll 1
+    for (int c = 0; c < DV_NEST; ++c) {
+      if (c == drop[0] || c == drop[1] || c == drop[2] || c == drop[3]) continue;
+      const double v = fdel_s[c][tid], er = err_s[c][tid];
+      // min() returns the first minimum in sorted order -> on ties the extrapolant that precedes the other
+      if (best_c < 0 || er < best_err || (er == best_err && dv_precedes(v, c, best_val, best_c))) {
+        best_err = er;
+        best_val = v;
+        best_c = c;
+      }
+    }
+    a.grad[o_s[pr] * NJ + s] = best_val;
+    if (touched && a.flags) {  // the flag belongs to the item's problem, not to this thread's phase-1 pair
+      const long long rest = tp / a.nobs;
+      const int slot = (int)(rest / a.H);
+      atomicOr(&a.flags[a.list ? a.list[slot] : slot], 0x100);
+      touched = 0;
     }
   }
-  a.grad[o * NJ + s] = der;
-  if (touched && a.flags) atomicOr(&a.flags[prob], 0x100);
+  if (touched && a.flags && prob >= 0) atomicOr(&a.flags[prob], 0x100);
+}
+
+template <int NJ>
+static cudaError_t launch_derivest_nj(const GradArgs &a, long long total, cudaStream_t s) {
+  // 128 pairs per CTA unless the launch would leave SMs without a CTA (late outer iterations): then 32 pairs per CTA, i.e.
+  // at most two rounds of work items instead of up to NJ (measured: 51 200 pairs 0.46 ms at 128, 0.50 ms at 32)
+  const int ppc = total >= 148LL * GRAD_THREADS ? GRAD_THREADS : 32;
+  const int grid = (int)((total + ppc - 1) / ppc);
+  const size_t dyn = sizeof(double) * (DV_NDEL + DV_NEST + 3 * NJ) * GRAD_THREADS;  // 60 KB at NJ = 5
+  cudaError_t e = cudaFuncSetAttribute(k_grad_derivest<NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+  if (e != cudaSuccess) return e;
+  k_grad_derivest<NJ><<<grid, GRAD_THREADS, dyn, s>>>(a, ppc);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_grad_derivest(const GradArgs &a, cudaStream_t s) {
-  const long long total = (long long)a.nslots * a.H * a.nobs * a.nj;
+  const long long total = (long long)a.nslots * a.H * a.nobs;  // (waypoint, obstacle) pairs
   if (total <= 0) return cudaSuccess;
-  const int grid = (int)((total + GRAD_THREADS - 1) / GRAD_THREADS);
   switch (a.nj) {
-    case 2: k_grad_derivest<2><<<grid, GRAD_THREADS, 0, s>>>(a); break;
-    case 3: k_grad_derivest<3><<<grid, GRAD_THREADS, 0, s>>>(a); break;
-    case 4: k_grad_derivest<4><<<grid, GRAD_THREADS, 0, s>>>(a); break;
-    case 5: k_grad_derivest<5><<<grid, GRAD_THREADS, 0, s>>>(a); break;
-    case 6: k_grad_derivest<6><<<grid, GRAD_THREADS, 0, s>>>(a); break;
+    case 2: return launch_derivest_nj<2>(a, total, s);
+    case 3: return launch_derivest_nj<3>(a, total, s);
+    case 4: return launch_derivest_nj<4>(a, total, s);
+    case 5: return launch_derivest_nj<5>(a, total, s);
+    case 6: return launch_derivest_nj<6>(a, total, s);
     default: return cudaErrorInvalidValue;
   }
-  return cudaGetLastError();
 }
 
 // ============================================================================================================
