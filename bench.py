@@ -339,8 +339,6 @@ def main():
     grad_flops = f_wp * st["grad_waypoints"]
     # stand-alone distance/gradient kernel on the same number of waypoints as the first outer iteration of the batch
     th_all = cfgs[0]["xref"].reshape(B, H, 2 * nj)[:, :, :nj].reshape(-1, nj)
-    if args.grad == "derivest":
-        th_all = th_all[: 1024 * H]  # 51 200 waypoints x 5 joints = 2000 CTAs: fills the GPU, 3 ms per launch
     k1_ms = ctx0.time_dist_grad(th_all, grad=grad_mode, reps=10)
     k1_tf = f_wp * th_all.shape[0] / (k1_ms * 1e-3) / 1e12
     # ---- e2e from start/goal pairs: the mains' problem set-up (main_FANUC.m:38-103) done on the device ---------------------
