@@ -43,13 +43,13 @@ FUSED_DRAM_BYTES_PER_LAUNCH = 44.82e6 + 13.84e6  # ncu capture of one 4096 x H=5
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=64)
+    ap.add_argument("--steps", type=int, default=96)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=4096)
     ap.add_argument("--horizon", type=int, default=50)
     ap.add_argument("--grad", default="numjac", choices=["numjac", "derivest"])
-    ap.add_argument("--contexts", type=int, default=16, help="library contexts (streams + buffer sets) the steps rotate over")
+    ap.add_argument("--contexts", type=int, default=24, help="library contexts (streams + buffer sets) the steps rotate over")
     ap.add_argument("--cpu-reps", type=int, default=3, help="CPU baseline: passes of the oracle over the same batch")
     return ap.parse_args()
 
