@@ -37,7 +37,7 @@ os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 F_WAYPOINT_NUMJAC = 9680.0   # algorithmic FLOPs of one num_jac gradient (11 dist_arm evaluations), SURVEY.md section 8d
 F_WAYPOINT_DERIVEST = 162080.0
 METRIC = "cfs_trajectories_per_sec"
-FUSED_DRAM_BYTES_PER_LAUNCH = 44.82e6 + 13.84e6  # ncu capture of one 4096 x H=50 batch (profiles/README.md)
+FUSED_DRAM_BYTES_PER_LAUNCH = 43.13e6 + 14.30e6  # ncu capture of one 4096 x H=50 batch (profiles/README.md)
 
 
 def parse_args():
@@ -404,7 +404,7 @@ def main():
                          "achieved": ach_tf, "peak": fp64_tf, "unit": "TFLOP/s", "frac": ach_tf / fp64_tf if fp64_tf else None,
                          "traffic": FUSED_DRAM_BYTES_PER_LAUNCH if (fused and B == 4096 and H == 50) else None,
                          "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of the bulk-tier launch, ncu --set "
-                                           "full, profiles/r01_prof_fused_final_raw.csv",
+                                           "full, profiles/r01_prof_fused_v6_raw.csv",
                          "peak_source": "measured here by cfs_measure_fp64_peak (DFMA micro-benchmark; MEASURED_PEAKS.json "
                                         "has no FP64 entry), implied SM clock %.0f MHz" % fp64_mhz,
                          "algorithmic_flops_per_launch": flops_per_launch, "avg_launch_ms": amort_ms,
