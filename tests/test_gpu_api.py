@@ -284,3 +284,52 @@ def test_rrt_to_cfs_pipeline_on_the_device(ctx, oracle):
     assert int(sol["status"][0]) == int(orc["status"][0]) and int(sol["iters"][0]) == int(orc["iters"][0])
     if (int(orc["status"][0]) & 0xFF) < 2:
         assert np.abs(sol["x"][0] - orc["x"][0]).max() < 1e-6
+
+
+@pytest.mark.parametrize("H", [40, 100])
+def test_two_link_arm_long_horizon(ctx, oracle, H):
+    """main_2L.m's planar arm at its own horizon and at H = 100 (> 64 waypoints: the prefix-sum primal recovery of the fused
+    bulk tier runs in two chunks), a few perturbed goals, against the oracle."""
+    robot = M.robotproperty2("2L")
+    nj = 2
+    goals = [[np.pi / 2, 0.0], [np.pi / 3, 0.4], [1.2, -0.3], [0.9, 0.8]]
+    obs = [{"l": np.array([[0.3, 0.3], [0.3, 0.3], [0.0, 0.0]]), "D": 0.05, "epsilon": 0.05}]
+    cfgs = [M.make_sys_info(robot, nj, H, [0.0, 0.0], g, Q=problem_mod().Q_2L, Rblk=problem_mod().R_2L, r_scale=0.1, lim=[0.1, 0.2],
+                            max_input=np.tile(np.array([1.0, 1.0]) * 0.5 * robot["delta_t"], H), epsilon_O=1e-6,
+                            MAX_O_ITER=40, x_ref=np.tile(np.array([0.0, 0.0, 0.0, 0.0]), H)) for g in goals]
+    s = cfgs[0]
+    r = dict(robot)
+    r["name"] = "2L"
+    ctx.set_robot(r, nj)
+    ctx.set_obstacles(obs)
+    ctx.set_cost(H, s["QQ"], s["lim"], s["MAX_input"])
+    x0 = np.stack([c["xR"][:, 0] for c in cfgs])
+    ff = np.stack([c["ff"] for c in cfgs])
+    caug = np.array([c["caug"] for c in cfgs])
+    xref = np.stack([c["x_"] for c in cfgs])
+    out = ctx.solve_batch(x0, ff, caug, xref, s["epsilon_O"], s["MAX_O_ITER"])
+    assert ctx.stats()["launches"] <= 6                      # the fused kernel took it
+    P = common.oracle_problem(oracle, "2L", obs, s)
+    ref = P.solve_batch(x0, ff, caug, xref)
+    assert (out["status"] == ref["status"]).all() and (out["iters"] == ref["iters"]).all()
+    ok = (ref["status"] & 0xFF) < 2
+    assert ok.any() and np.abs(out["x"][ok] - ref["x"][ok]).max() < 1e-6 and np.abs(out["u"][ok] - ref["u"][ok]).max() < 1e-6
+
+
+def problem_mod():
+    from motionplanning_5d_m_b200 import problem
+    return problem
+
+
+def test_five_joint_horizon_sweep(ctx, oracle):
+    """Horizons around the shared-memory limits of the fused tiers (whichever path the library picks must match the oracle)."""
+    for H in (8, 33, 60, 72):
+        cfg = common.batch_m16ib(oracle, 12, horizon=H)
+        s = _setup(ctx, cfg)
+        out = ctx.solve_batch(cfg["x0"], cfg["ff"], cfg["caug"], cfg["xref"], s["epsilon_O"], s["MAX_O_ITER"])
+        P = common.oracle_problem(oracle, "M16iB", cfg["obs"], s)
+        ref = P.solve_batch(cfg["x0"], cfg["ff"], cfg["caug"], cfg["xref"], nthreads=8)
+        assert (out["status"] == ref["status"]).all() and (out["iters"] == ref["iters"]).all(), H
+        ok = (ref["status"] & 0xFF) < 2
+        if ok.any():
+            assert np.abs(out["x"][ok] - ref["x"][ok]).max() < 1e-6, H
