@@ -333,3 +333,23 @@ def test_five_joint_horizon_sweep(ctx, oracle):
         ok = (ref["status"] & 0xFF) < 2
         if ok.any():
             assert np.abs(out["x"][ok] - ref["x"][ok]).max() < 1e-6, H
+
+
+@pytest.mark.timeout(120)
+def test_non_finite_inputs_terminate(ctx, oracle):
+    """NaN / Inf in a problem's inputs must neither hang the persistent kernels nor disturb the other problems of the batch."""
+    cfg = common.batch_m16ib(oracle, 16, horizon=20)
+    s = _setup(ctx, cfg)
+    ref = ctx.solve_batch(cfg["x0"], cfg["ff"], cfg["caug"], cfg["xref"], s["epsilon_O"], s["MAX_O_ITER"])
+    x0, ff, caug, xref = (cfg[k].copy() for k in ("x0", "ff", "caug", "xref"))
+    ff[3, 7] = np.nan
+    xref[5, 12] = np.inf
+    x0[9, 1] = np.nan
+    for fused in (1, 0):
+        ctx.set_option("fused", fused)
+        out = ctx.solve_batch(x0, ff, caug, xref, s["epsilon_O"], s["MAX_O_ITER"])
+        ctx.set_option("fused", 1)
+        good = np.setdiff1d(np.arange(16), [3, 5, 9])
+        assert np.array_equal(out["status"][good], ref["status"][good]) and np.array_equal(out["iters"][good], ref["iters"][good])
+        assert np.abs(out["x"][good] - ref["x"][good]).max() < (1e-12 if fused else 1e-6)   # lock-step: parity tolerance
+        assert ((out["status"][[3, 5, 9]] & 0xFF) <= 3).all()
