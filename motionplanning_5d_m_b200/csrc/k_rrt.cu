@@ -57,8 +57,9 @@ __global__ void __launch_bounds__(RRT_THREADS) k_rrt_find_routes(RrtArgs a) {
   extern __shared__ __align__(16) unsigned char rrt_smem[];
   __shared__ alignas(128) DevTables tab;
   __shared__ alignas(8) uint64_t mbar;
-  __shared__ double s_sample[CFS_MAXL], s_new[CFS_MAXL], red_v[RRT_THREADS / 32];
+  __shared__ double s_sample[CFS_MAXL], s_new[CFS_MAXL], red_v[RRT_THREADS / 32], s_cs[2 * CFS_MAXL], s_p[6 * CFS_MAXL];
   __shared__ int red_i[RRT_THREADS / 32], s_ctl[4];
+  __shared__ double s_rnd[2 * RRT_THREADS];  // window of the seed's random stream (refilled by the whole CTA)
   const int nj = a.nj, cap = a.max_iter + 2, tid = threadIdx.x, seed = blockIdx.x;
   const RrtLayout L = rrt_layout(nj, cap);
   double *nodes = reinterpret_cast<double *>(rrt_smem + L.nodes);
@@ -70,7 +71,7 @@ __global__ void __launch_bounds__(RRT_THREADS) k_rrt_find_routes(RrtArgs a) {
   const double *rnd = a.rnd + (size_t)seed * a.nrnd;
   if (tid < nj) { nodes[tid] = x0[tid]; s_new[tid] = x0[tid]; }
   if (tid == 0) { parent[0] = -1; total[0] = 0.0; }
-  int node_num = 1, cur = 0, par = 0, fail = 0, exhausted = 0, touched = 0;
+  int node_num = 1, cur = 0, par = 0, fail = 0, exhausted = 0, touched = 0, win = -(1 << 30);
   __syncthreads();
   for (;;) {
     // ---- goal_reached (:193-207): every joint inside the goal box ----
@@ -82,18 +83,23 @@ __global__ void __launch_bounds__(RRT_THREADS) k_rrt_find_routes(RrtArgs a) {
     // ---- getNode (:97-104): sample, nearest, steer, until feasible ----
     for (;;) {
       __syncthreads();
+      if (cur + nj + 1 > win + 2 * RRT_THREADS) {  // the next draw (1 + nj numbers) must lie inside the window
+        win = cur;
+        for (int e = tid; e < 2 * RRT_THREADS; e += RRT_THREADS) s_rnd[e] = win + e < a.nrnd ? rnd[win + e] : 0.0;
+        __syncthreads();
+      }
       if (tid == 0) {
         int c = cur, ex = 0;
         if (c >= a.nrnd) {
           ex = 1;
         } else {
-          const double pp = rnd[c++];
+          const double pp = s_rnd[c++ - win];
           if (pp < a.bi) {
             if (c + nj > a.nrnd) {
               ex = 1;
             } else {
               for (int k = 0; k < nj; ++k)
-                s_sample[k] = __dadd_rn(__dmul_rn(__dmul_rn(__dsub_rn(rnd[c + k], 0.5), a.region_s[k]), 2.0), a.sample_off[k]);
+                s_sample[k] = __dadd_rn(__dmul_rn(__dmul_rn(__dsub_rn(s_rnd[c + k - win], 0.5), a.region_s[k]), 2.0), a.sample_off[k]);
               c += nj;
             }
           } else {
@@ -133,21 +139,30 @@ __global__ void __launch_bounds__(RRT_THREADS) k_rrt_find_routes(RrtArgs a) {
         for (int k = 0; k < nj; ++k) s_new[k] = __dadd_rn(pn[k], __ddiv_rn(__dmul_rn(__dsub_rn(s_sample[k], pn[k]), 0.1), nrm));
       }
       __syncthreads();
-      // feasible (:146-181): one thread per obstacle runs the chain; infeasible if any link is closer than obs{j}.D
-      int ok = 1;
-      if (tid < a.nobs) {
+      // feasible (:146-181): sin/cos per joint lane, the chain of link transforms on one thread (the only sequential part),
+      // then one thread per (link, obstacle) pair; infeasible if any link is closer than obs{j}.D
+      if (tid < nj) {
+        double sn, cs;
+        sincos(s_new[tid] + tab.link[tid].th_off, &sn, &cs);
+        s_cs[tid] = cs;
+        s_cs[CFS_MAXL + tid] = sn;
+      }
+      __syncthreads();
+      if (tid == 0) {
         Xf M;
-        double p[6];
         for (int l = 0; l < nj; ++l) {
-          double sn, cs;
-          sincos(s_new[l] + tab.link[l].th_off, &sn, &cs);
           if (l == 0)
-            xf_first(tab.link[0], cs, sn, M);
+            xf_first(tab.link[0], s_cs[0], s_cs[CFS_MAXL], M);
           else
-            xf_step_inplace(M, tab.link[l], cs, sn);
-          link_endpoints(M, tab.link[l], tab.base, p);
-          if (link_obs_dist(p, tab.obs[tid], touched) < tab.obs[tid].D) ok = 0;
+            xf_step_inplace(M, tab.link[l], s_cs[l], s_cs[CFS_MAXL + l]);
+          link_endpoints(M, tab.link[l], tab.base, &s_p[6 * l]);
         }
+      }
+      __syncthreads();
+      int ok = 1;
+      for (int e = tid; e < nj * a.nobs; e += RRT_THREADS) {
+        const int l = e % nj, j = e / nj;
+        if (link_obs_dist(&s_p[6 * l], tab.obs[j], touched) < tab.obs[j].D) ok = 0;
       }
       if (__syncthreads_and(ok)) break;
     }
