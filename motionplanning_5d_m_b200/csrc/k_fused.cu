@@ -11,12 +11,16 @@
 //   * the trajectory x_, the controls u, the linearised rows (-grad, rhs) and the QP working set never leave shared
 //     memory between iterations: HBM sees each problem's inputs once and its outputs once (6.1 KB in, 6.3 KB out at
 //     H = 50), the batch-shared Gram operator G (4.5 MB) streams from L2;
-//   * the robot/obstacle tables are staged once per CTA with one TMA bulk copy (UBLKCP), the 30 sin/cos values of a
-//     waypoint's 11 num_jac evaluations are cached in shared memory that the QP phase reuses for its working-set inverse.
-//   * two tiers of the same code: the bulk tier (128 threads, 3 CTAs/SM, working-set inverse up to 48 x 48 in shared
-//     memory) hands the rare QP whose working set outgrows that, or that needs more than esc_steps dual steps (almost
-//     always an infeasible linearisation on its way to the infeasibility certificate), to the heavy tier (256 threads,
-//     1 CTA/SM, 128 x 128 inverse on chip), which resumes the problem from its last completed outer iteration.
+//   * the robot/obstacle tables are staged once per CTA with one TMA bulk copy (UBLKCP); the sin/cos values, kinematic
+//     prefixes and running minima of a trajectory's num_jac evaluations (cfs_numjac_cols.cuh: 35 link steps per waypoint
+//     instead of 55) live in shared memory that the QP phase reuses for its cached directions and working-set inverse;
+//   * two tiers of the same code: the bulk tier (128 threads, 3 CTAs/SM, working sets of up to 15 rows with every member's
+//     direction QQ^-1 c' cached in shared memory: no L2 access inside a dual step) hands the rare QP whose working set
+//     outgrows that, or that needs more than esc_steps dual steps (almost always an infeasible linearisation on its way to
+//     the infeasibility certificate), to the heavy tier (256 threads, 1 CTA/SM, 144 x 144 inverse on chip, primal recovery
+//     through the Gram operator), which resumes the problem from its last completed outer iteration;
+//   * the bulk tier pulls the problems longest-expected-first (launch_work_order, k_grad.cu): the ones whose reference line
+//     passes inside an obstacle margin start first, so the batch ends with short problems instead of a tail of long ones.
 #include "cfs_numjac_cols.cuh"
 #include "qp_core.cuh"
 
