@@ -111,6 +111,27 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
+def bind_to_gpu_numa(index):
+    """Multi-rank runs: keep this rank's threads (and hence its first-touch pinned staging buffers) on the CPU cores local to
+    its GPU (sysfs local_cpulist of the GPU's PCI function).  Returns a short description for the JSON line, or None."""
+    try:
+        bus = subprocess.check_output(["nvidia-smi", "-i", str(index), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                                      text=True, timeout=20).strip().lower()
+        if bus.startswith("00000000:"):
+            bus = bus[4:]
+        cpus = set()
+        for part in open("/sys/bus/pci/devices/%s/local_cpulist" % bus).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return "%s: %d local cores" % (bus, len(cpus))
+    except Exception:
+        return None
+
+
 def cpu_count():
     try:
         return len(os.sched_getaffinity(0))
@@ -193,6 +214,7 @@ def main():
         raise SystemExit("bench.py: no CUDA device; this framework has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = bind_to_gpu_numa(local_rank) if world > 1 else None  # N = 1 keeps every core for the CPU baseline leg
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -381,7 +403,7 @@ def main():
             "config": {"workload": workload_text(args), "batch_per_gpu": B, "horizon": H,
                        "l2": "%d rotating buffer sets (one seeded batch each, %.0f MB of inputs+state+outputs in total) "
                              "> 126 MB L2; 256 MB flush before each timed region" % (NC, NC * B * (bytes_per_problem + 8 * 4 * n) / 1e6),
-                       "contexts": NC, "seed": synthetic.SEED,
+                       "contexts": NC, "seed": synthetic.SEED, "numa_binding": numa,
                        "parallelism": "independent problems sharded over %d GPU(s), no data-path collective; per-step NCCL "
                                       "all-gather of (cost,status) for best-of" % world},
             "e2e": {"value": world * B * args.steps / (ms_e2e * 1e-3), "unit": "trajectories/s",
