@@ -353,3 +353,19 @@ def test_non_finite_inputs_terminate(ctx, oracle):
         assert np.array_equal(out["status"][good], ref["status"][good]) and np.array_equal(out["iters"][good], ref["iters"][good])
         assert np.abs(out["x"][good] - ref["x"][good]).max() < (1e-12 if fused else 1e-6)   # lock-step: parity tolerance
         assert ((out["status"][[3, 5, 9]] & 0xFF) <= 3).all()
+
+
+def test_scheduling_options_never_change_results(ctx, oracle):
+    """lpt (longest-expected-first work order), bulk_grid / heavy_grid caps and heavy_prio only change WHEN a problem is solved."""
+    cfg = common.batch_m16ib(oracle, 160, horizon=30)
+    s = _setup(ctx, cfg)
+    args = (cfg["x0"], cfg["ff"], cfg["caug"], cfg["xref"])
+    ref = ctx.solve_batch(*args, s["epsilon_O"], s["MAX_O_ITER"])
+    for name, val, back in (("lpt", 0, 1), ("bulk_grid", 7, 0), ("heavy_grid", 3, 0), ("heavy_prio", 0, 1)):
+        ctx.set_option(name, val)
+        out = ctx.solve_batch(*args, s["epsilon_O"], s["MAX_O_ITER"])
+        ctx.set_option(name, back)
+        for k in ("u", "x", "iters", "status"):
+            assert np.array_equal(out[k], ref[k]), (name, k)
+    with pytest.raises(M.CfsError, match="unknown option"):
+        ctx.set_option("no_such_option", 1)
