@@ -64,7 +64,11 @@ int cfs_set_stream(cfs_ctx *ctx, void *cuda_stream);
 /* Options: "fused" (default 1): solve CFS / num_jac batches with the persistent fused kernel (one CTA carries a problem
  * through all outer iterations); 0 = one gradient launch + one QP launch per outer iteration (the path PSGCFS and the
  * DERIVEST gradients always take).  "esc_steps" (default 48): dual active-set steps one QP may take in the fused
- * kernel's bulk tier before the problem is handed to its heavy tier (0 = never). */
+ * kernel's bulk tier before the problem is handed to its heavy tier (0 = never).  Scheduling knobs, none of which changes a
+ * result: "lpt" (default 1): the fused solver pulls the problems longest-expected-first (a distance pre-pass over every
+ * reference line orders them by the number of waypoints inside an obstacle margin); "bulk_grid" / "heavy_grid" (default 0 =
+ * every resident slot / one CTA per SM): caps of the two tiers' grids; "heavy_prio" (default 1): heavy tier on a
+ * highest-priority stream. */
 int cfs_set_option(cfs_ctx *ctx, const char *name, int value);
 
 /* ---- problem data ------------------------------------------------------------------------------------- */
