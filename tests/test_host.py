@@ -94,3 +94,39 @@ def test_synthetic_batch_is_deterministic(oracle):
     o6 = oracle.obs6(a["obs"][0]["l"])
     for th in np.concatenate([a["theta0"], a["thetag"]]):
         assert oracle.dist_arm(r, th, o6)[0] >= 0.2
+
+
+def test_bench_reference_arm_contract():
+    """bench.py --impl reference: one JSON line with the contract's keys (the oracle port on the host cores; no GPU needed),
+    and under a multi-rank launch only rank 0 prints."""
+    import json
+    import subprocess
+    import sys
+    bench = os.path.join(ROOT, "bench.py")
+    cmd = [sys.executable, bench, "--impl", "reference", "--steps", "2", "--warmup", "1", "--batch", "24", "--horizon", "12"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-400:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "cfs_trajectories_per_sec" and d["unit"] == "trajectories/s"
+    assert d["higher_is_better"] is True and d["steps"] == 2 and d["value"] > 0 and d["dtype"] == "f64"
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "trajectories/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    env = dict(os.environ, RANK="1", LOCAL_RANK="1", WORLD_SIZE="2")
+    other = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env)
+    assert other.returncode == 0 and not [l for l in other.stdout.splitlines() if l.startswith("{")]
+
+
+def test_bench_helpers_degrade_without_a_gpu():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    b = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(b)
+    import shutil
+    if shutil.which("nvidia-smi") is None:
+        assert b.bind_to_gpu_numa(0) is None
+        smp = b.ClockSampler(0)
+        smp.start()
+        assert smp.stop()["sm_mhz"] is None
+    assert b.cpu_count() >= 1
