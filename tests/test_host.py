@@ -130,3 +130,19 @@ def test_bench_helpers_degrade_without_a_gpu():
         smp.start()
         assert smp.stop()["sm_mhz"] is None
     assert b.cpu_count() >= 1
+
+
+def test_flat_fixture_round_trip(oracle, tmp_path):
+    """the flat little-endian fixture MATLAB / Python / C share (matlab/read_cfs_fixture.m reads it)."""
+    from motionplanning_5d_m_b200 import fixture_io
+    cfg = common.batch_m16ib(oracle, 6, horizon=10)
+    p = str(tmp_path / "batch.bin")
+    fixture_io.write_batch_fixture(p, cfg)
+    back = fixture_io.read_fixture(p)
+    assert np.array_equal(back["QQ"], cfg["sys_info"]["QQ"]) and np.array_equal(back["xref"], cfg["xref"])
+    assert np.array_equal(back["ff"], cfg["ff"]) and back["ff"].shape == (6, 50) and float(back["H"]) == 10
+    raw = open(p, "rb").read()
+    assert raw[:4] == b"CFSB" and raw[12:14] == b"H\0"
+    # column-major on disk: the first 8 values of QQ in the file are its first COLUMN
+    off = raw.index(b"QQ".ljust(32, b"\0")) + 32 + 4 + 16
+    assert np.array_equal(np.frombuffer(raw[off:off + 64], dtype="<f8"), cfg["sys_info"]["QQ"][:8, 0])
