@@ -25,7 +25,7 @@ for b in blocks:
     # find matching function table: by template args
     key = re.sub(r'\(int\)', '', b['name'])
     nums = re.findall(r'<([^>]*)>', key)
-    cand = [f for f in tables if 'fused' in f or 'k_qp' in f]
+    cand = [f for f in tables if 'fused' in f or 'k_qp' in f or 'warp' in f]
     want = 'ILi' + 'ELi'.join(x.strip() for x in nums[0].split(',')) + 'E' if nums else ''
     fnm = [f for f in cand if want in f]
     tab = tables[fnm[0]] if fnm else {}

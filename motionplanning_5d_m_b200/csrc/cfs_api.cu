@@ -57,7 +57,7 @@ struct cfs_ctx {
   DevBuf th0, thg;
   // batch buffers
   DevBuf x0, ff, caug, xref, noise, u, x, cost, eu, u0, v0, cost0, dist, grad, lid, iters, status, flags, listA, listB,
-      counters, slab, scratch_theta, scratch_out, qpsteps, fupper, probsteps, psg_w, psg_cost, psg_skip, routes;
+      counters, slab, scratch_theta, scratch_out, qpsteps, fupper, probsteps, psg_w, psg_cost, psg_skip, routes, zslab;
   int slab_grid = 0, slab_ld = 0;
   // timing
   std::vector<cudaEvent_t> ev;
@@ -75,6 +75,9 @@ struct cfs_ctx {
   int bulk_grid = 0;      // cfs_set_option("bulk_grid"): cap of the bulk tier's grid (0 = every resident slot)
   int heavy_prio = 1;     // cfs_set_option("heavy_prio"): heavy tier on the highest-priority stream
   int lpt = 1;            // cfs_set_option("lpt"): fused solver pulls the problems longest-expected-first
+  int use_warp = 1;       // cfs_set_option("warp"): bulk tier = one warp per problem (k_warp.cu); 0 = one CTA per problem
+  int warp_cfg = 0;       // cfs_set_option("warp_cfg"): 0 = 12 warps in one CTA per SM, 1 = 3 CTAs of 3 warps per SM
+  int warp_zs = 0;        // cfs_set_option("warp_zs"): direction slots in shared memory (0 = as many as fit, at most 4)
   bool fused_last = false;
   std::vector<double> it_grad_ms, it_qp_ms;
   cfs_stats stats;
@@ -231,7 +234,7 @@ extern "C" void cfs_destroy(cfs_ctx *ctx) {
                     &ctx->u0, &ctx->v0, &ctx->cost0, &ctx->dist, &ctx->grad, &ctx->lid, &ctx->iters, &ctx->status,
                     &ctx->flags, &ctx->listA, &ctx->listB, &ctx->counters, &ctx->slab, &ctx->scratch_theta,
                     &ctx->scratch_out, &ctx->qpsteps, &ctx->fupper, &ctx->probsteps, &ctx->routes, &ctx->psg_w, &ctx->psg_cost,
-                    &ctx->psg_skip, &ctx->th0, &ctx->thg};
+                    &ctx->psg_skip, &ctx->th0, &ctx->thg, &ctx->zslab};
   for (DevBuf *b : bufs) free_buf(*b);
   if (ctx->dQblk) cudaFree(ctx->dQblk);
   double *ds[] = {ctx->dQQraw, ctx->dQQ, ctx->dG, ctx->dgn, ctx->dGI, ctx->dgnI, ctx->dlim, ctx->dumax, ctx->dworkL, ctx->dworkY};
@@ -492,7 +495,17 @@ static int solve_device(cfs_ctx *ctx, int B, int solver, int grad, const double 
   a.slab_ld = n;
 
   const bool fused = ctx->use_fused && !psg && grad == CFS_GRAD_NUMJAC && fused_supported(a);
-  int grid = fused ? fused_max_grid(a, ctx->device, 0) : qp_max_grid(a, ctx->device);
+  // bulk tier of the fused solver: one warp per problem (k_warp.cu) when its shared-memory regions fit
+  bool warp = false;
+  if (fused && ctx->use_warp) {
+    for (int zs = ctx->warp_zs > 0 ? ctx->warp_zs : 4; zs >= 1 && !warp; --zs) {
+      a.warp_zs = zs;
+      warp = warp_supported(a, ctx->warp_cfg);
+      if (ctx->warp_zs > 0) break;
+    }
+  }
+  int grid = fused ? (warp ? warp_max_grid(a, ctx->device, ctx->warp_cfg) : fused_max_grid(a, ctx->device, 0))
+                   : qp_max_grid(a, ctx->device);
   int grid_heavy = fused ? fused_max_grid(a, ctx->device, 1) : 0;
   if (grid <= 0 || (fused && grid_heavy <= 0))
     return fail(ctx, CFS_E_CUDA, "solver kernel does not fit on this device (shared memory)");
@@ -500,6 +513,13 @@ static int solve_device(cfs_ctx *ctx, int B, int solver, int grad, const double 
     int sms = 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
     if (grid > 8 * sms) grid = 8 * sms;
+  }
+  if (warp) {
+    const int wpc = warp_warps_per_cta(ctx->warp_cfg);
+    if (grid > (B + wpc - 1) / wpc) grid = (B + wpc - 1) / wpc;
+    if (grid < 1) grid = 1;
+    if ((rc = ensure(ctx, ctx->zslab, sizeof(double) * (size_t)grid * wpc * 16 * n))) return rc;
+    a.zslab = ptr<double>(ctx->zslab);
   }
   if (grid > B) grid = B;
   if (grid < 1) grid = 1;
@@ -538,7 +558,7 @@ static int solve_device(cfs_ctx *ctx, int B, int solver, int grad, const double 
       a.order = ptr<int>(ctx->listB);
     }
     if (detail) CU(cudaEventRecord(ctx->ev[0], st));
-    CU(launch_fused(a, grid, 0, st)); ++launches;        // bulk tier: every problem
+    CU(warp ? launch_warp(a, grid, ctx->warp_cfg, st) : launch_fused(a, grid, 0, st)); ++launches;  // bulk tier: every problem
     if (detail) CU(cudaEventRecord(ctx->ev[1], st));
     // heavy tier: the (device-side) escalation list, usually < 1 % of the problems.  It runs on a highest-priority stream
     // so that, with several contexts in flight, its few CTAs (one per SM) are placed before another context's bulk tier
@@ -1160,6 +1180,9 @@ extern "C" int cfs_set_option(cfs_ctx *ctx, const char *name, int value) {
   if (strcmp(name, "bulk_grid") == 0) { ctx->bulk_grid = value; return 0; }
   if (strcmp(name, "heavy_prio") == 0) { ctx->heavy_prio = value; return 0; }
   if (strcmp(name, "lpt") == 0) { ctx->lpt = value; return 0; }
+  if (strcmp(name, "warp") == 0) { ctx->use_warp = value; return 0; }
+  if (strcmp(name, "warp_cfg") == 0) { ctx->warp_cfg = value ? 1 : 0; return 0; }
+  if (strcmp(name, "warp_zs") == 0) { ctx->warp_zs = value; return 0; }
   return fail(ctx, CFS_E_ARG, "cfs_set_option: unknown option '%s'", name);
 }
 

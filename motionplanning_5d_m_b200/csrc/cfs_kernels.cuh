@@ -126,6 +126,9 @@ struct SolveArgs {
   int *work_counter2;         // work queue of the heavy tier
   int esc_steps;              // bulk tier: dual steps per QP before escalation
   long long *prof;            // optional 8-slot phase profile of k_qp (clock64 ticks of thread 0), or nullptr
+  // warp-per-problem bulk tier (k_warp.cu)
+  double *zslab;              // per-warp overflow of the direction cache: (WQ_QZ - warp_zs) * n doubles per resident warp
+  int warp_zs;                // direction slots kept in shared memory
 };
 cudaError_t launch_solve_init(const SolveArgs &a, cudaStream_t s);
 cudaError_t launch_v0(const SolveArgs &a, cudaStream_t s);
@@ -141,6 +144,13 @@ bool fused_supported(const SolveArgs &a);  // CFS solver, num_jac gradients, nj 
 size_t fused_smem_bytes(const SolveArgs &a, int tier);
 int fused_max_grid(const SolveArgs &a, int device, int tier);
 cudaError_t launch_fused(const SolveArgs &a, int grid, int tier, cudaStream_t s);
+
+// ---- warp-per-problem bulk tier of the fused solver (k_warp.cu): cfg 0 = 12 warps in one CTA per SM, 1 = 3 CTAs x 3 warps ----
+bool warp_supported(const SolveArgs &a, int cfg);  // CFS solver, num_jac gradients, nj in {2, 5}, shared memory fits
+size_t warp_smem_bytes(const SolveArgs &a, int cfg);
+int warp_max_grid(const SolveArgs &a, int device, int cfg);
+int warp_warps_per_cta(int cfg);
+cudaError_t launch_warp(const SolveArgs &a, int grid, int cfg, cudaStream_t s);
 
 // ---- dense get_con rows (one problem) -------------------------------------------------------------------------
 cudaError_t launch_get_con_rows(const DevTables *tab, int H, int nj, int nobs, int has_lim, int margin_is_D,

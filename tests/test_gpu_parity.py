@@ -139,22 +139,33 @@ def test_main_2l_solve_parity(ctx, oracle):
     _compare_solve(out, ref)
 
 
-@pytest.mark.parametrize("fused", [1, 0])
-def test_batch_m16ib_solve_parity(ctx, oracle, fused):
-    """Seeded random start/goal batch at the headline configuration (H=50), including infeasible problems; through the
-    fused persistent kernel (default) and through the launch-per-iteration path."""
+BULK_MODES = {"warp": dict(fused=1, warp=1, warp_cfg=0), "warp_3x3": dict(fused=1, warp=1, warp_cfg=1),
+              "warp_zs1": dict(fused=1, warp=1, warp_cfg=0, warp_zs=1), "cta": dict(fused=1, warp=0), "lockstep": dict(fused=0)}
+BULK_DEFAULT = dict(fused=1, warp=1, warp_cfg=0, warp_zs=0)
+
+
+@pytest.mark.parametrize("mode", list(BULK_MODES))
+def test_batch_m16ib_solve_parity(ctx, oracle, mode):
+    """Seeded random start/goal batch at the headline configuration (H=50), including infeasible problems; through every
+    form of the solver: the fused persistent solver with its warp-per-problem bulk tier (default; both CTA shapes, and with
+    a single direction slot in shared memory so that the global overflow slab is exercised), with the CTA-per-problem bulk
+    tier, and through the launch-per-iteration path."""
     O = oracle
-    ctx.set_option("fused", fused)
-    cfg = common.batch_m16ib(O, 192)
-    s = cfg["sys_info"]
-    _set(ctx, "M16iB", cfg["robot"], cfg["obs"], s)
-    P = common.oracle_problem(O, "M16iB", cfg["obs"], s)
-    ref = P.solve_batch(cfg["x0"], cfg["ff"], cfg["caug"], cfg["xref"], nthreads=8)
-    out = ctx.solve_batch(cfg["x0"], cfg["ff"], cfg["caug"], cfg["xref"], s["epsilon_O"], s["MAX_O_ITER"])
-    ctx.set_option("fused", 1)
+    for k, v in BULK_MODES[mode].items():
+        ctx.set_option(k, v)
+    try:
+        cfg = common.batch_m16ib(O, 192)
+        s = cfg["sys_info"]
+        _set(ctx, "M16iB", cfg["robot"], cfg["obs"], s)
+        P = common.oracle_problem(O, "M16iB", cfg["obs"], s)
+        ref = P.solve_batch(cfg["x0"], cfg["ff"], cfg["caug"], cfg["xref"], nthreads=8)
+        out = ctx.solve_batch(cfg["x0"], cfg["ff"], cfg["caug"], cfg["xref"], s["epsilon_O"], s["MAX_O_ITER"])
+    finally:
+        for k, v in BULK_DEFAULT.items():
+            ctx.set_option(k, v)
     assert ((ref["status"] & 0xFF) == 2).any() and ((ref["status"] & 0xFF) == 0).any()
     _compare_solve(out, ref)
-    assert ctx.stats()["launches"] == (6 if fused else 44)
+    assert ctx.stats()["launches"] == (44 if mode == "lockstep" else 6)
 
 
 def test_psgcfs_main_fanuc_parity(ctx, oracle):
