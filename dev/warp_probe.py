@@ -13,9 +13,9 @@ H, nj, K = 50, 5, 20
 robot = dict(M.robotproperty2("M16iB")); robot["name"] = "M16iB"
 ctx = M.Context(0)
 ctx.set_robot(robot, nj); ctx.set_obstacles([synthetic.OBS_M16IB])
-MODES = [("cta", dict(warp=0)), ("warp12 zs3", dict(warp=1, warp_cfg=0, warp_zs=0)), ("warp12 zs2", dict(warp=1, warp_cfg=0, warp_zs=2)),
-         ("warp12 zs1", dict(warp=1, warp_cfg=0, warp_zs=1)), ("warp3x3 zs4", dict(warp=1, warp_cfg=1, warp_zs=4)),
-         ("warp3x3 zs2", dict(warp=1, warp_cfg=1, warp_zs=2)), ("warp12 esc200", dict(warp=1, warp_cfg=0, warp_zs=0, esc_steps=200))]
+MODES = [("cta", dict(warp=0)), ("warp12 noscreen", dict(warp=1, warp_cfg=0, warp_zs=0, screen=0)), ("warp12 screen", dict(warp=1, warp_cfg=0, warp_zs=0, screen=1)),
+         ("warp2x5 screen", dict(warp=1, warp_cfg=4, warp_zs=3, screen=1)), ("warp2x5 screen hg32", dict(warp=1, warp_cfg=4, warp_zs=3, screen=1, heavy_grid=32))]
+LEVEL = int(sys.argv[3]) if len(sys.argv) > 3 else 1
 for seed in range(SEEDS):
     cfg = synthetic.batch_config_m16ib(B, lambda cand: ctx.nodes_feasible(cand)[0], horizon=H, seed=synthetic.SEED + seed)
     s = cfg["sys_info"]
@@ -23,9 +23,9 @@ for seed in range(SEEDS):
     args = [cfg[k] for k in ("x0", "ff", "caug", "xref")]
     base = None
     for name, opts in MODES:
-        ctx.set_option("esc_steps", 48)
+        ctx.set_option("esc_steps", 48); ctx.set_option("heavy_cfg", 0); ctx.set_option("heavy_grid", 0); ctx.set_option("screen", 1)
         for k, v in opts.items(): ctx.set_option(k, v)
-        ctx.set_timing(2)
+        ctx.set_timing(LEVEL)
         best = None
         for rep in range(3):
             out = ctx.solve_batch(*args, s["epsilon_O"], K)

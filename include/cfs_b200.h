@@ -67,8 +67,12 @@ int cfs_set_stream(cfs_ctx *ctx, void *cuda_stream);
  * kernel's bulk tier before the problem is handed to its heavy tier (0 = never).  Scheduling knobs, none of which changes a
  * result: "lpt" (default 1): the fused solver pulls the problems longest-expected-first (a distance pre-pass over every
  * reference line orders them by the number of waypoints inside an obstacle margin); "bulk_grid" / "heavy_grid" (default 0 =
- * every resident slot / one CTA per SM): caps of the two tiers' grids; "heavy_prio" (default 1): heavy tier on a
- * highest-priority stream. */
+ * every resident slot / 48 CTAs): caps of the two tiers' grids; "heavy_prio" (default 1): heavy tier on a
+ * highest-priority stream; "warp" (default 1): bulk tier with one WARP per problem (k_warp.cu; 0 = one CTA per problem);
+ * "warp_cfg" (default 3): its CTA shape (0: 12 warps x 1 CTA/SM, 1: 3 x 3, 2: 4 x 3, 3: 1 x 10, 4: 2 x 5); "warp_zs"
+ * (default 0 = as many as fit): cached directions per warp kept in shared memory; "screen" (default 1): the warp tier runs in
+ * two launches (outer iteration 1 | the rest) so that the heavy tier starts after the first; "heavy_cfg" (default 0): 1 =
+ * slim heavy tier (64 x 64 inverse on chip, 168 registers). */
 int cfs_set_option(cfs_ctx *ctx, const char *name, int value);
 
 /* ---- problem data ------------------------------------------------------------------------------------- */

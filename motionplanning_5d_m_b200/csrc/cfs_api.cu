@@ -57,7 +57,7 @@ struct cfs_ctx {
   DevBuf th0, thg;
   // batch buffers
   DevBuf x0, ff, caug, xref, noise, u, x, cost, eu, u0, v0, cost0, dist, grad, lid, iters, status, flags, listA, listB,
-      counters, slab, scratch_theta, scratch_out, qpsteps, fupper, probsteps, psg_w, psg_cost, psg_skip, routes, zslab;
+      counters, slab, scratch_theta, scratch_out, qpsteps, fupper, probsteps, psg_w, psg_cost, psg_skip, routes, zslab, cont;
   int slab_grid = 0, slab_ld = 0;
   // timing
   std::vector<cudaEvent_t> ev;
@@ -71,13 +71,17 @@ struct cfs_ctx {
   int timing_level = 1;
   bool use_fused = true;  // cfs_set_option("fused")
   int esc_steps = 48;     // cfs_set_option("esc_steps")
-  int heavy_grid = 0;     // cfs_set_option("heavy_grid"): cap of the heavy tier's grid (0 = one CTA per SM)
+  int heavy_grid = 48;    // cfs_set_option("heavy_grid"): cap of the heavy tier's grid (0 = one CTA per SM)
   int bulk_grid = 0;      // cfs_set_option("bulk_grid"): cap of the bulk tier's grid (0 = every resident slot)
   int heavy_prio = 1;     // cfs_set_option("heavy_prio"): heavy tier on the highest-priority stream
   int lpt = 1;            // cfs_set_option("lpt"): fused solver pulls the problems longest-expected-first
   int use_warp = 1;       // cfs_set_option("warp"): bulk tier = one warp per problem (k_warp.cu); 0 = one CTA per problem
-  int warp_cfg = 0;       // cfs_set_option("warp_cfg"): 0 = 12 warps in one CTA per SM, 1 = 3 CTAs of 3 warps per SM
+  int warp_cfg = 3;       // cfs_set_option("warp_cfg"): CTA shape of the warp tier (k_warp.cu): 0 = 12 warps x 1 CTA/SM, 1 = 3 x 3, 2 = 4 x 3,
+                          // 3 = 1 warp x 10 CTAs/SM (default: the finest granularity pipelines best across contexts), 4 = 2 x 5
   int warp_zs = 0;        // cfs_set_option("warp_zs"): direction slots in shared memory (0 = as many as fit, at most 4)
+  int screen = 1;         // cfs_set_option("screen"): warp tier in two launches (iteration 1 | the rest), heavy tier starts after the first
+  int heavy_cfg = 0;      // cfs_set_option("heavy_cfg"): 0 = 144 x 144 inverse on chip (whole SM), 1 = slim (64 x 64 on chip, 168 registers)
+  int heavy_skip = 0;     // cfs_set_option("heavy_skip"): measurement only -- the heavy tier is not launched (escalated problems keep status 4)
   bool fused_last = false;
   std::vector<double> it_grad_ms, it_qp_ms;
   cfs_stats stats;
@@ -234,7 +238,7 @@ extern "C" void cfs_destroy(cfs_ctx *ctx) {
                     &ctx->u0, &ctx->v0, &ctx->cost0, &ctx->dist, &ctx->grad, &ctx->lid, &ctx->iters, &ctx->status,
                     &ctx->flags, &ctx->listA, &ctx->listB, &ctx->counters, &ctx->slab, &ctx->scratch_theta,
                     &ctx->scratch_out, &ctx->qpsteps, &ctx->fupper, &ctx->probsteps, &ctx->routes, &ctx->psg_w, &ctx->psg_cost,
-                    &ctx->psg_skip, &ctx->th0, &ctx->thg, &ctx->zslab};
+                    &ctx->psg_skip, &ctx->th0, &ctx->thg, &ctx->zslab, &ctx->cont};
   for (DevBuf *b : bufs) free_buf(*b);
   if (ctx->dQblk) cudaFree(ctx->dQblk);
   double *ds[] = {ctx->dQQraw, ctx->dQQ, ctx->dG, ctx->dgn, ctx->dGI, ctx->dgnI, ctx->dlim, ctx->dumax, ctx->dworkL, ctx->dworkY};
@@ -453,7 +457,8 @@ static int solve_device(cfs_ctx *ctx, int B, int solver, int grad, const double 
   if ((rc = ensure(ctx, ctx->flags, sizeof(int) * B))) return rc;
   if ((rc = ensure(ctx, ctx->listA, sizeof(int) * B))) return rc;
   if ((rc = ensure(ctx, ctx->listB, sizeof(int) * B))) return rc;
-  if ((rc = ensure(ctx, ctx->counters, sizeof(int) * 8))) return rc;
+  if ((rc = ensure(ctx, ctx->counters, sizeof(int) * 16))) return rc;
+  if ((rc = ensure(ctx, ctx->cont, sizeof(int) * 3 * (size_t)B))) return rc;
   if ((rc = ensure(ctx, ctx->qpsteps, sizeof(long long) * 32))) return rc;
 
   SolveArgs a;
@@ -506,13 +511,14 @@ static int solve_device(cfs_ctx *ctx, int B, int solver, int grad, const double 
   }
   int grid = fused ? (warp ? warp_max_grid(a, ctx->device, ctx->warp_cfg) : fused_max_grid(a, ctx->device, 0))
                    : qp_max_grid(a, ctx->device);
-  int grid_heavy = fused ? fused_max_grid(a, ctx->device, 1) : 0;
+  const int heavy_tier = ctx->heavy_cfg ? 2 : 1;
+  int grid_heavy = fused ? fused_max_grid(a, ctx->device, heavy_tier) : 0;
   if (grid <= 0 || (fused && grid_heavy <= 0))
     return fail(ctx, CFS_E_CUDA, "solver kernel does not fit on this device (shared memory)");
   {
     int sms = 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
-    if (grid > 8 * sms) grid = 8 * sms;
+    if (grid > 16 * sms) grid = 16 * sms;
   }
   if (warp) {
     const int wpc = warp_warps_per_cta(ctx->warp_cfg);
@@ -525,6 +531,7 @@ static int solve_device(cfs_ctx *ctx, int B, int solver, int grad, const double 
   if (grid < 1) grid = 1;
   if (grid_heavy > B) grid_heavy = B;
   if (fused && ctx->heavy_grid > 0 && grid_heavy > ctx->heavy_grid) grid_heavy = ctx->heavy_grid;
+  const int grid_heavy2 = grid_heavy > 32 ? 32 : grid_heavy;  // second heavy launch of the screened pipeline: late escalations
   if (fused && ctx->bulk_grid > 0 && grid > ctx->bulk_grid) grid = ctx->bulk_grid;
   if ((rc = ensure(ctx, ctx->slab, sizeof(double) * (size_t)n * n * (grid > grid_heavy ? grid : grid_heavy)))) return rc;
   a.slab = ptr<double>(ctx->slab);
@@ -538,7 +545,7 @@ static int solve_device(cfs_ctx *ctx, int B, int solver, int grad, const double 
   }
   int launches = 0;
   CU(cudaEventRecord(ctx->ev_a, st));
-  CU(cudaMemsetAsync(cnt, 0, sizeof(int) * 8, st));
+  CU(cudaMemsetAsync(cnt, 0, sizeof(int) * 16, st));
   CU(cudaMemsetAsync(ctx->qpsteps.p, 0, sizeof(long long) * 32, st));
   CU(cudaMemsetAsync(ctx->probsteps.p, 0, sizeof(int) * B, st));
   a.list_cur = ptr<int>(ctx->listA); a.count_cur = cnt + 0;
@@ -557,20 +564,52 @@ static int solve_device(cfs_ctx *ctx, int B, int solver, int grad, const double 
       launches += 2;
       a.order = ptr<int>(ctx->listB);
     }
+    const bool screen = warp && ctx->screen && !ctx->heavy_skip;
+    const bool side = ctx->heavy_stream && ctx->heavy_prio && !detail;  // heavy tier on its own highest-priority stream
     if (detail) CU(cudaEventRecord(ctx->ev[0], st));
-    CU(warp ? launch_warp(a, grid, ctx->warp_cfg, st) : launch_fused(a, grid, 0, st)); ++launches;  // bulk tier: every problem
-    if (detail) CU(cudaEventRecord(ctx->ev[1], st));
-    // heavy tier: the (device-side) escalation list, usually < 1 % of the problems.  It runs on a highest-priority stream
-    // so that, with several contexts in flight, its few CTAs (one per SM) are placed before another context's bulk tier
-    // refills the SMs.
-    if (ctx->heavy_stream && ctx->heavy_prio && !detail) {
-      CU(cudaEventRecord(ctx->ev_bulk, st));
-      CU(cudaStreamWaitEvent(ctx->heavy_stream, ctx->ev_bulk, 0));
-      CU(launch_fused(a, grid_heavy, 1, ctx->heavy_stream)); ++launches;
-      CU(cudaEventRecord(ctx->ev_heavy, ctx->heavy_stream));
-      CU(cudaStreamWaitEvent(st, ctx->ev_heavy, 0));
+    if (screen) {
+      // Screening pass: outer iteration 1 of every problem.  The long dual chains (almost all of them infeasibility
+      // certificates of the FIRST linearisation) reach the heavy tier ~0.3 ms into the batch and run concurrently with the
+      // rest of the bulk tier instead of after it; everything unfinished continues from iteration 2 in the second launch.
+      SolveArgs a1 = a, a2 = a;
+      int *ext = ptr<int>(ctx->cont);
+      a1.phase = 1;
+      a1.cont_list = a2.cont_list = ext;
+      a1.touch = a2.touch = ext + B;
+      a1.cont_count = a2.cont_count = cnt + 6;
+      CU(launch_warp(a1, grid, ctx->warp_cfg, st)); ++launches;
+      a2.phase = 2;
+      a2.work_counter = cnt + 7;
+      a2.esc_list = ext + 2 * (size_t)B;  // late escalations (working sets that outgrow the warp tier in later iterations)
+      a2.esc_count = cnt + 8;
+      a2.work_counter2 = cnt + 9;
+      if (side) {
+        CU(cudaEventRecord(ctx->ev_bulk, st));
+        CU(cudaStreamWaitEvent(ctx->heavy_stream, ctx->ev_bulk, 0));
+        CU(launch_fused(a1, grid_heavy, heavy_tier, ctx->heavy_stream)); ++launches;
+        CU(cudaEventRecord(ctx->ev_heavy, ctx->heavy_stream));
+      }
+      CU(launch_warp(a2, grid, ctx->warp_cfg, st)); ++launches;
+      if (detail) CU(cudaEventRecord(ctx->ev[1], st));
+      if (!side) { CU(launch_fused(a1, grid_heavy, heavy_tier, st)); ++launches; }
+      CU(launch_fused(a2, grid_heavy2, heavy_tier, st)); ++launches;
+      if (side) CU(cudaStreamWaitEvent(st, ctx->ev_heavy, 0));
     } else {
-      CU(launch_fused(a, grid_heavy, 1, st)); ++launches;
+      CU(warp ? launch_warp(a, grid, ctx->warp_cfg, st) : launch_fused(a, grid, 0, st)); ++launches;  // bulk tier: every problem
+      if (detail) CU(cudaEventRecord(ctx->ev[1], st));
+      // heavy tier: the (device-side) escalation list, usually < 1 % of the problems.  It runs on a highest-priority stream
+      // so that, with several contexts in flight, its few CTAs (one per SM) are placed before another context's bulk tier
+      // refills the SMs.
+      if (ctx->heavy_skip) {
+      } else if (side) {
+        CU(cudaEventRecord(ctx->ev_bulk, st));
+        CU(cudaStreamWaitEvent(ctx->heavy_stream, ctx->ev_bulk, 0));
+        CU(launch_fused(a, grid_heavy, heavy_tier, ctx->heavy_stream)); ++launches;
+        CU(cudaEventRecord(ctx->ev_heavy, ctx->heavy_stream));
+        CU(cudaStreamWaitEvent(st, ctx->ev_heavy, 0));
+      } else {
+        CU(launch_fused(a, grid_heavy, heavy_tier, st)); ++launches;
+      }
     }
     if (detail) CU(cudaEventRecord(ctx->ev[2], st));
     ctx->fused_last = true;
@@ -1181,7 +1220,10 @@ extern "C" int cfs_set_option(cfs_ctx *ctx, const char *name, int value) {
   if (strcmp(name, "heavy_prio") == 0) { ctx->heavy_prio = value; return 0; }
   if (strcmp(name, "lpt") == 0) { ctx->lpt = value; return 0; }
   if (strcmp(name, "warp") == 0) { ctx->use_warp = value; return 0; }
-  if (strcmp(name, "warp_cfg") == 0) { ctx->warp_cfg = value ? 1 : 0; return 0; }
+  if (strcmp(name, "screen") == 0) { ctx->screen = value; return 0; }
+  if (strcmp(name, "heavy_cfg") == 0) { ctx->heavy_cfg = value; return 0; }
+  if (strcmp(name, "heavy_skip") == 0) { ctx->heavy_skip = value; return 0; }
+  if (strcmp(name, "warp_cfg") == 0) { ctx->warp_cfg = value; return 0; }
   if (strcmp(name, "warp_zs") == 0) { ctx->warp_zs = value; return 0; }
   return fail(ctx, CFS_E_ARG, "cfs_set_option: unknown option '%s'", name);
 }

@@ -129,6 +129,11 @@ struct SolveArgs {
   // warp-per-problem bulk tier (k_warp.cu)
   double *zslab;              // per-warp overflow of the direction cache: (WQ_QZ - warp_zs) * n doubles per resident warp
   int warp_zs;                // direction slots kept in shared memory
+  // phase 0: every problem start to finish.  phase 1 ("screen"): outer iteration 1 only; problems that are not finished go
+  // to cont_list.  phase 2: resume the problems of cont_list from outer iteration 2 (state in x / u / iters / touch).
+  int phase;
+  int *cont_list, *cont_count;
+  int *touch;                 // B: CFS_FLAG_TOUCH of the problems in cont_list
 };
 cudaError_t launch_solve_init(const SolveArgs &a, cudaStream_t s);
 cudaError_t launch_v0(const SolveArgs &a, cudaStream_t s);

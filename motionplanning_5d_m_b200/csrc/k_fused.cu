@@ -58,8 +58,8 @@ __host__ __device__ inline FusedLayout fused_layout(int n, int nj, int OH, int m
   return L;
 }
 
-template <int NJ, int NT, int QS, int MINB, int QZ>
-__global__ void __launch_bounds__(NT, MINB) k_cfs_fused(SolveArgs a) {
+template <int NJ, int NT, int QS, int MINB, int QZ, int MAXREG = (MINB == 1 ? 255 : 168)>
+__global__ void __launch_bounds__(NT) __maxnreg__(MAXREG) k_cfs_fused(SolveArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int n = a.n, nj = NJ, H = a.H, np = 3 * n, OH = a.nobs * H, m = OH + 4 * n, N = 2 * n;
   const int tid = threadIdx.x;
@@ -297,9 +297,12 @@ __global__ void __launch_bounds__(NT, MINB) k_cfs_fused(SolveArgs a) {
 
 static bool fused_supported_nj(int nj) { return nj == 2 || nj == 5; }
 
+// tier 0: bulk (CTA per problem); tier 1: heavy, 144 x 144 inverse on chip (a whole SM per CTA); tier 2: "slim" heavy,
+// FUSED_SLIM_QS^2 on chip and the rest spilled to the global slab, 168 registers: leaves room for bulk warps on the same SM
+#define FUSED_SLIM_QS 64
 static void tier_cfg(int tier, int &nt, int &qs, int &qz) {
   nt = tier ? FUSED_HEAVY_NT : FUSED_BULK_NT;
-  qs = tier ? FUSED_HEAVY_QS : FUSED_BULK_QS;
+  qs = tier == 2 ? FUSED_SLIM_QS : (tier ? FUSED_HEAVY_QS : FUSED_BULK_QS);
   qz = tier ? 0 : FUSED_BULK_QZ;
 }
 
@@ -313,7 +316,7 @@ size_t fused_smem_bytes(const SolveArgs &a, int tier) {
 bool fused_supported(const SolveArgs &a) {
   if (!fused_supported_nj(a.nj)) return false;
   const int OH = a.nobs * a.H;
-  for (int tier = 0; tier < 2; ++tier) {
+  for (int tier = 0; tier < 3; ++tier) {
     int nt, qs, qz;
     tier_cfg(tier, nt, qs, qz);
     // the gradient-phase scratch must fit into the QP scratch span it aliases, and the CTA into one SM's shared memory
@@ -338,24 +341,31 @@ int fused_max_grid(const SolveArgs &a, int device, int tier) {
   if (tier == 0) {
     if (a.nj == 2) return grid_of(k_cfs_fused<2, FUSED_BULK_NT, FUSED_BULK_QS, 3, FUSED_BULK_QZ>, FUSED_BULK_NT, smem, device);
     if (a.nj == 5) return grid_of(k_cfs_fused<5, FUSED_BULK_NT, FUSED_BULK_QS, 3, FUSED_BULK_QZ>, FUSED_BULK_NT, smem, device);
-  } else {
+  } else if (tier == 1) {
     if (a.nj == 2) return grid_of(k_cfs_fused<2, FUSED_HEAVY_NT, FUSED_HEAVY_QS, 1, 0>, FUSED_HEAVY_NT, smem, device);
     if (a.nj == 5) return grid_of(k_cfs_fused<5, FUSED_HEAVY_NT, FUSED_HEAVY_QS, 1, 0>, FUSED_HEAVY_NT, smem, device);
+  } else {
+    if (a.nj == 2) return grid_of(k_cfs_fused<2, FUSED_HEAVY_NT, FUSED_SLIM_QS, 1, 0, 168>, FUSED_HEAVY_NT, smem, device);
+    if (a.nj == 5) return grid_of(k_cfs_fused<5, FUSED_HEAVY_NT, FUSED_SLIM_QS, 1, 0, 168>, FUSED_HEAVY_NT, smem, device);
   }
   return 0;
 }
 
 cudaError_t launch_fused(const SolveArgs &a_in, int grid, int tier, cudaStream_t st) {
   SolveArgs a = a_in;
-  a.tier = tier;
+  a.tier = tier ? 1 : 0;
   const size_t smem = fused_smem_bytes(a, tier);
   if (tier == 0) {
     if (a.nj == 2) k_cfs_fused<2, FUSED_BULK_NT, FUSED_BULK_QS, 3, FUSED_BULK_QZ><<<grid, FUSED_BULK_NT, smem, st>>>(a);
     else if (a.nj == 5) k_cfs_fused<5, FUSED_BULK_NT, FUSED_BULK_QS, 3, FUSED_BULK_QZ><<<grid, FUSED_BULK_NT, smem, st>>>(a);
     else return cudaErrorInvalidValue;
-  } else {
+  } else if (tier == 1) {
     if (a.nj == 2) k_cfs_fused<2, FUSED_HEAVY_NT, FUSED_HEAVY_QS, 1, 0><<<grid, FUSED_HEAVY_NT, smem, st>>>(a);
     else if (a.nj == 5) k_cfs_fused<5, FUSED_HEAVY_NT, FUSED_HEAVY_QS, 1, 0><<<grid, FUSED_HEAVY_NT, smem, st>>>(a);
+    else return cudaErrorInvalidValue;
+  } else {
+    if (a.nj == 2) k_cfs_fused<2, FUSED_HEAVY_NT, FUSED_SLIM_QS, 1, 0, 168><<<grid, FUSED_HEAVY_NT, smem, st>>>(a);
+    else if (a.nj == 5) k_cfs_fused<5, FUSED_HEAVY_NT, FUSED_SLIM_QS, 1, 0, 168><<<grid, FUSED_HEAVY_NT, smem, st>>>(a);
     else return cudaErrorInvalidValue;
   }
   return cudaGetLastError();

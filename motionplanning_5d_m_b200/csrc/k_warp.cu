@@ -133,8 +133,8 @@ __host__ __device__ inline WarpSmem warp_smem(int n, int nj, int OH, int zs, int
   return L;
 }
 
-template <int NJ, int NT, int MINB, int OC>
-__global__ void __launch_bounds__(NT, MINB) k_cfs_warp(SolveArgs a) {
+template <int NJ, int NT, int MAXREG, int OC>
+__global__ void __launch_bounds__(NT) __maxnreg__(MAXREG) k_cfs_warp(SolveArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr int WPC = NT / 32;
   const int n = a.n, H = a.H, O = a.nobs, OH = O * H, m = OH + 4 * n, N = 2 * n;
@@ -153,12 +153,14 @@ __global__ void __launch_bounds__(NT, MINB) k_cfs_warp(SolveArgs a) {
   long long steps_total = 0;
   int qmax_seen = 0;
 
+  const bool resume = a.phase == 2;
+  const int count = resume ? *a.cont_count : a.B;
   for (;;) {
     int slot = 0;
     if (lane == 0) slot = atomicAdd(a.work_counter, 1);
     slot = __shfl_sync(FULLMASK, slot, 0);
-    if (slot >= a.B) break;
-    const int b = a.order ? a.order[slot] : slot;
+    if (slot >= count) break;
+    const int b = resume ? a.cont_list[slot] : (a.order ? a.order[slot] : slot);
     const double *x0 = a.x0 + (size_t)b * 2 * NJ;
     const double *xref = a.xref + (size_t)b * N;
     double *ub = a.u + (size_t)b * n;
@@ -169,34 +171,41 @@ __global__ void __launch_bounds__(NT, MINB) k_cfs_warp(SolveArgs a) {
     double part = 0.0;
 #pragma unroll 2
     for (int e = lane; e < N; e += 32) {
-      const double xv = xref[e];
+      const double xv = resume ? xb[e] : xref[e];  // resume: x_ of the completed iterations
       part += (xv - 1.0) * (xv - 1.0);
-      xb[e] = xv;
+      if (!resume) xb[e] = xv;
       const int i = e / (2 * NJ), r = e - i * 2 * NJ;
       if (r < NJ) s.th[i * NJ + r] = xv;
     }
 #pragma unroll 2
     for (int c = lane; c < n; c += 32) {
-      ub[c] = 0.0;
+      if (!resume) ub[c] = 0.0;
       s.u0s[c] = a.u0[(size_t)b * n + c];
     }
+    if (!resume) {
 #pragma unroll 1
-    for (int e = lane; e < a.max_outer; e += 32) {
-      a.cost_hist[(size_t)b * a.max_outer + e] = qnan;
-      if (a.e_u_hist) a.e_u_hist[(size_t)b * a.max_outer + e] = qnan;
+      for (int e = lane; e < a.max_outer; e += 32) {
+        a.cost_hist[(size_t)b * a.max_outer + e] = qnan;
+        if (a.e_u_hist) a.e_u_hist[(size_t)b * a.max_outer + e] = qnan;
+      }
     }
     if (lane < 2 * NJ) s.x0s[lane] = x0[lane];
     const double nrm0 = sqrt(warp_sum(part));
     const double cost0 = a.cost0[b];
     const double fupper = (a.has_bounds && a.fupper) ? a.fupper[b] : INFINITY;
     int status = -1, iters = 0, touched = 0, steps_prob = 0;
-    if (nrm0 < a.eps_outer)
+    if (resume) {
+      iters = a.iters[b];
+      touched = lane == 0 ? a.touch[b] : 0;
+      steps_prob = a.prob_steps ? a.prob_steps[b] : 0;
+    } else if (nrm0 < a.eps_outer) {
       status = 0;
-    else if (1 > a.max_outer)
+    } else if (1 > a.max_outer) {
       status = 1;
+    }
     __syncwarp();
 
-    for (int it = 1; status < 0; ++it) {
+    for (int it = iters + 1; status < 0; ++it) {
       // ---- get_con: distance + num_jac gradient of every waypoint, rows written in place (CFS_FANUC.m:110-124) ----
 #pragma unroll 1
       for (int i = lane; i < H; i += 32) {
@@ -254,7 +263,7 @@ __global__ void __launch_bounds__(NT, MINB) k_cfs_warp(SolveArgs a) {
 #pragma unroll 1
         for (int w = 0; w < q; ++w) {
           const int cw = s.act[w];
-          pc += s.lam[w] * (w_row_dot<NJ>(cw, s.u0s, s, P) - w_row_rhs<NJ>(cw, s, P));  // lambda_w * violation at u0
+          pc += s.lam[w] * (W_ROW_DOT(cw, s.u0s) - w_row_rhs<NJ>(cw, s, P));  // lambda_w * violation at u0
         }
         cost = cost0 + 0.5 * pc;
       }
@@ -318,15 +327,21 @@ __global__ void __launch_bounds__(NT, MINB) k_cfs_warp(SolveArgs a) {
       else if (it + 1 > a.max_outer)
         status = 1;  // MAX_ITER (EVAL.m:69-72)
       __syncwarp();
+      if (a.phase == 1) break;  // screening pass: one outer iteration
     }
 
     // ---- results: u and x_ of the last completed iteration are already in global memory ----
     const int any_touch = __any_sync(FULLMASK, touched);
     if (lane == 0) {
       a.iters[b] = iters;
-      a.status[b] = status | (any_touch ? 0x100 : 0);
       if (a.prob_steps) a.prob_steps[b] = steps_prob;
-      if (status == 4) a.esc_list[atomicAdd(a.esc_count, 1)] = b;
+      if (status < 0) {  // screening pass: the problem continues in phase 2
+        a.touch[b] = any_touch ? 0x100 : 0;
+        a.cont_list[atomicAdd(a.cont_count, 1)] = b;
+      } else {
+        a.status[b] = status | (any_touch ? 0x100 : 0);
+        if (status == 4) a.esc_list[atomicAdd(a.esc_count, 1)] = b;
+      }
     }
   }
   if (lane == 0) {
@@ -336,41 +351,40 @@ __global__ void __launch_bounds__(NT, MINB) k_cfs_warp(SolveArgs a) {
 }
 
 // ---- host side ------------------------------------------------------------------------------------------------------------
-// configurations: 0 = 12 warps in one CTA per SM (<= 168 registers), 1 = 3 CTAs of 3 warps per SM (<= 224 registers)
-static void warp_cfg(int cfg, int &nt, int &minb) {
-  nt = cfg == 1 ? 96 : 384;
-  minb = cfg == 1 ? 3 : 1;
-}
+// CTA shapes (warps of one CTA share nothing but the staged tables; small CTAs let another context's launch move into an SM
+// as soon as a few warps have drained):  cfg 0: 12 warps x 1 CTA/SM, 1: 3 warps x 3, 2: 4 warps x 3, 3: 1 warp x 10, 4: 2 warps x 5
+#define WARP_NCFG 5
+static const int kWarpNT[WARP_NCFG] = {384, 96, 128, 32, 64};
 
 size_t warp_smem_bytes(const SolveArgs &a, int cfg) {
-  int nt, minb;
-  warp_cfg(cfg, nt, minb);
-  return warp_smem(a.n, a.nj, a.nobs * a.H, a.warp_zs, nt / 32).total;
+  return warp_smem(a.n, a.nj, a.nobs * a.H, a.warp_zs, kWarpNT[cfg] / 32).total;
 }
 
 bool warp_supported(const SolveArgs &a, int cfg) {
+  if (cfg < 0 || cfg >= WARP_NCFG) return false;
   if (a.nj != 2 && a.nj != 5) return false;
-  if (a.H > 64) return false;  // two waypoints per lane in the prefix sums
+  if (a.H > 64 || a.n > 32 * W_NC) return false;  // two waypoints per lane in the prefix sums; W_NC controls per lane
   if (a.warp_zs < 1 || a.warp_zs > WQ_QZ) return false;
   return warp_smem_bytes(a, cfg) <= 227 * 1024;
 }
 
-int warp_warps_per_cta(int cfg) {
-  int nt, minb;
-  warp_cfg(cfg, nt, minb);
-  return nt / 32;
-}
+int warp_warps_per_cta(int cfg) { return kWarpNT[cfg] / 32; }
 
 typedef void (*WarpKernel)(SolveArgs);
-static WarpKernel warp_kernel(int nj, int cfg, int nobs) {
-  const bool two = nobs > 1;
-  if (cfg == 1) {
-    if (nj == 2) return two ? k_cfs_warp<2, 96, 3, 2> : k_cfs_warp<2, 96, 3, 1>;
-    if (nj == 5) return two ? k_cfs_warp<5, 96, 3, 2> : k_cfs_warp<5, 96, 3, 1>;
-  } else {
-    if (nj == 2) return two ? k_cfs_warp<2, 384, 1, 2> : k_cfs_warp<2, 384, 1, 1>;
-    if (nj == 5) return two ? k_cfs_warp<5, 384, 1, 2> : k_cfs_warp<5, 384, 1, 1>;
+template <int NJ>
+static WarpKernel warp_kernel_nj(int cfg, bool two) {
+  switch (cfg) {
+    case 0: return two ? k_cfs_warp<NJ, 384, 168, 2> : k_cfs_warp<NJ, 384, 168, 1>;
+    case 1: return two ? k_cfs_warp<NJ, 96, 224, 2> : k_cfs_warp<NJ, 96, 224, 1>;
+    case 2: return two ? k_cfs_warp<NJ, 128, 168, 2> : k_cfs_warp<NJ, 128, 168, 1>;
+    case 3: return two ? k_cfs_warp<NJ, 32, 200, 2> : k_cfs_warp<NJ, 32, 200, 1>;
+    case 4: return two ? k_cfs_warp<NJ, 64, 200, 2> : k_cfs_warp<NJ, 64, 200, 1>;
   }
+  return nullptr;
+}
+static WarpKernel warp_kernel(int nj, int cfg, int nobs) {
+  if (nj == 2) return warp_kernel_nj<2>(cfg, nobs > 1);
+  if (nj == 5) return warp_kernel_nj<5>(cfg, nobs > 1);
   return nullptr;
 }
 
@@ -378,20 +392,17 @@ int warp_max_grid(const SolveArgs &a, int device, int cfg) {
   const size_t smem = warp_smem_bytes(a, cfg);
   WarpKernel k = warp_kernel(a.nj, cfg, a.nobs);
   if (!k) return 0;
-  int nt, minb, sms = 0, per = 0;
-  warp_cfg(cfg, nt, minb);
+  int sms = 0, per = 0;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
   if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k, nt, smem);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k, kWarpNT[cfg], smem);
   return sms * per;
 }
 
 cudaError_t launch_warp(const SolveArgs &a, int grid, int cfg, cudaStream_t st) {
   WarpKernel k = warp_kernel(a.nj, cfg, a.nobs);
   if (!k) return cudaErrorInvalidValue;
-  int nt, minb;
-  warp_cfg(cfg, nt, minb);
-  k<<<grid, nt, warp_smem_bytes(a, cfg), st>>>(a);
+  k<<<grid, kWarpNT[cfg], warp_smem_bytes(a, cfg), st>>>(a);
   return cudaGetLastError();
 }
 

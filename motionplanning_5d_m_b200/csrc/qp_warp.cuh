@@ -129,14 +129,14 @@ __device__ __forceinline__ double w_row_rhs(int cid, const WView &s, const WDims
 //   obstacle row (j,i):        sum_{jj<=i} sum_k cv[k] (0.5+(i-jj)) dt^2 vec[jj,k]      (CFS_FANUC.m:121, B_theta blocks)
 //   velocity row (i,k), +-:    +- dt sum_{jj<=i} vec[jj,k]                               (CFS_FANUC.m:126-129)
 //   control row c, +-:         +- vec[c]                                                  (lb/ub of CFS_FANUC.m:85)
-// Every lane returns the same value.
+// Every lane returns the same value.  Not inlined (four call sites); every argument is a scalar, so nothing goes through
+// local memory.
 template <int NJ>
-static __device__ __noinline__ double w_row_dot(int cid, const double *vec, const WView &s, const WDims &P) {
+static __device__ __noinline__ double w_row_dot(int cid, const double *vec, const double *ocoef, int OH, int H, int n, double dt) {
   const int lane = threadIdx.x & 31;
-  const double dt = P.dt;
-  if (cid < P.OH) {
-    const int i = w_wp_of(cid, P.H);
-    const double *cv = s.ocoef + (size_t)cid * NJ;
+  if (cid < OH) {
+    const int i = w_wp_of(cid, H);
+    const double *cv = ocoef + (size_t)cid * NJ;
     const int lim = (i + 1) * NJ;
     double acc = 0.0;
 #pragma unroll 2
@@ -146,27 +146,36 @@ static __device__ __noinline__ double w_row_dot(int cid, const double *vec, cons
     }
     return warp_sum(acc);
   }
-  const int e = cid - P.OH, pr = e >> 1;
+  const int e = cid - OH, pr = e >> 1;
   const double sgn = (e & 1) ? -1.0 : 1.0;
-  if (pr < P.n) {
+  if (pr < n) {
     const int i = pr / NJ, k = pr - i * NJ;
     double acc = 0.0;
     for (int jj = lane; jj <= i; jj += 32) acc += vec[jj * NJ + k];
     return sgn * dt * warp_sum(acc);
   }
-  return sgn * vec[pr - P.n];
+  return sgn * vec[pr - n];
 }
+#define W_ROW_DOT(cid, vec) w_row_dot<NJ>(cid, vec, s.ocoef, P.OH, P.H, P.n, P.dt)
 
-// primal recovery u = u0 - sum_w lambda_w z_w
-static __device__ __noinline__ void w_refresh(const WView &s, const WDims &P, int q) {
+// primal recovery u = u0 - sum_w lambda_w z_w (n <= 32 * W_NC)
+#define W_NC 10
+__device__ __forceinline__ void w_refresh(const WView &s, const WDims &P, int q) {
   const int lane = threadIdx.x & 31, n = P.n;
-#pragma unroll 2
-  for (int c = lane; c < n; c += 32) {
-    double acc = 0.0;
+  double acc[W_NC];
+#pragma unroll
+  for (int j = 0; j < W_NC; ++j) acc[j] = 0.0;
 #pragma unroll 1
-    for (int w = 0; w < q; ++w) acc += s.lam[w] * wz(s, s.zslot[w], n)[c];
-    s.uq[c] = s.u0s[c] - acc;
+  for (int w = 0; w < q; ++w) {
+    const double lw = s.lam[w];
+    const double *z = wz(s, s.zslot[w], n) + lane;
+#pragma unroll
+    for (int j = 0; j < W_NC; ++j)
+      if (lane + 32 * j < n) acc[j] += lw * z[32 * j];
   }
+#pragma unroll
+  for (int j = 0; j < W_NC; ++j)
+    if (lane + 32 * j < n) s.uq[lane + 32 * j] = s.u0s[lane + 32 * j] - acc[j];
   __syncwarp();
 }
 
@@ -197,69 +206,49 @@ __device__ __forceinline__ void w_prefix2(double a0, double a1, double &s0, doub
 
 // (1) most violated inactive row at the current uq, normalised by its QQ^-1 norm (same rule as qp_solve): returns its id
 // (-1: none) and its slack.  B_theta u / B_omega u come from prefix sums held in registers (H <= 64: one pair of waypoints
-// per lane); obstacles are taken two at a time, the velocity / control rows ride along with the first pair.
+// per lane, the NJ joints' scans interleaved); obstacles are taken two at a time.  While phase-A masking is on, the
+// candidates of the masked levels are tracked in the same pass: when no unmasked row is violated, the next level is
+// unmasked and its most violated row taken, exactly as a rescan with the same u would do.
 template <int NJ>
-static __device__ __noinline__ int w_scan(const WView &s, const WDims &P, double &slack_out) {
+__device__ __forceinline__ int w_scan(const WView &s, const WDims &P, int &masked, double &slack_out) {
   const int lane = threadIdx.x & 31, n = P.n, H = P.H, OH = P.OH, O = P.O;
   const double dt = P.dt, dt2 = dt * dt;
-  double best = 0.0, bsl = 0.0;
-  int bidx = -1;
+  double best = 0.0, bsl = 0.0, best2 = 0.0, bsl2 = 0.0, best3 = 0.0, bsl3 = 0.0;
+  int bidx = -1, bidx2 = -1, bidx3 = -1;
   const int i0 = 2 * lane, i1 = i0 + 1;
   const bool v0 = i0 < H, v1 = i1 < H;
 #pragma unroll 1
   for (int j0 = 0; j0 < (O > 0 ? O : 1); j0 += 2) {
     double accA0 = 0.0, accA1 = 0.0, accB0 = 0.0, accB1 = 0.0;
     const bool hasA = j0 < O, hasB = j0 + 1 < O;
-#pragma unroll 1
+    const double *cA = s.ocoef + ((size_t)j0 * H + i0) * NJ, *cB = cA + (size_t)H * NJ;
+#pragma unroll
     for (int k = 0; k < NJ; ++k) {
       const double a0 = v0 ? s.uq[i0 * NJ + k] : 0.0, a1 = v1 ? s.uq[i1 * NJ + k] : 0.0;
       double s0, s1, t0, t1;
       w_prefix2(a0, a1, s0, s1, t0, t1);
       const double th0 = dt2 * (0.5 * s0 + t0), th1 = dt2 * (0.5 * s1 + t1);
       if (hasA) {
-        if (v0) accA0 += s.ocoef[((size_t)j0 * H + i0) * NJ + k] * th0;
-        if (v1) accA1 += s.ocoef[((size_t)j0 * H + i1) * NJ + k] * th1;
+        if (v0) accA0 += cA[k] * th0;
+        if (v1) accA1 += cA[NJ + k] * th1;
       }
       if (hasB) {
-        if (v0) accB0 += s.ocoef[((size_t)(j0 + 1) * H + i0) * NJ + k] * th0;
-        if (v1) accB1 += s.ocoef[((size_t)(j0 + 1) * H + i1) * NJ + k] * th1;
+        if (v0) accB0 += cB[k] * th0;
+        if (v1) accB1 += cB[NJ + k] * th1;
       }
-      if (j0 == 0 && (P.has_vel || P.has_bnd)) {
-#pragma unroll 1
+      if (j0 == 0 && P.has_vel) {  // velocity rows +-(w0 + (B_omega u)(i,k)) <= lim   (CFS_FANUC.m:126-129)
+        const double lim = __ldg(P.lim + k), w0 = s.x0s[NJ + k];
+        const double tol = 1e-11 * (1.0 + lim);
+#pragma unroll
         for (int h = 0; h < 2; ++h) {
-          if (!(h ? v1 : v0)) continue;
-          const int e = (h ? i1 : i0) * NJ + k;
-#pragma unroll 1
-          for (int kind = 0; kind < 2; ++kind) {
-            // kind 0: velocity rows +-(B_omega u)(i,k) <= lim -+ w0 (CFS_FANUC.m:126-129); kind 1: control rows +-u <= MAX_input
-            if (kind ? !P.has_bnd : !P.has_vel) continue;
-            double vv, hi, lo, sc;
-            if (kind == 0) {
-              const double lim = __ldg(P.lim + k), w0 = s.x0s[NJ + k];
-              vv = dt * (h ? s1 : s0);
-              hi = lim - w0;
-              lo = lim + w0;
-              sc = lim;
-            } else {
-              vv = h ? a1 : a0;
-              hi = lo = sc = __ldg(P.umax + e);
-            }
-            const double up = hi - vv, dn = lo + vv;
-            const double tol = 1e-11 * (1.0 + sc);
-            if (up < -tol || dn < -tol) {
-              const int pr = kind ? n + e : e;
-              const double gd = __ldg(P.gdiag + n + pr), sg = gd * gd;
-              const int cu = OH + 2 * pr;
-              if (sg > 0.0) {
-                if (up < -tol && !s.inact[cu]) {
-                  const double key = -(up * up) / sg;
-                  if (key < best || bidx < 0) { best = key; bidx = cu; bsl = up; }
-                }
-                if (dn < -tol && !s.inact[cu + 1]) {
-                  const double key = -(dn * dn) / sg;
-                  if (key < best || bidx < 0) { best = key; bidx = cu + 1; bsl = dn; }
-                }
-              }
+          const double vw = w0 + dt * (h ? s1 : s0);
+          const double sl = lim - fabs(vw);  // slack of the side that can be violated
+          if ((h ? v1 : v0) && sl < -tol) {
+            const int e = (h ? i1 : i0) * NJ + k, cu = OH + 2 * e + (vw < 0.0 ? 1 : 0);
+            const double gd = __ldg(P.gdiag + n + e), sg = gd * gd;
+            if (sg > 0.0 && !s.inact[cu]) {
+              const double key = -(sl * sl) / sg;
+              if (key < best || bidx < 0) { best = key; bidx = cu; bsl = sl; }
             }
           }
         }
@@ -273,17 +262,56 @@ static __device__ __noinline__ int w_scan(const WView &s, const WDims &P, double
       if (!(second ? v1 : v0)) continue;
       const int cid = (j0 + (obsB ? 1 : 0)) * H + (second ? i1 : i0);
       const double sg = s.onrm[cid];
-      if (s.inact[cid] || !(sg > 0.0)) continue;
+      const int lvl = s.inact[cid];
+      if (lvl == 1 || !(sg > 0.0)) continue;
       const double val = obsB ? (second ? accB1 : accB0) : (second ? accA1 : accA0);
       const double rhs = s.orhs[cid];
       const double sl = rhs - val;
       if (sl < -1e-11 * (1.0 + fabs(rhs))) {
         const double key = -(sl * sl) / sg;
-        if (key < best || bidx < 0) { best = key; bidx = cid; bsl = sl; }
+        if (lvl == 0) {
+          if (key < best || bidx < 0) { best = key; bidx = cid; bsl = sl; }
+        } else if (lvl == 2) {
+          if (key < best2 || bidx2 < 0) { best2 = key; bidx2 = cid; bsl2 = sl; }
+        } else {
+          if (key < best3 || bidx3 < 0) { best3 = key; bidx3 = cid; bsl3 = sl; }
+        }
+      }
+    }
+  }
+  if (P.has_bnd) {  // control rows +-u <= MAX_input
+#pragma unroll 1
+    for (int c = lane; c < n; c += 32) {
+      const double uv = s.uq[c], um = __ldg(P.umax + c);
+      const double sl = um - fabs(uv);
+      if (sl < -1e-11 * (1.0 + um)) {
+        const int cu = OH + 2 * (n + c) + (uv < 0.0 ? 1 : 0);
+        const double gd = __ldg(P.gdiag + 2 * n + c), sg = gd * gd;
+        if (sg > 0.0 && !s.inact[cu]) {
+          const double key = -(sl * sl) / sg;
+          if (key < best || bidx < 0) { best = key; bidx = cu; bsl = sl; }
+        }
       }
     }
   }
   warp_argmin(best, bidx, bsl);
+  while (bidx < 0 && masked) {  // this phase is feasible: unmask the next level, same working set
+    const int lvl = masked == 2 ? 2 : 3;
+#pragma unroll 1
+    for (int cid = lane; cid < OH; cid += 32)
+      if (s.inact[cid] == lvl) s.inact[cid] = 0;
+    if (lvl == 2) {
+      warp_argmin(best2, bidx2, bsl2);
+      bidx = bidx2;
+      bsl = bsl2;
+    } else {
+      warp_argmin(best3, bidx3, bsl3);
+      bidx = bidx3;
+      bsl = bsl3;
+    }
+    --masked;
+    __syncwarp();
+  }
   slack_out = bsl;
   return bidx;
 }
@@ -295,9 +323,10 @@ __device__ __forceinline__ int w_mask_antiparallel(const WView &s, const WDims &
   const int lane = threadIdx.x & 31, OH = P.OH, H = P.H;
   double best = 0.0, aux = 0.0;
   int bidx = -1;
+  unsigned apbits = 0;  // bit j: rows (cid, cid+1), cid = lane + 32 j, are anti-parallel
 #pragma unroll 1
-  for (int cid = lane; cid < OH; cid += 32) {
-    if (w_wp_of(cid, H) == H - 1) continue;
+  for (int cid = lane, j = 0; cid < OH; cid += 32, ++j) {
+    if (w_wp_of(cid, H) == H - 1) continue;  // the pair must belong to the same obstacle
     const double *a = s.ocoef + (size_t)cid * NJ, *b = a + NJ;
     double ab = 0.0, aa = 0.0, bb = 0.0;
 #pragma unroll
@@ -306,7 +335,8 @@ __device__ __forceinline__ int w_mask_antiparallel(const WView &s, const WDims &
       aa += a[k] * a[k];
       bb += b[k] * b[k];
     }
-    if (ab < 0.0 && ab * ab > 0.81 * aa * bb) {
+    if (ab < 0.0 && ab * ab > 0.81 * aa * bb) {  // cos < -0.9
+      apbits |= 1u << (j & 31);
       const double cs = ab / sqrt(aa * bb);
       if (bidx < 0 || cs < best) {
         best = cs;
@@ -320,21 +350,11 @@ __device__ __forceinline__ int w_mask_antiparallel(const WView &s, const WDims &
   for (int cid = lane; cid < OH; cid += 32) s.inact[cid] = 3;
   __syncwarp();
 #pragma unroll 1
-  for (int cid = lane; cid < OH; cid += 32) {
-    if (w_wp_of(cid, H) == H - 1) continue;
-    const double *a = s.ocoef + (size_t)cid * NJ, *b = a + NJ;
-    double ab = 0.0, aa = 0.0, bb = 0.0;
-#pragma unroll
-    for (int k = 0; k < NJ; ++k) {
-      ab += a[k] * b[k];
-      aa += a[k] * a[k];
-      bb += b[k] * b[k];
-    }
-    if (ab < 0.0 && ab * ab > 0.81 * aa * bb) {
+  for (int cid = lane, j = 0; cid < OH; cid += 32, ++j)
+    if ((apbits >> (j & 31)) & 1u) {
       s.inact[cid] = 2;
       s.inact[cid + 1] = 2;
     }
-  }
   __syncwarp();
   if (lane == 0) {
     s.inact[bidx] = 0;
@@ -360,17 +380,7 @@ __device__ __forceinline__ int wqp_solve(const WView &s, const WDims &P, double 
   while (status < 0) {
     w_refresh(s, P, q);
     double sp;
-    const int p = w_scan<NJ>(s, P, sp);
-    if (p < 0 && masked) {  // this phase is feasible: unmask the next level, same working set
-      const int lvl = masked == 2 ? 2 : 3;
-#pragma unroll 1
-      for (int cid = lane; cid < OH; cid += 32)
-        if (s.inact[cid] == lvl) s.inact[cid] = 0;
-      --masked;
-      __syncwarp();
-      polished = false;
-      continue;
-    }
+    const int p = w_scan<NJ>(s, P, masked, sp);
     if (p < 0) {
       if (q == 0 || polished || (steps <= 6 && q <= 6)) {
         status = 0;
@@ -380,7 +390,7 @@ __device__ __forceinline__ int wqp_solve(const WView &s, const WDims &P, double 
 #pragma unroll 1
       for (int w = 0; w < q; ++w) {
         const int cw = s.act[w];
-        const double val = w_row_dot<NJ>(cw, s.uq, s, P) - w_row_rhs<NJ>(cw, s, P);
+        const double val = W_ROW_DOT(cw, s.uq) - w_row_rhs<NJ>(cw, s, P);
         if (lane == 0) s.g[w] = val;
       }
       __syncwarp();
@@ -425,11 +435,16 @@ __device__ __forceinline__ int wqp_solve(const WView &s, const WDims &P, double 
       }
     }
     __syncwarp();
-    const double sigma = w_row_dot<NJ>(p, zp, s, P);
+    // sigma = c_p z_p and g_w = c_w z_p: one call site, the candidate rides along as "member q"
+    double sigma = 0.0;
 #pragma unroll 1
-    for (int w = 0; w < q; ++w) {
-      const double val = w_row_dot<NJ>(s.act[w], zp, s, P);
-      if (lane == 0) s.g[w] = val;
+    for (int w = 0; w <= q; ++w) {
+      const double val = W_ROW_DOT(w < q ? s.act[w] : p, zp);
+      if (w < q) {
+        if (lane == 0) s.g[w] = val;
+      } else {
+        sigma = val;
+      }
     }
     __syncwarp();
     double lam_p = 0.0;

@@ -165,7 +165,7 @@ def test_batch_m16ib_solve_parity(ctx, oracle, mode):
             ctx.set_option(k, v)
     assert ((ref["status"] & 0xFF) == 2).any() and ((ref["status"] & 0xFF) == 0).any()
     _compare_solve(out, ref)
-    assert ctx.stats()["launches"] == (44 if mode == "lockstep" else 6)
+    assert ctx.stats()["launches"] == (44 if mode == "lockstep" else (6 if mode == "cta" else 8))
 
 
 def test_psgcfs_main_fanuc_parity(ctx, oracle):
