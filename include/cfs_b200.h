@@ -44,7 +44,9 @@ enum { CFS_GRAD_NUMJAC = 0,    /* Lib/functions/num_jac.m (class path, CFS_FANUC
 enum { CFS_STATUS_CONVERGED = 0,  /* ||x_-x_old|| < epsilon_O                 (EVAL.m:64-67)  */
        CFS_STATUS_MAX_ITER = 1,   /* iter_O > MAX_O_ITER                      (EVAL.m:69-72)  */
        CFS_STATUS_INFEASIBLE = 2, /* QP infeasible: quadprog returns [] and the reference's rollout throws (CFS_FANUC.m:85-92) */
-       CFS_STATUS_NUMERICAL = 3 };
+       CFS_STATUS_NUMERICAL = 3,
+       CFS_STATUS_NO_ROUTE = 5 }; /* cfs_solve_routes_var: route_len < 2, i.e. the RRT seed failed (RRT_FANUC.m:201-205; routeL = 1000
+                                     in Lib/functions/s_Parallel_rrt.m:11): nothing to smooth, u = 0 */
 /* status[b] flag bits */
 #define CFS_FLAG_TOUCH 0x100 /* the |dis|<1e-4 "axes touch" branch was taken at some evaluated configuration
                                 (dist_arm_3D_Heu_2.m:22-24).  On M16iB the reference subtracts a 3x1 from a 6x1
@@ -131,6 +133,19 @@ int cfs_solve_routes(cfs_ctx *ctx, int B, int W, int solver, int grad, const dou
 int cfs_solve_routes_async(cfs_ctx *ctx, int B, int W, int solver, int grad, const double *routes, const double *noise,
                            double eps_outer, int max_outer, double alpha, double *u, double *x, double *cost_hist,
                            double *e_u_hist, int *iters, int *status);
+/* The same for routes of different lengths (one per RRT seed: Lib/functions/s_Parallel_rrt.m:16-25): routes is nj x W x B with
+ * the first route_len[b] columns of problem b valid.  route_len[b] < 2 (failed seed): status CFS_STATUS_NO_ROUTE. */
+int cfs_solve_routes_var(cfs_ctx *ctx, int B, int W, const int *route_len /*B*/, int solver, int grad, const double *routes,
+                         const double *noise, double eps_outer, int max_outer, double alpha, double *u, double *x,
+                         double *cost_hist, double *e_u_hist, int *iters, int *status);
+int cfs_solve_routes_var_async(cfs_ctx *ctx, int B, int W, const int *route_len, int solver, int grad, const double *routes,
+                               const double *noise, double eps_outer, int max_outer, double alpha, double *u, double *x,
+                               double *cost_hist, double *e_u_hist, int *iters, int *status);
+/* ... every pointer a DEVICE pointer (route_len may be NULL: all routes have W waypoints); asynchronous unless sync != 0.
+ * Chains with cfs_rrt_find_routes_device without a host round trip: the RRT -> CFS pipeline of RRTstar_CFS.m:76-195. */
+int cfs_solve_routes_device(cfs_ctx *ctx, int B, int W, const int *route_len, int solver, int grad, const double *routes,
+                            const double *noise, double eps_outer, int max_outer, double alpha, double *u, double *x,
+                            double *cost_hist, double *e_u_hist, int *iters, int *status, int sync);
 /* The resampling step alone: sampled (nj x (H+1) x B) = cubicpolytraj(route, (0:W-1)*dt, linspace(0,(W-1)*dt,H+1)). */
 int cfs_resample_routes(cfs_ctx *ctx, int B, int W, int H, const double *routes /*nj x W x B*/, double *sampled);
 /* Blocks until the context's stream is idle and collects the statistics of the batch in flight (if any). */
@@ -178,6 +193,14 @@ int cfs_rrt_find_routes(cfs_ctx *ctx, int S, int star, const double *x0, const d
                         const double *region_g, const double *region_s, const double *sample_off, const double *ratial,
                         double bi, int max_iter, const double *rnd, int nrnd, double *routes, int *route_len, int *n_nodes,
                         int *fail, int *rnd_used, double *tree_nodes, int *tree_parent, double *tree_total, double *ms_kernel);
+
+/* cfs_rrt_find_routes with every array in device memory (params = [region_g; region_s; sample_off; ratial], 4*nj doubles);
+ * asynchronous on the context stream unless sync != 0.  A failed seed reports route_len as found by the back-trace and
+ * fail = 1; use route_len_or_fail (S ints, may be NULL) to get 0 for failed / exhausted seeds, ready for
+ * cfs_solve_routes_device. */
+int cfs_rrt_find_routes_device(cfs_ctx *ctx, int S, int star, const double *x0, const double *goal, const double *goal_th,
+                               const double *params, double bi, int max_iter, const double *rnd, int nrnd, double *routes,
+                               int *route_len, int *n_nodes, int *fail, int *rnd_used, int *route_len_or_fail, int sync);
 
 /* ---- introspection (profiling / bench) ---------------------------------------------------------------- */
 typedef struct {

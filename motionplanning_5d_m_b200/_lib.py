@@ -14,13 +14,13 @@ LIB_PATH = os.path.join(_HERE, "libcfs_b200.so")
 ROBOT_KIND = {"M16iB": 0, "M200i": 1, "2L": 2}
 SOLVER_CFS, SOLVER_PSGCFS = 0, 1
 GRAD_NUMJAC, GRAD_DERIVEST = 0, 1
-STATUS_CONVERGED, STATUS_MAX_ITER, STATUS_INFEASIBLE, STATUS_NUMERICAL = 0, 1, 2, 3
+STATUS_CONVERGED, STATUS_MAX_ITER, STATUS_INFEASIBLE, STATUS_NUMERICAL, STATUS_NO_ROUTE = 0, 1, 2, 3, 5
 FLAG_TOUCH = 0x100
 
 # every symbol include/cfs_b200.h declares (tests check that the library exports all of them)
 SYMBOLS = ["cfs_create", "cfs_destroy", "cfs_last_error", "cfs_version", "cfs_set_stream", "cfs_set_option", "cfs_set_robot", "cfs_set_obstacles",
-           "cfs_set_cost", "cfs_set_cost_blocks", "cfs_solve_start_goal", "cfs_solve_start_goal_async", "cfs_solve_routes", "cfs_solve_routes_async", "cfs_resample_routes", "cfs_solve_batch", "cfs_solve_batch_async", "cfs_wait", "cfs_solve_batch_device", "cfs_dist_grad", "cfs_time_dist_grad", "cfs_get_con",
-           "cfs_nodes_feasible", "cfs_nearest_steer", "cfs_rrt_find_routes", "cfs_get_stats", "cfs_set_timing", "cfs_get_iter_times", "cfs_get_problem_steps", "cfs_get_qp_profile", "cfs_measure_fp64_peak"]
+           "cfs_set_cost", "cfs_set_cost_blocks", "cfs_solve_start_goal", "cfs_solve_start_goal_async", "cfs_solve_routes", "cfs_solve_routes_async", "cfs_solve_routes_var", "cfs_solve_routes_var_async", "cfs_solve_routes_device", "cfs_resample_routes", "cfs_solve_batch", "cfs_solve_batch_async", "cfs_wait", "cfs_solve_batch_device", "cfs_dist_grad", "cfs_time_dist_grad", "cfs_get_con",
+           "cfs_nodes_feasible", "cfs_nearest_steer", "cfs_rrt_find_routes", "cfs_rrt_find_routes_device", "cfs_get_stats", "cfs_set_timing", "cfs_get_iter_times", "cfs_get_problem_steps", "cfs_get_qp_profile", "cfs_measure_fp64_peak"]
 
 
 class CfsError(RuntimeError):
@@ -172,6 +172,50 @@ class Context:
                                         _dp(out["status"]))
         self._check(rc, "cfs_solve_routes")
         return out
+
+    def solve_routes_var(self, routes, route_len, eps_outer, max_outer, solver=SOLVER_CFS, grad=GRAD_NUMJAC, noise=None, alpha=0.0):
+        """routes (B, W, nj) padded, route_len (B,): one RRT route per seed (s_Parallel_rrt.m:16-25), all smoothed in one call;
+        route_len < 2 (failed seed) -> status STATUS_NO_ROUTE."""
+        r = _f64(routes)
+        rl = np.require(route_len, dtype=np.int32, requirements=["C", "ALIGNED"])
+        B, W = r.shape[0], r.shape[1]
+        n, N, K = self.n, 2 * self.n, max(int(max_outer), 1)
+        out = dict(u=np.zeros((B, n)), x=np.zeros((B, N)), cost_hist=np.full((B, K), np.nan), e_u_hist=np.full((B, K), np.nan),
+                   iters=np.zeros(B, dtype=np.int32), status=np.zeros(B, dtype=np.int32))
+        nz = None if noise is None else _f64(noise)
+        rc = self._lib.cfs_solve_routes_var(self._h, C.c_int(B), C.c_int(W), _dp(rl), C.c_int(solver), C.c_int(grad), _dp(r), _dp(nz),
+                                            C.c_double(eps_outer), C.c_int(max_outer), C.c_double(alpha), _dp(out["u"]),
+                                            _dp(out["x"]), _dp(out["cost_hist"]), _dp(out["e_u_hist"]), _dp(out["iters"]),
+                                            _dp(out["status"]))
+        self._check(rc, "cfs_solve_routes_var")
+        return out
+
+    def solve_routes_var_ptr(self, B, W, route_len, routes, eps_outer, max_outer, u, x, cost_hist, e_u_hist, iters, status,
+                             solver=SOLVER_CFS, grad=GRAD_NUMJAC, device=False, sync=True):
+        """Raw-pointer entry (ints): host pointers (cfs_solve_routes_var[_async]) or device pointers (cfs_solve_routes_device)."""
+        vp = lambda p: C.c_void_p(p) if p else None
+        if device:
+            rc = self._lib.cfs_solve_routes_device(self._h, C.c_int(B), C.c_int(W), vp(route_len), C.c_int(solver), C.c_int(grad),
+                                                   vp(routes), None, C.c_double(eps_outer), C.c_int(max_outer), C.c_double(0.0),
+                                                   vp(u), vp(x), vp(cost_hist), vp(e_u_hist), vp(iters), vp(status),
+                                                   C.c_int(1 if sync else 0))
+            self._check(rc, "cfs_solve_routes_device")
+        else:
+            fn = self._lib.cfs_solve_routes_var if sync else self._lib.cfs_solve_routes_var_async
+            rc = fn(self._h, C.c_int(B), C.c_int(W), vp(route_len), C.c_int(solver), C.c_int(grad), vp(routes), None,
+                    C.c_double(eps_outer), C.c_int(max_outer), C.c_double(0.0), vp(u), vp(x), vp(cost_hist), vp(e_u_hist),
+                    vp(iters), vp(status))
+            self._check(rc, "cfs_solve_routes_var")
+
+    def rrt_find_routes_device_ptr(self, S, star, x0, goal, goal_th, params, bi, max_iter, rnd, nrnd, routes, route_len, n_nodes,
+                                   fail, rnd_used, route_len_or_fail=0, sync=False):
+        """cfs_rrt_find_routes_device: every argument a device pointer (int)."""
+        vp = lambda p: C.c_void_p(p) if p else None
+        rc = self._lib.cfs_rrt_find_routes_device(self._h, C.c_int(S), C.c_int(1 if star else 0), vp(x0), vp(goal), vp(goal_th),
+                                                  vp(params), C.c_double(bi), C.c_int(max_iter), vp(rnd), C.c_int(nrnd),
+                                                  vp(routes), vp(route_len), vp(n_nodes), vp(fail), vp(rnd_used),
+                                                  vp(route_len_or_fail), C.c_int(1 if sync else 0))
+        self._check(rc, "cfs_rrt_find_routes_device")
 
     def resample_routes(self, routes, H):
         """routes (B, W, nj) -> (B, H+1, nj): cubicpolytraj(route, (0:W-1)*dt, linspace(0,(W-1)*dt,H+1)) on the device."""

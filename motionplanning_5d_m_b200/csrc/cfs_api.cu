@@ -17,11 +17,18 @@
 #include <string>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>  // header-only NVTX v3: ranges around set-up, copies and the solver tiers
+
 #include "cfs_kernels.cuh"
 
 using namespace cfs;
 
-static std::string g_create_error;
+static thread_local std::string g_create_error;  // last cfs_create failure of the calling thread
+
+struct NvtxRange {
+  explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
 
 struct DevBuf {
   void *p = nullptr;
@@ -57,8 +64,15 @@ struct cfs_ctx {
   DevBuf th0, thg;
   // batch buffers
   DevBuf x0, ff, caug, xref, noise, u, x, cost, eu, u0, v0, cost0, dist, grad, lid, iters, status, flags, listA, listB,
-      counters, slab, scratch_theta, scratch_out, qpsteps, fupper, probsteps, psg_w, psg_cost, psg_skip, routes, zslab, cont;
+      counters, slab, scratch_theta, scratch_out, qpsteps, fupper, probsteps, psg_w, psg_cost, psg_skip, routes, zslab, cont, rlen, rrt_in;
   int slab_grid = 0, slab_ld = 0;
+  // pinned staging of the host-pointer entries: pageable caller buffers (MATLAB's mxGetPr memory, numpy arrays) are copied
+  // through these so that cudaMemcpyAsync stays asynchronous; pinned / registered caller buffers are used in place
+  void *stage_in = nullptr, *stage_out = nullptr;
+  size_t stage_in_cap = 0, stage_out_cap = 0;
+  struct CopyBack { void *dst; const void *src; size_t bytes; };
+  std::vector<CopyBack> copy_back;  // staged results to hand to the caller in cfs_wait
+  bool staged_last = false;
   // timing
   std::vector<cudaEvent_t> ev;
   cudaEvent_t ev_a = nullptr, ev_b = nullptr;
@@ -130,9 +144,9 @@ extern "C" int cfs_create(cfs_ctx **out, int device_id) {
   if (!out) return fail(nullptr, CFS_E_ARG, "cfs_create: out is NULL");
   *out = nullptr;
   // Several contexts pipeline copy | solve | copy on their own streams; with the default of 8 hardware queues the copies of
-  // one context queue behind the persistent kernels of another.  Only effective if this is the process's first CUDA call
-  // (a MEX host), never overrides the user's setting.
-  setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
+  // one context queue behind the persistent kernels of another: hosts that run more than 8 contexts should export
+  // CUDA_DEVICE_MAX_CONNECTIONS=32 before their first CUDA call (bench.py and the MEX loader do).  The library
+  // never touches the process environment.
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev == 0)
@@ -238,7 +252,7 @@ extern "C" void cfs_destroy(cfs_ctx *ctx) {
                     &ctx->u0, &ctx->v0, &ctx->cost0, &ctx->dist, &ctx->grad, &ctx->lid, &ctx->iters, &ctx->status,
                     &ctx->flags, &ctx->listA, &ctx->listB, &ctx->counters, &ctx->slab, &ctx->scratch_theta,
                     &ctx->scratch_out, &ctx->qpsteps, &ctx->fupper, &ctx->probsteps, &ctx->routes, &ctx->psg_w, &ctx->psg_cost,
-                    &ctx->psg_skip, &ctx->th0, &ctx->thg, &ctx->zslab, &ctx->cont};
+                    &ctx->psg_skip, &ctx->th0, &ctx->thg, &ctx->zslab, &ctx->cont, &ctx->rlen, &ctx->rrt_in};
   for (DevBuf *b : bufs) free_buf(*b);
   if (ctx->dQblk) cudaFree(ctx->dQblk);
   double *ds[] = {ctx->dQQraw, ctx->dQQ, ctx->dG, ctx->dgn, ctx->dGI, ctx->dgnI, ctx->dlim, ctx->dumax, ctx->dworkL, ctx->dworkY};
@@ -252,6 +266,8 @@ extern "C" void cfs_destroy(cfs_ctx *ctx) {
   if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);
   for (cudaEvent_t e : ctx->ev_h)
     if (e) cudaEventDestroy(e);
+  if (ctx->stage_in) cudaFreeHost(ctx->stage_in);
+  if (ctx->stage_out) cudaFreeHost(ctx->stage_out);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   if (ctx->heavy_stream) cudaStreamDestroy(ctx->heavy_stream);
   if (ctx->ev_bulk) cudaEventDestroy(ctx->ev_bulk);
@@ -373,6 +389,7 @@ extern "C" int cfs_set_cost(cfs_ctx *ctx, int H, const double *QQ, const double 
   if (max_input) CU(cudaMemcpyAsync(ctx->dumax, max_input, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
   ctx->has_lim = lim != nullptr;
   ctx->has_bounds = max_input != nullptr;
+  NvtxRange nvtx_setup("cfs:set_cost (Cholesky + Gram operator)");
   CU(cudaEventRecord(ctx->ev_a, ctx->stream));
   CU(setup_gram(n, H, nj, ctx->htab.dt, ctx->dQQ, ctx->dworkL, ctx->dworkY, ctx->dG, ctx->dgn, ctx->dinfo, ctx->stream));
   CU(cudaEventRecord(ctx->ev_b, ctx->stream));
@@ -564,6 +581,7 @@ static int solve_device(cfs_ctx *ctx, int B, int solver, int grad, const double 
       launches += 2;
       a.order = ptr<int>(ctx->listB);
     }
+    NvtxRange nvtx_solve("cfs:fused solve (screen | bulk | heavy)");
     const bool screen = warp && ctx->screen && !ctx->heavy_skip;
     const bool side = ctx->heavy_stream && ctx->heavy_prio && !detail;  // heavy tier on its own highest-priority stream
     if (detail) CU(cudaEventRecord(ctx->ev[0], st));
@@ -636,6 +654,7 @@ static int solve_device(cfs_ctx *ctx, int B, int solver, int grad, const double 
   g.dist = a.dist; g.linkid = nullptr; g.grad = a.grad; g.flags = a.flags;
 
   for (int it = 1; it <= max_outer; ++it) {
+    NvtxRange nvtx_it("cfs:outer iteration (gradient | QP)");
     a.outer_iter = it;
     g.list = a.list_cur;
     g.count = a.count_cur;
@@ -721,7 +740,7 @@ static int check_solve_args(cfs_ctx *ctx, int B, int solver, int grad, const voi
   if (B < 0 || max_outer < 0) return fail(ctx, CFS_E_ARG, "cfs_solve_batch: B=%d max_outer=%d", B, max_outer);
   if (solver != CFS_SOLVER_CFS && solver != CFS_SOLVER_PSGCFS) return fail(ctx, CFS_E_ARG, "cfs_solve_batch: solver=%d", solver);
   if (grad != CFS_GRAD_NUMJAC && grad != CFS_GRAD_DERIVEST) return fail(ctx, CFS_E_ARG, "cfs_solve_batch: grad=%d", grad);
-  if (B > 0 && (!x0 || !ff || !caug || !xref || !u || !x || !cost_hist || !iters || !status))
+  if (B > 0 && (!x0 || !ff || !caug || !xref || !u || !cost_hist || !iters || !status))
     return fail(ctx, CFS_E_ARG, "cfs_solve_batch: NULL buffer");
   return 0;
 }
@@ -733,6 +752,7 @@ extern "C" int cfs_solve_batch_device(cfs_ctx *ctx, int B, int solver, int grad,
   int rc = check_solve_args(ctx, B, solver, grad, x0, ff, caug, xref, max_outer, u, x, cost_hist, iters, status);
   if (rc) return rc;
   if (B == 0) return 0;
+  if (!x) return fail(ctx, CFS_E_ARG, "cfs_solve_batch_device: NULL x");
   CU(cudaSetDevice(ctx->device));
   ctx->pending.active = false;  // device-pointer entry: statistics of an un-waited earlier batch are dropped
   rc = solve_device(ctx, B, solver, grad, x0, ff, caug, xref, noise, eps_outer, max_outer, alpha, u, x, cost_hist,
@@ -752,6 +772,8 @@ static int finish_pending(cfs_ctx *ctx) {
   if (!ctx->pending.active) return 0;
   ctx->pending.active = false;
   int rc = collect_stats(ctx, ctx->pending.B, ctx->pending.max_outer, ctx->pending.d_iters, ctx->pending.d_status);
+  for (const cfs_ctx::CopyBack &cb : ctx->copy_back) memcpy(cb.dst, cb.src, cb.bytes);  // staged results -> caller's buffers
+  ctx->copy_back.clear();
   if (ctx->pending.host) {
     float a = 0, b = 0;
     cudaEventElapsedTime(&a, ctx->ev_h[0], ctx->ev_h[1]);
@@ -772,12 +794,67 @@ extern "C" int cfs_wait(cfs_ctx *ctx) {
   return finish_pending(ctx);
 }
 
+static bool is_pinned_host(const void *p) {
+  if (!p) return true;
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged;
+}
+
+static int ensure_stage(cfs_ctx *ctx, void *&p, size_t &cap, size_t bytes) {
+  if (bytes <= cap) return 0;
+  if (p) cudaFreeHost(p);
+  p = nullptr;
+  cap = 0;
+  cudaError_t e = cudaHostAlloc(&p, bytes, cudaHostAllocDefault);
+  if (e != cudaSuccess) return fail(ctx, CFS_E_NOMEM, "cudaHostAlloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+  cap = bytes;
+  return 0;
+}
+
+// H2D of one input: in place when the caller's buffer is pinned, else through the context's pinned staging area
+struct StageIn {
+  cfs_ctx *ctx;
+  bool use;
+  size_t off = 0;
+  cudaError_t put(void *dev, const void *host, size_t bytes, cudaStream_t st) {
+    if (!host || bytes == 0) return cudaSuccess;
+    const void *src = host;
+    if (use) {
+      void *slot = static_cast<char *>(ctx->stage_in) + off;
+      memcpy(slot, host, bytes);
+      off += (bytes + 255) / 256 * 256;
+      src = slot;
+    }
+    return cudaMemcpyAsync(dev, src, bytes, cudaMemcpyHostToDevice, st);
+  }
+};
+struct StageOut {
+  cfs_ctx *ctx;
+  bool use;
+  size_t off = 0;
+  cudaError_t get(void *host, const void *dev, size_t bytes, cudaStream_t st) {
+    if (!host || bytes == 0) return cudaSuccess;
+    void *dst = host;
+    if (use) {
+      dst = static_cast<char *>(ctx->stage_out) + off;
+      off += (bytes + 255) / 256 * 256;
+      ctx->copy_back.push_back({host, dst, bytes});
+    }
+    return cudaMemcpyAsync(dst, dev, bytes, cudaMemcpyDeviceToHost, st);
+  }
+};
+
 // host-pointer solve, asynchronous.  Either the reference's per-problem arrays (x0, ff, caug, xref) or, with theta0/thetag,
 // start/goal pairs from which the device builds them (main_FANUC.m:38-49,98-103).  x and e_u_hist may be NULL (not copied back).
 static int solve_host_async(cfs_ctx *ctx, int B, int solver, int grad, const double *x0, const double *ff, const double *caug,
                             const double *xref, const double *theta0, const double *thetag, const double *noise,
                             double eps_outer, int max_outer, double alpha, double *u, double *x, double *cost_hist,
-                            double *e_u_hist, int *iters, int *status, const double *routes = nullptr, int W = 0) {
+                            double *e_u_hist, int *iters, int *status, const double *routes = nullptr, int W = 0,
+                            const int *route_len = nullptr) {
   int rc;
   CU(cudaSetDevice(ctx->device));
   if (ctx->pending.active && (rc = finish_pending(ctx))) return rc;  // one batch in flight per context
@@ -796,28 +873,56 @@ static int solve_host_async(cfs_ctx *ctx, int B, int solver, int grad, const dou
   if (noise && (rc = ensure(ctx, ctx->noise, sizeof(double) * (size_t)n * K * B))) return rc;
   for (cudaEvent_t &e : ctx->ev_h)
     if (!e) CU(cudaEventCreate(&e));
+  // pageable caller buffers go through the context's pinned staging area (one memcpy each way) so that every copy below is
+  // truly asynchronous; pinned / registered buffers are used in place
+  const size_t al = 256;
+  auto pad = [al](size_t b) { return (b + al - 1) / al * al; };
+  size_t in_bytes = 0, out_bytes = 0;
+  bool pinned_in = true, pinned_out = true;
+  auto in = [&](const void *hp, size_t b) { if (hp && b) { in_bytes += pad(b); pinned_in = pinned_in && is_pinned_host(hp); } };
+  auto outb = [&](const void *hp, size_t b) { if (hp && b) { out_bytes += pad(b); pinned_out = pinned_out && is_pinned_host(hp); } };
+  in(routes, sizeof(double) * (size_t)nj * W * B); in(route_len, sizeof(int) * B);
+  in(theta0, sizeof(double) * nj * B); in(thetag, sizeof(double) * nj * B);
+  in(x0, sizeof(double) * 2 * nj * B); in(ff, sizeof(double) * (size_t)n * B); in(caug, sizeof(double) * B);
+  in(xref, sizeof(double) * (size_t)2 * n * B); in(noise, sizeof(double) * (size_t)n * K * B);
+  outb(u, sizeof(double) * (size_t)n * B); outb(x, sizeof(double) * (size_t)2 * n * B);
+  outb(cost_hist, sizeof(double) * (size_t)max_outer * B); outb(e_u_hist, sizeof(double) * (size_t)max_outer * B);
+  outb(iters, sizeof(int) * B); outb(status, sizeof(int) * B);
+  StageIn sin{ctx, !pinned_in};
+  StageOut sout{ctx, !pinned_out};
+  if (sin.use && (rc = ensure_stage(ctx, ctx->stage_in, ctx->stage_in_cap, in_bytes))) return rc;
+  if (sout.use && (rc = ensure_stage(ctx, ctx->stage_out, ctx->stage_out_cap, out_bytes))) return rc;
+  ctx->copy_back.clear();
+  ctx->staged_last = sin.use || sout.use;
   CU(cudaEventRecord(ctx->ev_h[0], st));
-  if (routes) {
-    if ((rc = ensure(ctx, ctx->th0, sizeof(double) * nj * B))) return rc;
-    if ((rc = ensure(ctx, ctx->thg, sizeof(double) * nj * B))) return rc;
-    if ((rc = ensure(ctx, ctx->routes, sizeof(double) * (size_t)nj * W * B))) return rc;
-    CU(cudaMemcpyAsync(ctx->routes.p, routes, sizeof(double) * (size_t)nj * W * B, cudaMemcpyHostToDevice, st));
-  } else if (theta0) {
-    if ((rc = ensure(ctx, ctx->th0, sizeof(double) * nj * B))) return rc;
-    if ((rc = ensure(ctx, ctx->thg, sizeof(double) * nj * B))) return rc;
-    CU(cudaMemcpyAsync(ctx->th0.p, theta0, sizeof(double) * nj * B, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(ctx->thg.p, thetag, sizeof(double) * nj * B, cudaMemcpyHostToDevice, st));
-  } else {
-    CU(cudaMemcpyAsync(ctx->x0.p, x0, sizeof(double) * 2 * nj * B, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(ctx->ff.p, ff, sizeof(double) * (size_t)n * B, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(ctx->caug.p, caug, sizeof(double) * B, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(ctx->xref.p, xref, sizeof(double) * (size_t)2 * n * B, cudaMemcpyHostToDevice, st));
+  {
+    NvtxRange r("cfs:h2d");
+    if (routes) {
+      if ((rc = ensure(ctx, ctx->th0, sizeof(double) * nj * B))) return rc;
+      if ((rc = ensure(ctx, ctx->thg, sizeof(double) * nj * B))) return rc;
+      if ((rc = ensure(ctx, ctx->routes, sizeof(double) * (size_t)nj * W * B))) return rc;
+      CU(sin.put(ctx->routes.p, routes, sizeof(double) * (size_t)nj * W * B, st));
+      if (route_len) {
+        if ((rc = ensure(ctx, ctx->rlen, sizeof(int) * B))) return rc;
+        CU(sin.put(ctx->rlen.p, route_len, sizeof(int) * B, st));
+      }
+    } else if (theta0) {
+      if ((rc = ensure(ctx, ctx->th0, sizeof(double) * nj * B))) return rc;
+      if ((rc = ensure(ctx, ctx->thg, sizeof(double) * nj * B))) return rc;
+      CU(sin.put(ctx->th0.p, theta0, sizeof(double) * nj * B, st));
+      CU(sin.put(ctx->thg.p, thetag, sizeof(double) * nj * B, st));
+    } else {
+      CU(sin.put(ctx->x0.p, x0, sizeof(double) * 2 * nj * B, st));
+      CU(sin.put(ctx->ff.p, ff, sizeof(double) * (size_t)n * B, st));
+      CU(sin.put(ctx->caug.p, caug, sizeof(double) * B, st));
+      CU(sin.put(ctx->xref.p, xref, sizeof(double) * (size_t)2 * n * B, st));
+    }
+    if (noise) CU(sin.put(ctx->noise.p, noise, sizeof(double) * (size_t)n * K * B, st));
   }
-  if (noise) CU(cudaMemcpyAsync(ctx->noise.p, noise, sizeof(double) * (size_t)n * K * B, cudaMemcpyHostToDevice, st));
   CU(cudaEventRecord(ctx->ev_h[1], st));
   if (routes) {  // N1: cubicpolytraj resampling, then the same problem set-up around that reference
-    CU(launch_resample_routes(B, W, ctx->H, nj, ctx->htab.dt, ptr<double>(ctx->routes), ptr<double>(ctx->th0),
-                              ptr<double>(ctx->thg), ptr<double>(ctx->xref), st));
+    CU(launch_resample_routes(B, W, ctx->H, nj, ctx->htab.dt, ptr<double>(ctx->routes), route_len ? ptr<int>(ctx->rlen) : nullptr,
+                              ptr<double>(ctx->th0), ptr<double>(ctx->thg), ptr<double>(ctx->xref), st));
     CU(launch_build_problems(B, ctx->H, nj, ctx->htab.dt, ctx->dQblk, ctx->stage_w, ctx->term_w, ptr<double>(ctx->th0),
                              ptr<double>(ctx->thg), ptr<double>(ctx->x0), nullptr, ptr<double>(ctx->ff),
                              ptr<double>(ctx->caug), st));
@@ -831,13 +936,17 @@ static int solve_host_async(cfs_ctx *ctx, int B, int solver, int grad, const dou
                     ptr<double>(ctx->u), ptr<double>(ctx->x), ptr<double>(ctx->cost), ptr<double>(ctx->eu),
                     ptr<int>(ctx->iters), ptr<int>(ctx->status));
   if (rc) return rc;
+  if (routes && route_len) CU(launch_mark_no_route(B, ptr<int>(ctx->rlen), ptr<int>(ctx->status), ptr<int>(ctx->iters), st));
   CU(cudaEventRecord(ctx->ev_h[2], st));
-  CU(cudaMemcpyAsync(u, ctx->u.p, sizeof(double) * (size_t)n * B, cudaMemcpyDeviceToHost, st));
-  if (x) CU(cudaMemcpyAsync(x, ctx->x.p, sizeof(double) * (size_t)2 * n * B, cudaMemcpyDeviceToHost, st));
-  CU(cudaMemcpyAsync(cost_hist, ctx->cost.p, sizeof(double) * (size_t)max_outer * B, cudaMemcpyDeviceToHost, st));
-  if (e_u_hist) CU(cudaMemcpyAsync(e_u_hist, ctx->eu.p, sizeof(double) * (size_t)max_outer * B, cudaMemcpyDeviceToHost, st));
-  CU(cudaMemcpyAsync(iters, ctx->iters.p, sizeof(int) * B, cudaMemcpyDeviceToHost, st));
-  CU(cudaMemcpyAsync(status, ctx->status.p, sizeof(int) * B, cudaMemcpyDeviceToHost, st));
+  {
+    NvtxRange r("cfs:d2h");
+    CU(sout.get(u, ctx->u.p, sizeof(double) * (size_t)n * B, st));
+    CU(sout.get(x, ctx->x.p, sizeof(double) * (size_t)2 * n * B, st));  // x, e_u_hist may be NULL: not copied back
+    CU(sout.get(cost_hist, ctx->cost.p, sizeof(double) * (size_t)max_outer * B, st));
+    CU(sout.get(e_u_hist, ctx->eu.p, sizeof(double) * (size_t)max_outer * B, st));
+    CU(sout.get(iters, ctx->iters.p, sizeof(int) * B, st));
+    CU(sout.get(status, ctx->status.p, sizeof(int) * B, st));
+  }
   CU(cudaEventRecord(ctx->ev_h[3], st));
   ctx->pending.active = true;
   ctx->pending.host = true;
@@ -901,6 +1010,72 @@ extern "C" int cfs_solve_routes(cfs_ctx *ctx, int B, int W, int solver, int grad
   return cfs_wait(ctx);
 }
 
+static int check_routes_args(cfs_ctx *ctx, const char *who, int B, int W, int solver, int grad, int max_outer, const void *routes,
+                             const void *u, const void *cost_hist, const void *iters, const void *status) {
+  if (!ctx) return CFS_E_ARG;
+  int rc = check_ready(ctx, true);
+  if (rc) return rc;
+  if (!ctx->have_blocks) return fail(ctx, CFS_E_STATE, "%s: the cost must be set with cfs_set_cost_blocks", who);
+  if (B < 0 || W < 2 || max_outer < 0 || (solver != CFS_SOLVER_CFS && solver != CFS_SOLVER_PSGCFS) ||
+      (grad != CFS_GRAD_NUMJAC && grad != CFS_GRAD_DERIVEST))
+    return fail(ctx, CFS_E_ARG, "%s: bad argument", who);
+  if (B > 0 && (!routes || !u || !cost_hist || !iters || !status)) return fail(ctx, CFS_E_ARG, "%s: NULL buffer", who);
+  return 0;
+}
+
+extern "C" int cfs_solve_routes_var_async(cfs_ctx *ctx, int B, int W, const int *route_len, int solver, int grad,
+                                          const double *routes, const double *noise, double eps_outer, int max_outer, double alpha,
+                                          double *u, double *x, double *cost_hist, double *e_u_hist, int *iters, int *status) {
+  int rc = check_routes_args(ctx, "cfs_solve_routes_var", B, W, solver, grad, max_outer, routes, u, cost_hist, iters, status);
+  if (rc || B == 0) return rc;
+  if (!route_len) return fail(ctx, CFS_E_ARG, "cfs_solve_routes_var: NULL route_len");
+  return solve_host_async(ctx, B, solver, grad, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, noise, eps_outer, max_outer,
+                          alpha, u, x, cost_hist, e_u_hist, iters, status, routes, W, route_len);
+}
+
+extern "C" int cfs_solve_routes_var(cfs_ctx *ctx, int B, int W, const int *route_len, int solver, int grad, const double *routes,
+                                    const double *noise, double eps_outer, int max_outer, double alpha, double *u, double *x,
+                                    double *cost_hist, double *e_u_hist, int *iters, int *status) {
+  int rc = cfs_solve_routes_var_async(ctx, B, W, route_len, solver, grad, routes, noise, eps_outer, max_outer, alpha, u, x, cost_hist,
+                                      e_u_hist, iters, status);
+  if (rc || B == 0) return rc;
+  return cfs_wait(ctx);
+}
+
+extern "C" int cfs_solve_routes_device(cfs_ctx *ctx, int B, int W, const int *route_len, int solver, int grad, const double *routes,
+                                       const double *noise, double eps_outer, int max_outer, double alpha, double *u, double *x,
+                                       double *cost_hist, double *e_u_hist, int *iters, int *status, int sync) {
+  int rc = check_routes_args(ctx, "cfs_solve_routes_device", B, W, solver, grad, max_outer, routes, u, cost_hist, iters, status);
+  if (rc || B == 0) return rc;
+  if (!x) return fail(ctx, CFS_E_ARG, "cfs_solve_routes_device: NULL x");
+  CU(cudaSetDevice(ctx->device));
+  ctx->pending.active = false;
+  const int nj = ctx->nj, n = ctx->n;
+  cudaStream_t st = ctx->stream;
+  if ((rc = ensure(ctx, ctx->x0, sizeof(double) * 2 * nj * B))) return rc;
+  if ((rc = ensure(ctx, ctx->ff, sizeof(double) * (size_t)n * B))) return rc;
+  if ((rc = ensure(ctx, ctx->caug, sizeof(double) * B))) return rc;
+  if ((rc = ensure(ctx, ctx->xref, sizeof(double) * (size_t)2 * n * B))) return rc;
+  if ((rc = ensure(ctx, ctx->th0, sizeof(double) * nj * B))) return rc;
+  if ((rc = ensure(ctx, ctx->thg, sizeof(double) * nj * B))) return rc;
+  CU(launch_resample_routes(B, W, ctx->H, nj, ctx->htab.dt, routes, route_len, ptr<double>(ctx->th0), ptr<double>(ctx->thg),
+                            ptr<double>(ctx->xref), st));
+  CU(launch_build_problems(B, ctx->H, nj, ctx->htab.dt, ctx->dQblk, ctx->stage_w, ctx->term_w, ptr<double>(ctx->th0),
+                           ptr<double>(ctx->thg), ptr<double>(ctx->x0), nullptr, ptr<double>(ctx->ff), ptr<double>(ctx->caug), st));
+  rc = solve_device(ctx, B, solver, grad, ptr<double>(ctx->x0), ptr<double>(ctx->ff), ptr<double>(ctx->caug), ptr<double>(ctx->xref),
+                    noise, eps_outer, max_outer, alpha, u, x, cost_hist, e_u_hist, iters, status);
+  if (rc) return rc;
+  CU(launch_mark_no_route(B, route_len, status, iters, st));
+  ctx->pending.active = true;
+  ctx->pending.host = false;
+  ctx->pending.B = B;
+  ctx->pending.max_outer = max_outer;
+  ctx->pending.d_iters = iters;
+  ctx->pending.d_status = status;
+  if (sync) return finish_pending(ctx);
+  return 0;
+}
+
 extern "C" int cfs_resample_routes(cfs_ctx *ctx, int B, int W, int H, const double *routes, double *sampled) {
   if (!ctx) return CFS_E_ARG;
   int rc = check_ready(ctx, false);
@@ -915,8 +1090,8 @@ extern "C" int cfs_resample_routes(cfs_ctx *ctx, int B, int W, int H, const doub
   if ((rc = ensure(ctx, ctx->thg, sizeof(double) * nj * B))) return rc;
   if ((rc = ensure(ctx, ctx->scratch_out, sizeof(double) * (size_t)2 * nj * H * B))) return rc;
   CU(cudaMemcpyAsync(ctx->routes.p, routes, sizeof(double) * (size_t)nj * W * B, cudaMemcpyHostToDevice, st));
-  CU(launch_resample_routes(B, W, H, nj, ctx->htab.dt, ptr<double>(ctx->routes), ptr<double>(ctx->th0), ptr<double>(ctx->thg),
-                            ptr<double>(ctx->scratch_out), st));
+  CU(launch_resample_routes(B, W, H, nj, ctx->htab.dt, ptr<double>(ctx->routes), nullptr, ptr<double>(ctx->th0),
+                            ptr<double>(ctx->thg), ptr<double>(ctx->scratch_out), st));
   // sampled (nj x (H+1) x B): column 0 = theta0, columns 1..H = the theta rows of x_
   CU(cudaMemcpy2DAsync(sampled, sizeof(double) * nj * (H + 1), ctx->th0.p, sizeof(double) * nj, sizeof(double) * nj, B,
                        cudaMemcpyDeviceToHost, st));
@@ -1167,6 +1342,32 @@ extern "C" int cfs_rrt_find_routes(cfs_ctx *ctx, int S, int star, const double *
     cudaEventElapsedTime(&ms, ctx->ev_a, ctx->ev_b);
     *ms_kernel = ms;
   }
+  return 0;
+}
+
+extern "C" int cfs_rrt_find_routes_device(cfs_ctx *ctx, int S, int star, const double *x0, const double *goal, const double *goal_th,
+                                          const double *params, double bi, int max_iter, const double *rnd, int nrnd,
+                                          double *routes, int *route_len, int *n_nodes, int *fail_out, int *rnd_used,
+                                          int *route_len_or_fail, int sync) {
+  if (!ctx) return CFS_E_ARG;
+  int rc = check_ready(ctx, false);
+  if (rc) return rc;
+  if (S < 0 || max_iter < 1 || nrnd < 1 ||
+      (S > 0 && (!x0 || !goal || !goal_th || !params || !rnd || !routes || !route_len || !n_nodes || !fail_out || !rnd_used)))
+    return fail(ctx, CFS_E_ARG, "cfs_rrt_find_routes_device: bad argument");
+  if (S == 0) return 0;
+  CU(cudaSetDevice(ctx->device));
+  const int nj = ctx->nj;
+  cudaStream_t st = ctx->stream;
+  RrtArgs a;
+  memset(&a, 0, sizeof(a));
+  a.tab = ctx->dtab; a.nj = nj; a.nobs = ctx->nobs; a.star = star; a.max_iter = max_iter; a.nrnd = nrnd; a.bi = bi;
+  a.x0 = x0; a.goal = goal; a.goal_th = goal_th;
+  a.region_g = params; a.region_s = params + nj; a.sample_off = params + 2 * nj; a.ratial = params + 3 * nj;
+  a.rnd = rnd; a.routes = routes; a.route_len = route_len; a.n_nodes = n_nodes; a.fail = fail_out; a.rnd_used = rnd_used;
+  CU(launch_rrt_find_routes(a, S, st));
+  if (route_len_or_fail) CU(launch_route_len_or_fail(S, route_len, fail_out, route_len_or_fail, st));
+  if (sync) CU(cudaStreamSynchronize(st));
   return 0;
 }
 

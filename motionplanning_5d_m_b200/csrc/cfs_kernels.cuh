@@ -75,8 +75,13 @@ cudaError_t launch_build_problems(int B, int H, int nj, double dt, const double 
 // RRT route (nj x W waypoints dt apart) -> H+1 samples of cubicpolytraj with zero waypoint velocities (RRTstar_CFS.m:96-100):
 // theta0 / thetag = first / last sample, xref = [sample_i; 0], i = 1..H.  launch_build_problems with xref == nullptr then
 // adds x0, ff, caug without touching that reference.
-cudaError_t launch_resample_routes(int B, int W, int H, int nj, double dt, const double *routes /*nj x W x B*/, double *theta0,
-                                   double *thetag, double *xref, cudaStream_t s);
+// route_len (B, or nullptr: every route has W waypoints): routes with fewer than 2 waypoints get xref = ones (the first stop
+// test of EVAL.m:47,64 then ends them before any iteration) and launch_mark_no_route sets their status afterwards.
+cudaError_t launch_resample_routes(int B, int W, int H, int nj, double dt, const double *routes /*nj x W x B*/,
+                                   const int *route_len, double *theta0, double *thetag, double *xref, cudaStream_t s);
+cudaError_t launch_mark_no_route(int B, const int *route_len, int *status, int *iters, cudaStream_t s);
+// route_len_or_fail[s] = fail[s] || route_len[s] < 0 ? 0 : route_len[s]
+cudaError_t launch_route_len_or_fail(int S, const int *route_len, const int *fail, int *out, cudaStream_t s);
 
 // C = alpha * op(A) * B  (column-major, A is M x K with lda (or K x M if transA), B is K x N, C is M x N)
 cudaError_t launch_dgemm(int M, int N, int K, double alpha, const double *A, int lda, bool transA, const double *B,

@@ -220,13 +220,23 @@ cudaError_t launch_build_problems(int B, int H, int nj, double dt, const double 
 // with the toolbox defaults (zero velocity at every waypoint): on segment k, q = q_k + (3 s^2 - 2 s^3)(q_{k+1} - q_k),
 // s = (t - t_k)/(t_{k+1} - t_k).  One CTA per route; outputs theta0 = sampled(:,1), thetag = sampled(:,H+1) and
 // x_ = [sampled(:,i); 0] for i = 2..H+1 (RRTstar_CFS.m:106-119).
-__global__ void __launch_bounds__(128) k_resample_routes(int B, int W, int H, int nj, double dt, const double *routes /*nj x W x B*/,
-                                                         double *theta0, double *thetag, double *xref) {
+__global__ void __launch_bounds__(128) k_resample_routes(int B, int Wmax, int H, int nj, double dt, const double *routes /*nj x W x B*/,
+                                                         const int *route_len, double *theta0, double *thetag, double *xref) {
   const int b = blockIdx.x, ns = 2 * nj;
-  const double *wp = routes + (size_t)b * nj * W;
+  const double *wp = routes + (size_t)b * nj * Wmax;
+  const int W = route_len ? (route_len[b] < Wmax ? route_len[b] : Wmax) : Wmax;
   const double t_end = (W - 1) * dt;
   for (int idx = threadIdx.x; idx < (H + 1) * nj; idx += blockDim.x) {
     const int i = idx / nj, k = idx - i * nj;
+    if (W < 2) {  // no route (failed RRT seed): a reference that passes the first stop test untouched
+      if (i == 0) theta0[(size_t)b * nj + k] = 0.0;
+      if (i == H) thetag[(size_t)b * nj + k] = 0.0;
+      if (i > 0) {
+        xref[(size_t)b * H * ns + (size_t)(i - 1) * ns + k] = 1.0;
+        xref[(size_t)b * H * ns + (size_t)(i - 1) * ns + nj + k] = 1.0;
+      }
+      continue;
+    }
     // MATLAB linspace: d1 + (0:n1)*(d2-d1)/n1 with the last point set to d2 exactly
     const double t = (i == H) ? t_end : (i * t_end) / H;
     int seg = 0;  // last waypoint time <= t, clipped to a valid segment
@@ -245,10 +255,33 @@ __global__ void __launch_bounds__(128) k_resample_routes(int B, int W, int H, in
   }
 }
 
-cudaError_t launch_resample_routes(int B, int W, int H, int nj, double dt, const double *routes, double *theta0, double *thetag,
-                                   double *xref, cudaStream_t s) {
+cudaError_t launch_resample_routes(int B, int W, int H, int nj, double dt, const double *routes, const int *route_len,
+                                   double *theta0, double *thetag, double *xref, cudaStream_t s) {
   if (B <= 0) return cudaSuccess;
-  k_resample_routes<<<B, 128, 0, s>>>(B, W, H, nj, dt, routes, theta0, thetag, xref);
+  k_resample_routes<<<B, 128, 0, s>>>(B, W, H, nj, dt, routes, route_len, theta0, thetag, xref);
+  return cudaGetLastError();
+}
+
+__global__ void k_mark_no_route(int B, const int *route_len, int *status, int *iters) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < B && route_len[b] < 2) {
+    status[b] = 5;  // CFS_STATUS_NO_ROUTE
+    iters[b] = 0;
+  }
+}
+cudaError_t launch_mark_no_route(int B, const int *route_len, int *status, int *iters, cudaStream_t s) {
+  if (B <= 0 || !route_len) return cudaSuccess;
+  k_mark_no_route<<<(B + 127) / 128, 128, 0, s>>>(B, route_len, status, iters);
+  return cudaGetLastError();
+}
+
+__global__ void k_route_len_or_fail(int S, const int *route_len, const int *fail, int *out) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < S) out[b] = (fail[b] || route_len[b] < 0) ? 0 : route_len[b];
+}
+cudaError_t launch_route_len_or_fail(int S, const int *route_len, const int *fail, int *out, cudaStream_t s) {
+  if (S <= 0) return cudaSuccess;
+  k_route_len_or_fail<<<(S + 127) / 128, 128, 0, s>>>(S, route_len, fail, out);
   return cudaGetLastError();
 }
 

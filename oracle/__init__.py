@@ -11,6 +11,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "libcfs_oracle.so")
+_SO_TWIN = os.path.join(_HERE, "libcfs_oracle_fma.so")
 
 M16IB, M200I, R2L = 0, 1, 2
 KIND = {"M16iB": M16IB, "M200i": M200I, "2L": R2L}
@@ -19,7 +20,7 @@ MAXL = 6
 
 def build(force=False):
     src = [os.path.join(_HERE, f) for f in ("cfs_oracle.c", "cfs_oracle.h")]
-    if force or not os.path.exists(_SO) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in src):
+    if force or not os.path.exists(_SO) or not os.path.exists(_SO_TWIN) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in src):
         subprocess.check_call(["make", "-C", _HERE, "-s"])
     return _SO
 
@@ -36,6 +37,19 @@ class Cfg(C.Structure):
 
 
 _lib = None
+_twin = None
+
+
+def twin():
+    """The same restatement compiled with FMA contraction (oracle/Makefile): conditioning probe only."""
+    global _twin
+    if _twin is None:
+        build()
+        with open("/proc/cpuinfo") as f:
+            if " fma" not in f.read():
+                raise RuntimeError("this CPU has no FMA: the twin oracle cannot run")
+        _twin = C.CDLL(_SO_TWIN)
+    return _twin
 
 
 def lib():
@@ -165,8 +179,8 @@ class Problem:
                           _p(dist), _p(lid), _p(grad), C.byref(t))
         return A, b, dist, lid, grad, t.value
 
-    def solve_batch(self, x0, ff, caug, xref, noise=None, nthreads=0):
-        """x0 (B,2nj) ff (B,n) caug (B,) xref (B,N) noise (B,max_outer,n) -> dict"""
+    def solve_batch(self, x0, ff, caug, xref, noise=None, nthreads=0, use_twin=False):
+        """x0 (B,2nj) ff (B,n) caug (B,) xref (B,N) noise (B,max_outer,n) -> dict.  use_twin: the FMA-contracted build."""
         x0, ff, caug, xref = map(_f64, (x0, ff, caug, xref))
         B = x0.shape[0]
         K = self.cfg.max_outer
@@ -178,7 +192,7 @@ class Problem:
         status = np.zeros(B, dtype=np.int32)
         nz = None if noise is None else _f64(noise)
         qp = np.zeros((B, 2), dtype=np.int32)
-        lib().orc_cfs_solve_batch2(C.byref(self.r), C.byref(self.cfg), C.c_int(B), C.c_int(nthreads), _p(x0), _p(ff),
+        (twin() if use_twin else lib()).orc_cfs_solve_batch2(C.byref(self.r), C.byref(self.cfg), C.c_int(B), C.c_int(nthreads), _p(x0), _p(ff),
                                    _p(caug), _p(xref), _p(nz), _p(u), _p(x), _p(cost), _p(e_u), _p(iters), _p(status),
                                    _p(qp))
         return dict(u=u, x=x, cost_hist=cost, e_u_hist=e_u, iters=iters, status=status, qp_iters=qp[:, 0],
