@@ -171,7 +171,7 @@ def workload_text(args):
 
 def make_oracle_problem(O, cfg, grad, solver=0):
     s = cfg["sys_info"]
-    return O.Problem(O.robot(cfg["ROBOT"]), s["H"], [o["l"] for o in cfg["obs"]],
+    return O.Problem(O.robot(cfg["ROBOT"]), s["H"], list(cfg["obs"]),
                      [o["epsilon"] if solver == 0 else o["D"] for o in cfg["obs"]], s["QQ"], s["lim"],
                      s["MAX_input"] if solver == 0 else None, s["epsilon_O"], s["MAX_O_ITER"], solver=solver, grad=grad,
                      alpha=s.get("alpha", 0.0))
@@ -179,7 +179,7 @@ def make_oracle_problem(O, cfg, grad, solver=0):
 
 def oracle_feasible(O, ROBOT, obs):
     r = O.robot(ROBOT)
-    o6 = [O.obs6(o["l"]) for o in obs]
+    o6 = [O.obs6(o) for o in obs]
     return lambda cand: np.array([all(O.dist_arm(r, th, o)[0] >= ob["D"] for o, ob in zip(o6, obs)) for th in cand])
 
 

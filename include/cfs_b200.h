@@ -84,6 +84,14 @@ int cfs_set_robot(cfs_ctx *ctx, int robot_kind, const double *DH /*6x4*/, int dh
                   const double *cap_p /*3x2xn_joints*/, int n_joints, const double *T2L /*3x3 or NULL*/, double dt);
 /* obs{j}.l (3x2), obs{j}.D, obs{j}.epsilon   (main_FANUC.m:56-60) */
 int cfs_set_obstacles(cfs_ctx *ctx, const double *seg /*3x2xn_obs*/, const double *D, const double *eps, int n_obs);
+/* The same with a kind per obstacle (NULL = all capsules).  CFS_OBS_CAPSULE: seg(:,:,j) = obs{j}.l, the capsule axis -- the
+ * only obstacle the reference has.  CFS_OBS_BOX (extension; MATLAB side: obs{j}.shape = 'box'):
+ * seg(:,1,j) / seg(:,2,j) = min / max corner of a solid axis-aligned box, e.g. the bounding box of an STL part of map/
+ * (Lib/functions/MapFromSTL.m:1-12 reads those, in mm).  The distance is taken between the link AXIS and the solid box, with
+ * the same "|dis| < 1e-4 -> -norm(P1 - link end)" rule and the same margins D / epsilon as for capsules. */
+enum { CFS_OBS_CAPSULE = 0, CFS_OBS_BOX = 1 };
+int cfs_set_obstacles_ex(cfs_ctx *ctx, const double *seg /*3x2xn_obs*/, const int *kind /*n_obs or NULL*/, const double *D,
+                         const double *eps, int n_obs);
 /* sys_info.{H, QQ, lim, MAX_input} (main_FANUC.m:106-127).  lim==NULL: no velocity rows (M16iB/main_CFS.m path);
  * max_input==NULL: no bounds.  Factors QQ once on the device and builds the shared Gram operator. */
 int cfs_set_cost(cfs_ctx *ctx, int H, const double *QQ /*n x n, n=H*n_joints*/, const double *lim /*n_joints*/,

@@ -1,6 +1,9 @@
 % PSGCFS_FANUC -- drop-in for Lib/PSGCFS_FANUC.m (optimizer() on the GPU through cfs_mex).
-% The normrnd(0,0.1,[nn,1]) draws of PSGCFS_FANUC.m:109 are made HERE, in the reference's order (one column per outer
-% iteration), and handed to the GPU so that MATLAB's random stream is the one consumed.
+% The normrnd(0,0.1,[nn,1]) draws of PSGCFS_FANUC.m:109 are made HERE, one column per outer iteration, and handed to the GPU so
+% that MATLAB's random stream is the one consumed.  Difference to the reference: all MAX_O_ITER columns are drawn up front,
+% whereas PSGCFS_FANUC.m:109 draws only when a PSG step is actually taken (stop_inner, :136-142, can skip it), so the
+% generator may advance further here; pass your own draws through the optional argument of optimizer(noise) to control that.
+% The gateway refuses PSGCFS without noise (a zero-noise run would be a different, deterministic method).
 classdef PSGCFS_FANUC
     properties
         obs cell
@@ -24,11 +27,15 @@ classdef PSGCFS_FANUC
             self.u = zeros(self.nn, 1);
             self.eval = struct('cost_all', [], 'e_cost_all', [], 'e_u_all', []);
         end
-        function self = optimizer(self)
+        function self = optimizer(self, varargin)
             K = self.sys_info.MAX_O_ITER;
-            noise = zeros(self.nn, K);
-            for k = 1:K
-                noise(:, k) = normrnd(0, 0.1, [self.nn, 1]);
+            if ~isempty(varargin)
+                noise = varargin{1};                     % nn x MAX_O_ITER, the caller's normrnd(0,0.1,[nn,1]) columns
+            else
+                noise = zeros(self.nn, K);
+                for k = 1:K
+                    noise(:, k) = normrnd(0, 0.1, [self.nn, 1]);
+                end
             end
             [u, x, cost, eu, it, st, qp] = cfs_mex('PSGCFS', 'num_jac', self.ROBOT, self.obs, self.sys_info, noise);
             if bitand(st(1), 255) == 2

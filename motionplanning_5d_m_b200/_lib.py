@@ -18,7 +18,7 @@ STATUS_CONVERGED, STATUS_MAX_ITER, STATUS_INFEASIBLE, STATUS_NUMERICAL, STATUS_N
 FLAG_TOUCH = 0x100
 
 # every symbol include/cfs_b200.h declares (tests check that the library exports all of them)
-SYMBOLS = ["cfs_create", "cfs_destroy", "cfs_last_error", "cfs_version", "cfs_set_stream", "cfs_set_option", "cfs_set_robot", "cfs_set_obstacles",
+SYMBOLS = ["cfs_create", "cfs_destroy", "cfs_last_error", "cfs_version", "cfs_set_stream", "cfs_set_option", "cfs_set_robot", "cfs_set_obstacles", "cfs_set_obstacles_ex",
            "cfs_set_cost", "cfs_set_cost_blocks", "cfs_solve_start_goal", "cfs_solve_start_goal_async", "cfs_solve_routes", "cfs_solve_routes_async", "cfs_solve_routes_var", "cfs_solve_routes_var_async", "cfs_solve_routes_device", "cfs_resample_routes", "cfs_solve_batch", "cfs_solve_batch_async", "cfs_wait", "cfs_solve_batch_device", "cfs_dist_grad", "cfs_time_dist_grad", "cfs_get_con",
            "cfs_nodes_feasible", "cfs_nearest_steer", "cfs_rrt_find_routes", "cfs_rrt_find_routes_device", "cfs_get_stats", "cfs_set_timing", "cfs_get_iter_times", "cfs_get_problem_steps", "cfs_get_qp_profile", "cfs_measure_fp64_peak"]
 
@@ -108,16 +108,20 @@ class Context:
         self.nj = njoint
 
     def set_obstacles(self, obs):
+        """obs: list of dicts with l (3x2), D, epsilon (main_FANUC.m:56-60).  shape == 'box' (extension): l = [min corner, max
+        corner] of a solid axis-aligned box, e.g. from stl_boxes.boxes_from_stl; anything else is a capsule axis."""
         O = len(obs)
         seg = np.zeros((3, 2, max(O, 1)), order="F")
         D = np.zeros(max(O, 1))
         eps = np.zeros(max(O, 1))
+        kind = np.zeros(max(O, 1), dtype=np.int32)
         for j, o in enumerate(obs):
             seg[:, :, j] = np.asarray(o["l"], dtype=np.float64)
             D[j] = o.get("D", 0.0)
             eps[j] = o.get("epsilon", 0.0)
-        rc = self._lib.cfs_set_obstacles(self._h, _dp(np.asfortranarray(seg)), _dp(D), _dp(eps), C.c_int(O))
-        self._check(rc, "cfs_set_obstacles")
+            kind[j] = 1 if o.get("shape") == "box" else 0
+        rc = self._lib.cfs_set_obstacles_ex(self._h, _dp(np.asfortranarray(seg)), _dp(kind), _dp(D), _dp(eps), C.c_int(O))
+        self._check(rc, "cfs_set_obstacles_ex")
         self.nobs = O
 
     def set_cost(self, H, QQ, lim, max_input):

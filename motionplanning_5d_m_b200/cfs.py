@@ -57,10 +57,15 @@ class _SolverBase:
         ctx.set_cost(s["H"], s["QQ"], s.get("lim"), s.get("MAX_input") if self.SOLVER == _lib.SOLVER_CFS else None)
         return ctx
 
-    def optimizer(self, noise=None):
+    def optimizer(self, noise=None, rng=None):
         s = self.sys_info
         ctx = self._context()
         K = int(s["MAX_O_ITER"])
+        if self.SOLVER == _lib.SOLVER_PSGCFS and noise is None:
+            # PSGCFS_FANUC.m:109 draws normrnd(0,0.1,[nn,1]) in every PSG step; a run without noise would be a different,
+            # deterministic method.  Drawn here with the reference's distribution, one row per outer iteration (all
+            # MAX_O_ITER rows up front: the reference only draws when a step is taken).
+            noise = (rng or np.random.default_rng()).normal(0.0, 0.1, size=(K, self.nn))
         out = ctx.solve_batch(np.asarray(s["xR"], dtype=np.float64)[:, 0][None], np.asarray(s["ff"])[None],
                               np.array([s["caug"]], dtype=np.float64), self.x_[None], float(s["epsilon_O"]), K,
                               solver=self.SOLVER, grad=self.GRAD,

@@ -325,13 +325,27 @@ extern "C" int cfs_set_robot(cfs_ctx *ctx, int robot_kind, const double *DH, int
   return upload_tables(ctx);
 }
 
-extern "C" int cfs_set_obstacles(cfs_ctx *ctx, const double *seg, const double *D, const double *eps, int n_obs) {
+extern "C" int cfs_set_obstacles_ex(cfs_ctx *ctx, const double *seg, const int *kind, const double *D, const double *eps, int n_obs) {
   if (!ctx) return CFS_E_ARG;
   if (n_obs < 0 || n_obs > CFS_MAX_OBS) return fail(ctx, CFS_E_ARG, "cfs_set_obstacles: n_obs=%d (0..%d)", n_obs, CFS_MAX_OBS);
   if (n_obs > 0 && !seg) return fail(ctx, CFS_E_ARG, "cfs_set_obstacles: NULL seg");
   DevTables &t = ctx->htab;
   for (int j = 0; j < n_obs; ++j) {
     ObsTab &o = t.obs[j];
+    memset(&o, 0, sizeof(o));
+    const int kd = kind ? kind[j] : CFS_OBS_CAPSULE;
+    if (kd != CFS_OBS_CAPSULE && kd != CFS_OBS_BOX) return fail(ctx, CFS_E_ARG, "cfs_set_obstacles: obstacle %d has kind %d", j, kd);
+    o.kind = kd;
+    o.D = D ? D[j] : 0.0;
+    o.eps = eps ? eps[j] : 0.0;
+    if (kd == CFS_OBS_BOX) {  // seg = [min corner, max corner]
+      for (int c = 0; c < 3; ++c) {
+        o.s[c] = seg[c + 6 * j];
+        o.d2[c] = seg[3 + c + 6 * j];
+        if (!(o.s[c] <= o.d2[c])) return fail(ctx, CFS_E_ARG, "cfs_set_obstacles: box %d has min > max on axis %d", j, c);
+      }
+      continue;
+    }
     double D2 = 0.0;
     for (int c = 0; c < 3; ++c) {
       o.s[c] = seg[c + 6 * j];
@@ -339,14 +353,16 @@ extern "C" int cfs_set_obstacles(cfs_ctx *ctx, const double *seg, const double *
     }
     for (int c = 0; c < 3; ++c) D2 += o.d2[c] * o.d2[c];  // distLinSeg.m:30
     o.D2 = D2;
-    o.D = D ? D[j] : 0.0;
-    o.eps = eps ? eps[j] : 0.0;
     o.rD2 = D2 != 0.0 ? 1.0 / D2 : 0.0;
   }
   t.nobs = n_obs;
   ctx->nobs = n_obs;
   ctx->have_obs = true;
   return upload_tables(ctx);
+}
+
+extern "C" int cfs_set_obstacles(cfs_ctx *ctx, const double *seg, const double *D, const double *eps, int n_obs) {
+  return cfs_set_obstacles_ex(ctx, seg, nullptr, D, eps, n_obs);
 }
 
 extern "C" int cfs_set_cost(cfs_ctx *ctx, int H, const double *QQ, const double *lim, const double *max_input) {

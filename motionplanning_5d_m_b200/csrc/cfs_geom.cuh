@@ -141,7 +141,77 @@ __device__ __forceinline__ double fixbound(double v) {  // distLinSeg.m:93-101
 #define CFS_TOUCH_KEY 1e-08
 __device__ __forceinline__ double key_to_dist(double k) { return k >= 0.0 ? sqrt(k) : -sqrt(-k); }
 
+// ---- N3 extension: solid axis-aligned box obstacles (obs{j}.shape = 'box', l = [min corner, max corner]) ----------------------
+// Squared distance between the link axis [p[0..2], p[3..5]] and the box, with the same touch rule as the capsule obstacles.
+// With x(t) = ps + t d and the signed per-axis excess e_k(x) (x_k - hi_k above, x_k - lo_k below, 0 inside), f(t) = sum e_k^2 is
+// convex and C1: g(t) = f'/2 = sum_k e_k d_k is piecewise linear and nondecreasing, its breakpoints are the (<= 6) parameters
+// where x_k crosses lo_k / hi_k.  t* = 0 if g(0) >= 0, 1 if g(1) <= 0, else the root of g: the nearest breakpoints on either
+// side of it are kept while g is evaluated at every breakpoint inside (0,1), then one linear interpolation.  Same algorithm,
+// same operation order as orc_dist_seg_box (oracle/cfs_oracle.c).
+__device__ __forceinline__ double box_excess_dot(const double p[6], const double d[3], const ObsTab &o, double t, double &ss) {
+  double g = 0.0;
+  ss = 0.0;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const double x = p[k] + d[k] * t;
+    const double e = x > o.d2[k] ? x - o.d2[k] : (x < o.s[k] ? x - o.s[k] : 0.0);
+    g += e * d[k];
+    ss += e * e;
+  }
+  return g;
+}
+
+// Not inlined (rare path, keeps the capsule path's code and registers as they were); scalar arguments only, so nothing goes
+// through local memory.  A negative key <=> the touch branch was taken.
+static __device__ __noinline__ double link_box_key(double p0, double p1, double p2, double p3, double p4, double p5, const ObsTab *op) {
+  const ObsTab &o = *op;
+  const double p[6] = {p0, p1, p2, p3, p4, p5};
+  double d[3], ss;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) d[k] = p[3 + k] - p[k];
+  double t;
+  const double g0 = box_excess_dot(p, d, o, 0.0, ss);
+  if (g0 >= 0.0) {
+    t = 0.0;
+  } else {
+    const double g1 = box_excess_dot(p, d, o, 1.0, ss);
+    if (g1 < 0.0) {
+      t = 1.0;
+    } else {
+      double tl = 0.0, gl = g0, th = 1.0, gh = g1;
+#pragma unroll 1
+      for (int k = 0; k < 3; ++k) {
+        if (d[k] == 0.0) continue;
+#pragma unroll 1
+        for (int side = 0; side < 2; ++side) {
+          const double c = ((side ? o.d2[k] : o.s[k]) - p[k]) / d[k];
+          if (!(c > 0.0 && c < 1.0)) continue;
+          const double gc = box_excess_dot(p, d, o, c, ss);
+          if (gc < 0.0) {
+            if (c > tl) { tl = c; gl = gc; }
+          } else if (c < th) {
+            th = c; gh = gc;
+          }
+        }
+      }
+      t = tl - gl * (th - tl) / (gh - gl);  // gl < 0 <= gh; gh == 0 gives t = th, the FIRST minimiser (entry point of a crossing)
+    }
+  }
+  (void)box_excess_dot(p, d, o, t, ss);
+  double key = ss;
+  if (key < CFS_TOUCH_KEY) {  // |dis| < 1e-4: dis = -norm(P1 - link end), the rule of dist_arm_3D_200i_2.m:22-24 applied to the box
+    const double wx = (p[0] + d[0] * t) - p[3], wy = (p[1] + d[1] * t) - p[4], wz = (p[2] + d[2] * t) - p[5];
+    key = -((wx * wx + wy * wy) + wz * wz);
+  }
+  return key;
+}
+
 __device__ __forceinline__ double link_obs_key(const double p[6], const ObsTab &o, int &touched) {
+  if (o.kind == CFS_OBS_BOX) {
+    const double key = link_box_key(p[0], p[1], p[2], p[3], p[4], p[5], &o);
+    if (key < 0.0) touched = 1;
+    return key;
+  }
   const double d1x = p[3] - p[0], d1y = p[4] - p[1], d1z = p[5] - p[2];
   const double d12x = o.s[0] - p[0], d12y = o.s[1] - p[1], d12z = o.s[2] - p[2];
   const double d2x = o.d2[0], d2y = o.d2[1], d2z = o.d2[2];

@@ -18,13 +18,17 @@ struct LinkTab {
 };  // 14 doubles = 112 B
 
 struct ObsTab {
-  double s[3];    // obs.l(:,1)
-  double d2[3];   // obs.l(:,2) - obs.l(:,1)   (distLinSeg.m:26, computed once, same value)
+  double s[3];    // obs.l(:,1)                                                    | box: min corner
+  double d2[3];   // obs.l(:,2) - obs.l(:,1)   (distLinSeg.m:26, computed once)    | box: max corner
   double D2;      // sum(d2.^2)                (distLinSeg.m:30)
   double D, eps;  // obs.D, obs.epsilon
   double rD2;     // RN(1/D2) (0 when D2 == 0): x / D2 is evaluated as q0 = x*rD2, q = q0 + (x - q0*D2)*rD2 with FMAs,
                   // which returns the correctly rounded quotient (Markstein) for 3 instructions instead of ~18
-};  // 10 doubles = 80 B
+  int kind;       // CFS_OBS_CAPSULE: capsule axis (every obstacle of the reference); CFS_OBS_BOX: solid axis-aligned box
+  int pad_[3];    //   (N3 extension, obs{j}.shape = 'box': e.g. the bounding box of an STL part of map/)
+};  // 12 doubles = 96 B
+#define CFS_OBS_CAPSULE 0
+#define CFS_OBS_BOX 1
 
 // Staged into shared memory with one TMA bulk copy (cp.async.bulk) per CTA.  sizeof % 16 == 0.
 struct DevTables {

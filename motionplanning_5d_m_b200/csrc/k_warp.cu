@@ -121,10 +121,10 @@ __device__ __forceinline__ void numjac_waypoint_lane(const DevTables &tab, const
 struct WarpSmem {
   size_t tab, mbar, regions, region_bytes, total;
 };
-__host__ __device__ inline WarpSmem warp_smem(int n, int nj, int OH, int zs, int wpc) {
+__host__ __device__ inline WarpSmem warp_smem(int n, int nj, int OH, int zs, int wpc, int nobs) {
   WarpSmem L;
   size_t o = 0;
-  L.tab = o; o += sizeof(DevTables);
+  L.tab = o; o += CFS_TAB_HEADER_BYTES + sizeof(ObsTab) * (size_t)nobs;  // only the staged part of DevTables
   L.mbar = o; o += 16;
   o = (o + 127) / 128 * 128;
   L.regions = o;
@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(NT) __maxnreg__(MAXREG) k_cfs_warp(SolveArgs a
   constexpr int WPC = NT / 32;
   const int n = a.n, H = a.H, O = a.nobs, OH = O * H, m = OH + 4 * n, N = 2 * n;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const WarpSmem L = warp_smem(n, NJ, OH, a.warp_zs, WPC);
+  const WarpSmem L = warp_smem(n, NJ, OH, a.warp_zs, WPC, O);
   DevTables &tab = *reinterpret_cast<DevTables *>(smem_raw + L.tab);
   uint64_t *mbar = reinterpret_cast<uint64_t *>(smem_raw + L.mbar);
   tma_stage(&tab, a.tab, tab_bytes(a.nobs), mbar);
@@ -357,7 +357,7 @@ __global__ void __launch_bounds__(NT) __maxnreg__(MAXREG) k_cfs_warp(SolveArgs a
 static const int kWarpNT[WARP_NCFG] = {384, 96, 128, 32, 64};
 
 size_t warp_smem_bytes(const SolveArgs &a, int cfg) {
-  return warp_smem(a.n, a.nj, a.nobs * a.H, a.warp_zs, kWarpNT[cfg] / 32).total;
+  return warp_smem(a.n, a.nj, a.nobs * a.H, a.warp_zs, kWarpNT[cfg] / 32, a.nobs).total;
 }
 
 bool warp_supported(const SolveArgs &a, int cfg) {

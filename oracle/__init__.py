@@ -92,10 +92,21 @@ def dist_lin_seg(p1s, p1e, p2s, p2e):
     return d, pts
 
 
-def obs6(l):
-    """obs{j}.l (3x2, columns = endpoints) -> flat [start(3), end(3)]"""
+def obs6(l, box=False):
+    """obs{j}.l (3x2, columns = endpoints, or min / max corner of a box) -> obstacle record [l(:,1), l(:,2), kind] (7 doubles)"""
+    if isinstance(l, dict):
+        l, box = l["l"], l.get("shape") == "box"
     l = np.asarray(l, dtype=np.float64)
-    return _f64(np.concatenate([l[:, 0], l[:, 1]]))
+    return _f64(np.concatenate([l[:, 0], l[:, 1], [1.0 if box else 0.0]]))
+
+
+def dist_seg_box(ps, pe, lo, hi):
+    """N3 extension: (distance, closest point of the segment) between [ps, pe] and the solid box [lo, hi]"""
+    pt = np.zeros(3)
+    f = lib().orc_dist_seg_box
+    f.restype = C.c_double
+    d = f(_p(_f64(ps)), _p(_f64(pe)), _p(_f64(lo)), _p(_f64(hi)), _p(pt))
+    return d, pt
 
 
 def dist_arm(r, theta, o6):

@@ -213,9 +213,71 @@ double orc_dist_lin_seg(const double *p1s, const double *p1e, const double *p2s,
 /* link distance with the "negative when axes touch" heuristic.
  * dist_arm_3D_200i_2.m:21-24 / dist_link_Heu.m:18-21 form (points(1:3)).  On M16iB the class path
  * (dist_arm_3D_Heu_2.m:23) subtracts a 3x1 from a 6x1 and MATLAB throws: flagged via *touched. */
+/* ---- N3: box obstacles -- an EXTENSION, the reference only has capsule-axis obstacles (obs{j}.l as a line
+ * segment; its mesh path Lib/functions/dist_arm_surface.m:44 calls point2surface_dis, which is defined nowhere).  An obstacle
+ * record is ORC_OBS_STRIDE = 7 doubles: [l(:,1); l(:,2); kind].  kind 0: capsule axis from l(:,1) to l(:,2).  kind 1
+ * (obs{j}.shape = 'box'): the solid axis-aligned box with min corner l(:,1) and max corner l(:,2), e.g. the bounding box of an
+ * STL part of map/ (MapFromSTL.m:1-12 reads those in mm; the robot lives in m).
+ *
+ * orc_dist_seg_box: distance between the segment [ps, pe] and the solid box [lo, hi], and the closest point of the segment.
+ * With x(t) = ps + t (pe - ps) and the signed per-axis excess e_k(x) = x_k - hi_k (x_k > hi_k), x_k - lo_k (x_k < lo_k), 0 inside,
+ * f(t) = sum_k e_k(x(t))^2 is convex and C1, so g(t) = f'(t)/2 = sum_k e_k d_k is continuous, piecewise linear and
+ * nondecreasing with breakpoints where x_k(t) crosses lo_k / hi_k.  The FIRST minimiser over [0,1]: t = 0 if g(0) >= 0, t = 1 if
+ * g(1) < 0, else the first root of g, found exactly by evaluating g at the (<= 6) breakpoints inside (0,1), keeping the nearest one
+ * on either side of the root and interpolating linearly between them.  A segment that meets the box gives distance 0 at the
+ * first such t. */
+static double box_excess_dot(const double *ps, const double *d, const double *lo, const double *hi, double t, double *f) {
+  double g = 0.0, ss = 0.0;
+  for (int k = 0; k < 3; ++k) {
+    const double x = ps[k] + d[k] * t;
+    const double e = x > hi[k] ? x - hi[k] : (x < lo[k] ? x - lo[k] : 0.0);
+    g += e * d[k];
+    ss += e * e;
+  }
+  if (f) *f = ss;
+  return g;
+}
+
+double orc_dist_seg_box(const double *ps, const double *pe, const double *lo, const double *hi, double *point /*3 or NULL*/) {
+  double d[3];
+  for (int k = 0; k < 3; ++k) d[k] = pe[k] - ps[k];
+  double t;
+  const double g0 = box_excess_dot(ps, d, lo, hi, 0.0, NULL);
+  if (g0 >= 0.0) {
+    t = 0.0;
+  } else {
+    const double g1 = box_excess_dot(ps, d, lo, hi, 1.0, NULL);
+    if (g1 < 0.0) {
+      t = 1.0;
+    } else {
+      double tl = 0.0, gl = g0, th = 1.0, gh = g1;
+      for (int k = 0; k < 3; ++k) {
+        if (d[k] == 0.0) continue;
+        for (int side = 0; side < 2; ++side) {
+          const double c = ((side ? hi[k] : lo[k]) - ps[k]) / d[k];
+          if (!(c > 0.0 && c < 1.0)) continue;
+          const double gc = box_excess_dot(ps, d, lo, hi, c, NULL);
+          if (gc < 0.0) {
+            if (c > tl) { tl = c; gl = gc; }
+          } else if (c < th) {
+            th = c; gh = gc;
+          }
+        }
+      }
+      t = tl - gl * (th - tl) / (gh - gl);  // gl < 0 <= gh; gh == 0 gives t = th, the FIRST minimiser (entry point of a crossing)
+    }
+  }
+  double ss;
+  (void)box_excess_dot(ps, d, lo, hi, t, &ss);
+  if (point)
+    for (int k = 0; k < 3; ++k) point[k] = ps[k] + d[k] * t;
+  return sqrt(ss);
+}
+
 static double link_dist(const double *pos_i /* 2*3 */, const double *obs6, int *touched) {
   double points[6];
-  double dis = orc_dist_lin_seg(pos_i, pos_i + 3, obs6, obs6 + 3, 3, points);
+  double dis = obs6[6] == 1.0 ? orc_dist_seg_box(pos_i, pos_i + 3, obs6, obs6 + 3, points)
+                              : orc_dist_lin_seg(pos_i, pos_i + 3, obs6, obs6 + 3, 3, points);
   if (fabs(dis) < 0.0001) {
     double ss = 0;
     for (int k = 0; k < 3; ++k) {
@@ -543,7 +605,7 @@ int orc_get_con(const orc_robot *r, const orc_cfg *c, const double *x0, const do
   const int rows_per = c->lim ? 1 + 2 * nj : 1;
   int row = 0;
   for (int j = 0; j < c->nobs; ++j) {
-    const double *obs6 = c->obs + 6 * j;
+    const double *obs6 = c->obs + ORC_OBS_STRIDE * j;
     for (int i = 1; i <= H; ++i) {
       const double *theta = xcur + ns * (i - 1); /* :114 */
       int lid = 0;
@@ -1027,7 +1089,7 @@ int orc_rrt_feasible(const orc_robot *r, const double *theta, int nobs, const do
   for (int j = 0; j < nobs; ++j) {
     orc_cap_pos(r, theta, pos);
     for (int i = 0; i < r->nj; ++i) {
-      const double dis = link_dist(pos + 6 * i, obs + 6 * j, touched);
+      const double dis = link_dist(pos + 6 * i, obs + ORC_OBS_STRIDE * j, touched);
       if (dis < dm) dm = dis;
       if (dis < D[j]) feas = 0;
     }

@@ -51,7 +51,7 @@ typedef struct {
 typedef struct {
   int H;                /* horizon                                                            */
   int nobs;             /* obstacles                                                          */
-  const double *obs;    /* 6*nobs: obs{j}.l(:,1), obs{j}.l(:,2)                               */
+  const double *obs;    /* ORC_OBS_STRIDE*nobs: obs{j}.l(:,1), obs{j}.l(:,2), kind (0 capsule axis, 1 box) */
   const double *margin; /* nobs: obs{j}.epsilon (CFS_FANUC.m:117) or obs{j}.D (PSGCFS:158)    */
   const double *QQ;     /* n*n (symmetric)                                                    */
   const double *lim;    /* nj   velocity limit, NULL = no velocity rows (M16iB/main_CFS.m)    */
@@ -63,7 +63,10 @@ typedef struct {
   double alpha;         /* PSG step (sys_info.alpha)                                          */
 } orc_cfg;
 
+#define ORC_OBS_STRIDE 7 /* doubles per obstacle record: l(:,1), l(:,2), kind */
 void orc_robot_init(orc_robot *r, int kind);
+/* N3 extension: distance between a segment and a solid axis-aligned box, closest point of the segment in point[3] */
+double orc_dist_seg_box(const double *ps, const double *pe, const double *lo, const double *hi, double *point);
 
 /* geometry */
 void   orc_cap_pos(const orc_robot *r, const double *theta, double *pos /* nj*2*3 */);

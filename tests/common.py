@@ -81,14 +81,14 @@ def oracle_problem(O, ROBOT, obs, s, solver=0, grad=0, margin=None, max_input="d
     if margin is None:
         margin = [o["epsilon"] if solver == 0 else o["D"] for o in obs]
     mi = s["MAX_input"] if max_input == "default" else max_input
-    return O.Problem(O.robot(ROBOT), s["H"], [o["l"] for o in obs], margin, s["QQ"], s.get("lim"),
+    return O.Problem(O.robot(ROBOT), s["H"], list(obs), margin, s["QQ"], s.get("lim"),
                      mi if solver == 0 else None, s["epsilon_O"], s["MAX_O_ITER"], solver=solver, grad=grad,
                      alpha=s.get("alpha", 0.0))
 
 
 def oracle_feasible_fn(O, ROBOT, obs):
     r = O.robot(ROBOT)
-    o6 = [O.obs6(o["l"]) for o in obs]
+    o6 = [O.obs6(o) for o in obs]
 
     def fn(cand):
         return np.array([all(O.dist_arm(r, th, o)[0] >= ob["D"] for o, ob in zip(o6, obs)) for th in cand])

@@ -28,6 +28,10 @@ size_t mxGetM(const mxArray *a);
 size_t mxGetN(const mxArray *a);
 size_t mxGetNumberOfElements(const mxArray *a);
 bool mxIsEmpty(const mxArray *a);
+bool mxIsDouble(const mxArray *a);
+bool mxIsStruct(const mxArray *a);
+bool mxIsCell(const mxArray *a);
+bool mxIsChar(const mxArray *a);
 mxArray *mxGetField(const mxArray *s, size_t index, const char *name);
 mxArray *mxGetCell(const mxArray *c, size_t index);
 int mxGetString(const mxArray *a, char *buf, size_t buflen);

@@ -128,3 +128,164 @@ def derivest(fun, x0):
     err = errors[tags]
     ind = int(np.argmin(err))
     return der_romb[tags][ind], err[ind], h * delta[tags][ind]
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# The solver classes, restated independently of the C oracle (own row assembly, own QP): Lib/CFS_FANUC.m, Lib/PSGCFS_FANUC.m,
+# Lib/EVAL.m.  quadprog is replaced by a primal-dual interior-point method (the algorithm family quadprog's default
+# 'interior-point-convex' belongs to) followed by an active-set polish to KKT <= 1e-10; the oracle uses a dual active-set
+# (Goldfarb-Idnani) solver, so agreement of the two pins get_con / the loop / the stop rule above the leaf functions.
+# ---------------------------------------------------------------------------------------------------------------------------
+def cap_pos2(base, theta, robot):
+    """Lib/2L/CapPos2.m:16-29 (planar chain: R = Rz(theta), T = robot.T(:,i+1))"""
+    M = np.eye(4)
+    M[:3, 3] = robot["T"][:, 0]
+    pos = []
+    for i in range(len(theta)):
+        c, s = np.cos(theta[i]), np.sin(theta[i])
+        X = np.eye(4)
+        X[:3, :3] = np.array([[c, -s, 0], [s, c, 0], [0, 0, 1.0]])
+        X[:3, 3] = robot["T"][:, i + 1] if i + 1 < robot["T"].shape[1] else robot["T"][:, -1]
+        M = M @ X
+        cp = robot["cap"][i]["p"]
+        pos.append(np.stack([M[:3, :3] @ cp[:, k] + M[:3, 3] + base for k in range(2)], axis=1))
+    return pos
+
+
+def dist_arm_all(theta, robot, obs, kind):
+    if kind != "2L":
+        return dist_arm(theta, robot, obs, kind)
+    raise NotImplementedError("the 2L chain is cross-checked at leaf level only (tests/test_oracle.py)")
+
+
+def qp_ipm(Hm, f, A, b, tol=1e-11, max_iter=200):
+    """min 1/2 x'Hx + f'x  s.t.  A x <= b   (H symmetric positive definite): Mehrotra predictor-corrector, then the active set
+    is read off the multipliers and the equality-constrained KKT system is solved exactly (polish).  Returns x, kkt, n_active;
+    raises ValueError when the iteration does not converge (infeasible problem)."""
+    Hm = 0.5 * (Hm + Hm.T)
+    Ab = np.unique(np.column_stack([A, b]), axis=0)             # the velocity rows are duplicated once per obstacle (CFS_FANUC.m:110)
+    A, b = Ab[:, :-1], Ab[:, -1]
+    m, n = A.shape
+    sc = np.abs(Hm).max()                                       # scale the objective: multipliers of order one
+    Hs, fs = Hm / sc, f / sc
+    x = np.linalg.solve(Hs, -fs)
+    s = np.maximum(b - A @ x, 1.0)
+    z = np.ones(m)
+    ok = False
+    for it in range(max_iter):
+        rd = Hs @ x + fs + A.T @ z
+        rp = A @ x + s - b
+        mu = s @ z / m
+        if max(np.abs(rd).max(), np.abs(rp).max()) < 1e-9 and mu < 1e-10:
+            ok = True                                           # moderately converged: the polish below makes it exact
+            break
+        d = z / s
+        K = Hs + A.T @ (d[:, None] * A)
+
+        def solve(rc):
+            rhs = -rd - A.T @ (d * rp) + A.T @ (rc / s)          # eliminate ds, dz
+            dx = np.linalg.solve(K, rhs)
+            ds = -rp - A @ dx
+            dz = -(rc + z * ds) / s
+            return dx, ds, dz
+        dxa, dsa, dza = solve(s * z)                            # predictor (mu = 0)
+
+        def step(v, dv):
+            neg = dv < 0
+            return min(1.0, (-v[neg] / dv[neg]).min()) if neg.any() else 1.0
+        aa = min(step(s, dsa), step(z, dza))
+        mu_aff = (s + aa * dsa) @ (z + aa * dza) / m
+        sigma = (mu_aff / mu) ** 3
+        dx, ds, dz = solve(s * z + dsa * dza - sigma * mu)      # corrector
+        a = 0.995 * min(step(s, ds), step(z, dz))
+        x, s, z = x + a * dx, s + a * ds, z + a * dz
+        if not (np.isfinite(x).all() and np.isfinite(z).all()) or np.abs(z).max() > 1e14:
+            break
+    if not ok:
+        raise ValueError("interior-point iteration did not converge (QP infeasible?)")
+    # polish: active set = rows whose multiplier dominates their slack
+    act = np.where(z > s)[0]
+    Lc = np.linalg.cholesky(Hm)
+    hinv = lambda v: np.linalg.solve(Lc.T, np.linalg.solve(Lc, v))
+    xu = hinv(-f)
+    for _ in range(400):                                        # one change per pass: most violated row in, else worst multiplier out
+        if len(act):                                             # Schur complement on the active rows: (Aa H^-1 Aa') lam = Aa xu - ba
+            Aa = A[act]
+            Y = hinv(Aa.T)
+            lam = np.linalg.solve(Aa @ Y, Aa @ xu - b[act])
+            xp = xu - Y @ lam
+        else:
+            xp, lam = xu, np.zeros(0)
+        viol = (A @ xp - b) / (1 + np.abs(b))
+        viol[act] = 0.0
+        if viol.max() > 1e-10:
+            act = np.append(act, int(np.argmax(viol)))
+        elif len(act) and lam.min() < -1e-9 * max(np.abs(lam).max(), 1e-300):
+            act = np.delete(act, int(np.argmin(lam)))
+        else:
+            kkt = np.abs(Hm @ xp + f + (A[act].T @ lam if len(act) else 0)).max() / np.abs(Hm).max()
+            return xp, kkt, len(act)
+    raise ValueError("active-set polish did not settle")
+
+
+def get_con(x_, u, x0, robot, obs_list, kind, Aaug, Baug, lim, H, nj, margin_key):
+    """Lib/CFS_FANUC.m:101-135 (margin obs.epsilon) / Lib/PSGCFS_FANUC.m:145-184 (margin obs.D): per obstacle j and step i one
+    obstacle row, then nj rows +Baug_w and nj rows -Baug_w -- the velocity rows are appended INSIDE the obstacle loop, so
+    they are duplicated once per obstacle (CFS_FANUC.m:110,126-129)."""
+    ns = 2 * nj
+    Ls, Ss = [], []
+    for obs in obs_list:
+        for i in range(H):
+            theta = x_[ns * i:ns * i + nj]
+            f = lambda th: dist_arm(th, robot, obs["l"], kind)[0]
+            d, _ = dist_arm(theta, robot, obs["l"], kind)
+            g = num_jac(f, theta)
+            Bj = Baug[ns * i:ns * (i + 1), :]
+            Ls.append(-g @ Bj[:nj, :])
+            Ss.append((d - obs[margin_key]) - g @ Bj[:nj, :] @ u)
+            if lim is not None:
+                Aw = Aaug[ns * i + nj:ns * (i + 1), :] @ x0
+                for k in range(nj):
+                    Ls.append(Bj[nj + k, :])
+                    Ss.append(lim[k] - Aw[k])
+                for k in range(nj):
+                    Ls.append(-Bj[nj + k, :])
+                    Ss.append(lim[k] + Aw[k])
+    return np.array(Ls), np.array(Ss)
+
+
+def cfs_optimizer(s, robot, obs_list, kind, psg=False, noise=None):
+    """CFS_FANUC.optimizer (Lib/CFS_FANUC.m:62-98) / PSGCFS_FANUC.optimizer (Lib/PSGCFS_FANUC.m:65-128) with EVAL's stop rule
+    (Lib/EVAL.m:61-73: ||x_ - x_old|| < epsilon_O or iter_O > MAX_O_ITER, x_old initialised to ones and, in PSGCFS, never
+    updated).  Returns u, x_, cost_all, iters."""
+    H, nj = s["H"], s["njoint"]
+    n = H * nj
+    A, Bm = s["Aaug"], s["Baug"]
+    QQ, ff, caug = s["QQ"], s["ff"], s["caug"]
+    x0 = s["xR"][:, 0]
+    x_ = np.array(s["x_"], dtype=np.float64)
+    u = np.zeros(n)                                              # CFS_FANUC.m:56 (iteration 1 linearises at x_ but around u = 0)
+    x_old = np.ones_like(x_)                                     # EVAL.m:47
+    cost_all = []
+    cost_old, cost_new = 100000.0, caug                          # EVAL.m:29, PSGCFS_FANUC.m:66
+    iter_O = 1
+    get_cost = lambda v: 0.5 * v @ QQ @ v + ff @ v + caug        # EVAL.m:51-53
+    while not (np.linalg.norm(x_ - x_old) < s["epsilon_O"] or iter_O > s["MAX_O_ITER"]):
+        Ainq, binq = get_con(x_, u, x0, robot, obs_list, kind, A, Bm, s.get("lim"), H, nj, "D" if psg else "epsilon")
+        if psg:
+            if not abs(cost_new - cost_old) < 1e-4:              # stop_inner, PSGCFS_FANUC.m:136-142 (MAX_I_ITER = 1)
+                cost_old = cost_new
+                nz = noise[iter_O - 1] if noise is not None else np.zeros(n)
+                u_ = u - s["alpha"] * ((QQ @ u + ff) + 10 * nz / (iter_O ** 2 + 1))     # PSG_update_arm, :106-112
+                u, _, _ = qp_ipm(np.eye(n), -u_, Ainq, binq)                          # Projection, :115-128 (no bounds)
+        else:
+            mi = s["MAX_input"]
+            Aall = np.vstack([Ainq, np.eye(n), -np.eye(n)])                          # lb / ub of CFS_FANUC.m:85
+            ball = np.concatenate([binq, mi, mi])
+            x_old = x_.copy()                                                         # CFS_FANUC.m:88
+            u, _, _ = qp_ipm(QQ, ff, Aall, ball)
+        x_ = A @ x0 + Bm @ u                                     # roll-out, CFS_FANUC.m:90-94
+        cost_new = get_cost(u)
+        cost_all.append(cost_new)
+        iter_O += 1
+    return u, x_, np.array(cost_all), iter_O - 1

@@ -274,3 +274,75 @@ def test_nodes_feasible_and_nearest(ctx, oracle):
         assert parent[k] == p
         ref_new = nodes[p] + (samples[k] - nodes[p]) * 0.1 / np.linalg.norm(nodes[p] - samples[k])
         assert np.abs(new[k] - ref_new).max() < 1e-14
+
+
+def test_touch_threshold_band(ctx, oracle):
+    """dist_arm_3D_200i_2.m:22-24: `if norm(dis) < 0.0001, dis = -norm(points(1:3,1) - pos{i}.p(:,2))` is a 0.07-wide jump.  The
+    configurations here sit on both sides of that threshold, as close as bisection on the oracle can place them: the raw axis
+    distance is 1e-4 +- delta for delta from 1e-13 (about a hundred times the last-place differences between two FP64 FK
+    evaluations) up to 1e-6.  On every one of them the stand-alone K1 and K1d kernels and the fused solver must take the SAME
+    branch as the oracle: sign and link id identical, value within 1e-12, TOUCH flag identical.  (Closer than 1e-13 the branch
+    is decided by the last bits of sin/cos: not a property any two implementations of the reference share.)"""
+    O = oracle
+    ROBOT, robot, obs, s = common.main_fanuc_config()
+    _set(ctx, ROBOT, robot, obs, s)
+    r = O.robot(ROBOT)
+    o6 = O.obs6(obs[0]["l"])
+    x0 = np.array([0.7825, 0.0284, 0.2172, 0.1444, -1.1779])
+    xg = np.array([-0.7825, 0.0284, 0.2172, 0.1444, -1.1779])
+    th = lambda t: x0 + (xg - x0) * t
+    raw = lambda t: O.dist_arm(r, th(t), o6)[0]
+    # the reference line of main_FANUC.m passes through the touch zone around waypoint 18 (t = 0.6): bracket both edges
+    ts = np.linspace(0.5, 0.7, 4001)
+    d = np.array([raw(t) for t in ts])
+    edges = [k for k in range(len(ts) - 1) if (d[k] < 0) != (d[k + 1] < 0)]
+    assert len(edges) >= 2
+    cases = []
+    for k in edges[:2]:
+        lo, hi = ts[k], ts[k + 1]
+        neg_lo = d[k] < 0
+        for _ in range(200):
+            mid = 0.5 * (lo + hi)
+            if mid == lo or mid == hi:
+                break
+            if (raw(mid) < 0) == neg_lo:
+                lo = mid
+            else:
+                hi = mid
+        # slope of the raw distance just outside the zone, to convert a distance offset into an offset of t
+        out_t, in_sign = (hi, -1.0) if neg_lo else (lo, 1.0)
+        h = 1e-7
+        slope = abs(raw(out_t - in_sign * 2 * h) - raw(out_t - in_sign * h)) / h
+        for delta in (1e-13, 3e-13, 1e-12, 1e-11, 1e-10, 1e-9, 1e-8, 1e-7, 1e-6):
+            cases.append(out_t - in_sign * delta / slope)        # outside the zone: positive distance ~ 1e-4 + delta
+            cases.append(out_t + in_sign * delta / slope)        # inside: negative branch
+    T = np.array(cases)
+    TH = np.stack([th(t) for t in T])
+    ref = [O.dist_arm(r, q, o6) for q in TH]
+    dref, lref = np.array([v[0] for v in ref]), np.array([v[1] for v in ref])
+    assert (dref < 0).sum() >= 12 and (dref > 0).sum() >= 12 and np.abs(dref[dref > 0] - 1e-4).min() < 1e-12
+    for gm in (_lib.GRAD_NUMJAC, _lib.GRAD_DERIVEST):
+        dist, lid, g, flags = ctx.dist_grad(TH, grad=gm)
+        assert (np.sign(dist[:, 0]) == np.sign(dref)).all(), gm
+        assert (lid[:, 0] == lref).all() and np.abs(dist[:, 0] - dref).max() < 1e-12, gm
+        assert ((flags & _lib.FLAG_TOUCH) != 0)[dref < 0].all()
+    # the fused solver: one problem per configuration, whose reference line has that configuration as EVERY waypoint, one outer
+    # iteration: the rows it builds (and hence status incl. the TOUCH flag, and x_) must match the oracle's
+    B = len(T)
+    s1 = dict(s)
+    s1["MAX_O_ITER"] = 1
+    xref = np.tile(np.concatenate([TH, np.zeros((B, 5))], axis=1), (1, s["H"]))
+    x0b = np.concatenate([TH, np.zeros((B, 5))], axis=1)
+    from motionplanning_5d_m_b200 import problem
+    gaug = np.tile(np.concatenate([np.tile(xg, (B, 1)), np.zeros((B, 5))], axis=1), (1, s["H"]))
+    Aaug, Baug, Qaug, QQ = problem.build_cost_matrices(robot, 5, s["H"], problem.Q_MAIN_FANUC, problem.R_MAIN_FANUC, 50.0)
+    ff, caug = problem.build_linear_term(Aaug, Baug, Qaug, x0b, gaug)
+    P = common.oracle_problem(O, ROBOT, obs, s1)
+    refs = P.solve_batch(x0b, ff, caug, xref, nthreads=8)
+    out = ctx.solve_batch(x0b, ff, caug, xref, s1["epsilon_O"], 1)
+    assert np.array_equal(out["status"], refs["status"]) and np.array_equal(out["iters"], refs["iters"])
+    # (status includes CFS_FLAG_TOUCH, the OR over the base AND the +-eps/2 evaluations of num_jac: equal to the oracle's above)
+    assert ((out["status"] & _lib.FLAG_TOUCH) != 0)[dref < 0].all()
+    ok = (refs["status"] & 0xFF) < 2
+    if ok.any():
+        assert np.abs(out["x"][ok] - refs["x"][ok]).max() < 1e-6

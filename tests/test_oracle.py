@@ -258,3 +258,24 @@ def test_rrt_find_route_restatement_properties(oracle):
     assert O.rrt_find_route(r, seg, D, x0, goal, region_g, region_s, off, goal, ratial, np.full(10, 0.3)) is None   # stream too short
     one = O.rrt_find_route(r, seg, D, goal, goal, region_g, region_s, off, goal, ratial, np.zeros(1))              # starts in the goal box
     assert len(one["route"]) == 1 and one["rnd_used"] == 0 and not one["fail"]
+
+
+@pytest.mark.parametrize("case", ["main_fanuc_cfs", "rrtstar_cfs", "main_fanuc_psgcfs"])
+def test_solver_loop_against_an_independent_restatement(oracle, case):
+    """the frozen oracle goldens of the shipped configurations against tests/np_restatement.py's own
+    get_con (duplicated velocity rows), CFS / PSGCFS loop (iteration-1 u = 0 quirk, EVAL stop rule, x_old = ones) and its own
+    QP (interior point + active-set polish) -- a second implementation that shares no code with oracle/cfs_oracle.c."""
+    g = common.golden("cases.npz")
+    if case == "rrtstar_cfs":
+        ROBOT, robot, obs, s = common.rrtstar_route_config(common.golden("inputs.npz")["route_wp"])
+    else:
+        ROBOT, robot, obs, s = common.main_fanuc_config()
+    psg = case.endswith("psgcfs")
+    noise = np.random.default_rng(123).normal(0.0, 0.1, size=(1, s["MAX_O_ITER"], s["H"] * 5))[0] if psg else None
+    rb = dict(robot)
+    rb["cap"] = [{"p": np.asarray(c["p"], dtype=np.float64)[:, :2]} for c in robot["cap"]]
+    u, x_, cost_all, iters = NP.cfs_optimizer(s, rb, obs, ROBOT, psg=psg, noise=noise)
+    assert iters == int(g[case + ".iters"])
+    assert np.abs(x_ - g[case + ".x"]).max() < 1e-7 and np.abs(u - g[case + ".u"]).max() < 1e-7
+    ref = g[case + ".cost_hist"][:iters]
+    assert np.all(np.abs(cost_all - ref) <= 1e-7 * np.abs(ref))
