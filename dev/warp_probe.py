@@ -13,8 +13,9 @@ H, nj, K = 50, 5, 20
 robot = dict(M.robotproperty2("M16iB")); robot["name"] = "M16iB"
 ctx = M.Context(0)
 ctx.set_robot(robot, nj); ctx.set_obstacles([synthetic.OBS_M16IB])
-MODES = [("cta", dict(warp=0)), ("warp12 noscreen", dict(warp=1, warp_cfg=0, warp_zs=0, screen=0)), ("warp12 screen", dict(warp=1, warp_cfg=0, warp_zs=0, screen=1)),
-         ("warp2x5 screen", dict(warp=1, warp_cfg=4, warp_zs=3, screen=1)), ("warp2x5 screen hg32", dict(warp=1, warp_cfg=4, warp_zs=3, screen=1, heavy_grid=32))]
+MODES = [("cta", dict(warp=0)), ("warp q15", dict(warp=1, warp_cfg=3, warp_qcap=15)), ("warp q24", dict(warp=1, warp_cfg=3, warp_qcap=24)),
+         ("warp q32", dict(warp=1, warp_cfg=3, warp_qcap=32)), ("warp q48", dict(warp=1, warp_cfg=3, warp_qcap=48)),
+         ("warp q48 esc96", dict(warp=1, warp_cfg=3, warp_qcap=48, esc_steps=96))]
 LEVEL = int(sys.argv[3]) if len(sys.argv) > 3 else 1
 for seed in range(SEEDS):
     cfg = synthetic.batch_config_m16ib(B, lambda cand: ctx.nodes_feasible(cand)[0], horizon=H, seed=synthetic.SEED + seed)
@@ -23,7 +24,7 @@ for seed in range(SEEDS):
     args = [cfg[k] for k in ("x0", "ff", "caug", "xref")]
     base = None
     for name, opts in MODES:
-        ctx.set_option("esc_steps", 48); ctx.set_option("heavy_cfg", 0); ctx.set_option("heavy_grid", 0); ctx.set_option("screen", 1)
+        ctx.set_option("esc_steps", 48); ctx.set_option("heavy_cfg", 0); ctx.set_option("heavy_grid", 48); ctx.set_option("screen", 1)
         for k, v in opts.items(): ctx.set_option(k, v)
         ctx.set_timing(LEVEL)
         best = None

@@ -94,6 +94,8 @@ struct cfs_ctx {
                           // 3 = 1 warp x 10 CTAs/SM (default: the finest granularity pipelines best across contexts), 4 = 2 x 5
   int warp_zs = 0;        // cfs_set_option("warp_zs"): direction slots in shared memory (0 = as many as fit, at most 4)
   int screen = 1;         // cfs_set_option("screen"): warp tier in two launches (iteration 1 | the rest), heavy tier starts after the first
+  int warp_qcap = 15;     // cfs_set_option("warp_qcap"): working-set rows the warp tier keeps (<= 31; inverse + directions spill to L2 beyond 16:
+                          // measured, a single warp on a 16..31-row working set lengthens the tail more than the heavy tier costs)
   int heavy_cfg = 0;      // cfs_set_option("heavy_cfg"): 0 = 144 x 144 inverse on chip (whole SM), 1 = slim (64 x 64 on chip, 168 registers)
   int heavy_skip = 0;     // cfs_set_option("heavy_skip"): measurement only -- the heavy tier is not launched (escalated problems keep status 4)
   bool fused_last = false;
@@ -535,6 +537,7 @@ static int solve_device(cfs_ctx *ctx, int B, int solver, int grad, const double 
   const bool fused = ctx->use_fused && !psg && grad == CFS_GRAD_NUMJAC && fused_supported(a);
   // bulk tier of the fused solver: one warp per problem (k_warp.cu) when its shared-memory regions fit
   bool warp = false;
+  a.warp_qcap = ctx->warp_qcap;
   if (fused && ctx->use_warp) {
     for (int zs = ctx->warp_zs > 0 ? ctx->warp_zs : 4; zs >= 1 && !warp; --zs) {
       a.warp_zs = zs;
@@ -557,7 +560,7 @@ static int solve_device(cfs_ctx *ctx, int B, int solver, int grad, const double 
     const int wpc = warp_warps_per_cta(ctx->warp_cfg);
     if (grid > (B + wpc - 1) / wpc) grid = (B + wpc - 1) / wpc;
     if (grid < 1) grid = 1;
-    if ((rc = ensure(ctx, ctx->zslab, sizeof(double) * (size_t)grid * wpc * 16 * n))) return rc;
+    if ((rc = ensure(ctx, ctx->zslab, warp_slab_bytes_per_warp(a) * (size_t)grid * wpc))) return rc;
     a.zslab = ptr<double>(ctx->zslab);
   }
   if (grid > B) grid = B;
@@ -1442,6 +1445,7 @@ extern "C" int cfs_set_option(cfs_ctx *ctx, const char *name, int value) {
   if (strcmp(name, "heavy_skip") == 0) { ctx->heavy_skip = value; return 0; }
   if (strcmp(name, "warp_cfg") == 0) { ctx->warp_cfg = value; return 0; }
   if (strcmp(name, "warp_zs") == 0) { ctx->warp_zs = value; return 0; }
+  if (strcmp(name, "warp_qcap") == 0) { ctx->warp_qcap = value; return 0; }
   return fail(ctx, CFS_E_ARG, "cfs_set_option: unknown option '%s'", name);
 }
 

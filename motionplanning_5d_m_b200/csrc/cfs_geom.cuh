@@ -105,6 +105,19 @@ __device__ __forceinline__ void xf_step_inplace(Xf &M, const LinkTab &L, double 
   }
 }
 
+// M <- M * [R T; 0 0 0 1] with R, T already built by link_RT: the same products as xf_step_inplace (two chains that take the
+// same link step -- same joint angle -- share R and T)
+__device__ __forceinline__ void xf_apply_inplace(Xf &M, const double R[9], const double T[3]) {
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    const double m0 = M.m[4 * a], m1 = M.m[4 * a + 1], m2 = M.m[4 * a + 2], m3 = M.m[4 * a + 3];
+    M.m[4 * a + 0] = m0 * R[0] + m1 * R[3];  // + m2*0
+    M.m[4 * a + 1] = (m0 * R[1] + m1 * R[4]) + m2 * R[7];
+    M.m[4 * a + 2] = (m0 * R[2] + m1 * R[5]) + m2 * R[8];
+    M.m[4 * a + 3] = ((m0 * T[0] + m1 * T[1]) + m2 * T[2]) + m3;
+  }
+}
+
 // pos{i}.p(:,k) = M(1:3,1:3)*cap.p(:,k) + M(1:3,4) + base   (CapPos.m:18-20); p[0..2]=start, p[3..5]=end
 __device__ __forceinline__ void link_endpoints(const Xf &M, const LinkTab &L, const double base[3], double p[6]) {
 #pragma unroll

@@ -134,6 +134,7 @@ struct SolveArgs {
   // warp-per-problem bulk tier (k_warp.cu)
   double *zslab;              // per-warp overflow of the direction cache: (WQ_QZ - warp_zs) * n doubles per resident warp
   int warp_zs;                // direction slots kept in shared memory
+  int warp_qcap;              // working-set capacity of the warp tier (rows), <= 31; beyond it -> heavy tier
   // phase 0: every problem start to finish.  phase 1 ("screen"): outer iteration 1 only; problems that are not finished go
   // to cont_list.  phase 2: resume the problems of cont_list from outer iteration 2 (state in x / u / iters / touch).
   int phase;
@@ -160,6 +161,7 @@ bool warp_supported(const SolveArgs &a, int cfg);  // CFS solver, num_jac gradie
 size_t warp_smem_bytes(const SolveArgs &a, int cfg);
 int warp_max_grid(const SolveArgs &a, int device, int cfg);
 int warp_warps_per_cta(int cfg);
+size_t warp_slab_bytes_per_warp(const SolveArgs &a);
 cudaError_t launch_warp(const SolveArgs &a, int grid, int cfg, cudaStream_t s);
 
 // ---- dense get_con rows (one problem) -------------------------------------------------------------------------

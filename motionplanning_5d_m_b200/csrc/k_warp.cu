@@ -145,7 +145,9 @@ __global__ void __launch_bounds__(NT) __maxnreg__(MAXREG) k_cfs_warp(SolveArgs a
   tma_stage(&tab, a.tab, tab_bytes(a.nobs), mbar);
 
   WView s = warp_view(smem_raw + L.regions + L.region_bytes * wid, n, NJ, OH, a.warp_zs);
-  s.zgl = a.zslab + (size_t)(blockIdx.x * WPC + wid) * (size_t)(WQ_QZ - a.warp_zs) * n;
+  s.zgl = a.zslab + (size_t)(blockIdx.x * WPC + wid) * warp_slab_doubles(n, a.warp_zs);
+  s.Mgl = s.zgl + (size_t)(WQ_QZ - a.warp_zs) * n;
+  s.qcap = a.warp_qcap < WQ_QBIG - 1 ? (a.warp_qcap > 1 ? a.warp_qcap : 1) : WQ_QBIG - 1;
   double *sc = s.zc, *pm = s.zc + 2 * NJ * 32;  // gradient-phase scratch aliases the direction cache
   const double dt = tab.dt, dt2 = dt * dt;
   const WDims P = {n, H, OH, O, m, 3 * n, a.has_lim, a.has_bounds, dt, a.G, a.gdiag, a.max_input, a.lim};
@@ -364,11 +366,12 @@ bool warp_supported(const SolveArgs &a, int cfg) {
   if (cfg < 0 || cfg >= WARP_NCFG) return false;
   if (a.nj != 2 && a.nj != 5) return false;
   if (a.H > 64 || a.n > 32 * W_NC) return false;  // two waypoints per lane in the prefix sums; W_NC controls per lane
-  if (a.warp_zs < 1 || a.warp_zs > WQ_QZ) return false;
+  if (a.warp_zs < 1 || a.warp_zs > 8) return false;
   return warp_smem_bytes(a, cfg) <= 227 * 1024;
 }
 
 int warp_warps_per_cta(int cfg) { return kWarpNT[cfg] / 32; }
+size_t warp_slab_bytes_per_warp(const SolveArgs &a) { return sizeof(double) * warp_slab_doubles(a.n, a.warp_zs); }
 
 typedef void (*WarpKernel)(SolveArgs);
 template <int NJ>

@@ -15,8 +15,9 @@
 
 namespace cfs {
 
-#define WQ_QS 16       // capacity of the working-set inverse (column-major, leading dimension WQ_QS)
-#define WQ_QZ 16       // direction slots (members + candidate): working sets of up to 15 rows
+#define WQ_QS 16       // working sets of up to WQ_QS rows keep their inverse in shared memory (column-major, leading dimension WQ_QS)
+#define WQ_QBIG 32     // ... beyond that, up to WQ_QBIG rows, in this warp's global slab (leading dimension WQ_QBIG, L2 resident)
+#define WQ_QZ (WQ_QBIG + 1)  // direction slots (members + candidate): the first `zs` in shared memory, the rest in the slab
 #define WQ_DEP_TOL 1e-8
 #define FULLMASK 0xffffffffu
 
@@ -38,13 +39,15 @@ struct WView {  // this warp's shared-memory region
   double *onrm;   // OH
   double *zc;     // zs*n    directions (also the gradient phase's scratch)
   double *M;      // WQ_QS*WQ_QS
-  double *lam, *r, *g;  // WQ_QS+1
+  double *lam, *r, *g;  // WQ_QBIG+2
   double *x0s;    // 2*NJ (padded to 16)
-  int *act;       // WQ_QS+1
+  int *act;       // WQ_QBIG+2
   int *zslot;     // WQ_QZ+2
   unsigned char *inact;  // m
-  double *zgl;    // global slab of this warp: (WQ_QZ - zs) * n
+  double *zgl;    // global slab of this warp: (WQ_QZ - zs) * n directions, then WQ_QBIG*WQ_QBIG for the spilled inverse
+  double *Mgl;
   int zs;         // direction slots in shared memory
+  int qcap;       // working-set capacity in use (<= WQ_QBIG): beyond it the problem is handed to the heavy tier
 };
 
 __host__ __device__ inline size_t warp_scratch_doubles(int n, int nj, int zs) {
@@ -53,7 +56,7 @@ __host__ __device__ inline size_t warp_scratch_doubles(int n, int nj, int zs) {
 }
 
 __host__ __device__ inline size_t warp_region_bytes(int n, int nj, int OH, int zs) {
-  size_t d = 3 * (size_t)n + (size_t)OH * (nj + 2) + warp_scratch_doubles(n, nj, zs) + WQ_QS * WQ_QS + 3 * (WQ_QS + 2) + 16;
+  size_t d = 3 * (size_t)n + (size_t)OH * (nj + 2) + warp_scratch_doubles(n, nj, zs) + WQ_QS * WQ_QS + 3 * (WQ_QBIG + 2) + 16;
   size_t b = d * sizeof(double) + sizeof(int) * (2 * WQ_QZ + 8) + (size_t)(OH + 4 * n);
   return (b + 15) / 16 * 16;
 }
@@ -69,18 +72,22 @@ __device__ __forceinline__ WView warp_view(unsigned char *base, int n, int nj, i
   s.onrm = d; d += OH;
   s.zc = d; d += warp_scratch_doubles(n, nj, zs);
   s.M = d; d += WQ_QS * WQ_QS;
-  s.lam = d; d += WQ_QS + 2;
-  s.r = d; d += WQ_QS + 2;
-  s.g = d; d += WQ_QS + 2;
+  s.lam = d; d += WQ_QBIG + 2;
+  s.r = d; d += WQ_QBIG + 2;
+  s.g = d; d += WQ_QBIG + 2;
   s.x0s = d; d += 16;
   int *ip = reinterpret_cast<int *>(d);
   s.act = ip; ip += WQ_QZ + 2;
   s.zslot = ip; ip += WQ_QZ + 6;
   s.inact = reinterpret_cast<unsigned char *>(ip);
   s.zgl = nullptr;
+  s.Mgl = nullptr;
   s.zs = zs;
+  s.qcap = WQ_QS - 1;
   return s;
 }
+
+__host__ __device__ inline size_t warp_slab_doubles(int n, int zs) { return (size_t)(WQ_QZ - zs) * n + (size_t)WQ_QBIG * WQ_QBIG; }
 
 __device__ __forceinline__ double *wz(const WView &s, int slot, int n) {
   return slot < s.zs ? s.zc + (size_t)slot * n : s.zgl + (size_t)(slot - s.zs) * n;
@@ -373,10 +380,13 @@ __device__ __forceinline__ int wqp_solve(const WView &s, const WDims &P, double 
   const int lane = threadIdx.x & 31, n = P.n, OH = P.OH;
   int q = 0, status = -1, steps = 0;
   bool polished = false;
-  if (lane <= WQ_QZ) s.zslot[lane] = lane;
+#pragma unroll 1
+  for (int e = lane; e <= WQ_QZ; e += 32) s.zslot[e] = e;
   __syncwarp();
   double fval = cost0;
   const int max_steps = 20 * (P.m + n) + 100;
+  double *Mp = s.M;  // working-set inverse: shared memory up to WQ_QS rows, then this warp's global slab
+  int ldm = WQ_QS;
   while (status < 0) {
     w_refresh(s, P, q);
     double sp;
@@ -394,18 +404,19 @@ __device__ __forceinline__ int wqp_solve(const WView &s, const WDims &P, double 
         if (lane == 0) s.g[w] = val;
       }
       __syncwarp();
-      if (lane < q) {
+#pragma unroll 1
+      for (int w = lane; w < q; w += 32) {
         double acc = 0.0;
 #pragma unroll 4
-        for (int c = 0; c < q; ++c) acc += s.M[lane + WQ_QS * c] * s.g[c];
-        s.lam[lane] += acc;
+        for (int c = 0; c < q; ++c) acc += Mp[w + (size_t)ldm * c] * s.g[c];
+        s.lam[w] += acc;
       }
       __syncwarp();
       polished = true;
       continue;
     }
     polished = false;
-    if (q > WQ_QZ - 1) {  // no slot left for the candidate's direction
+    if (q > s.qcap) {  // no slot left for the candidate's direction: the heavy tier redoes this iteration
       status = 4;
       break;
     }
@@ -448,7 +459,7 @@ __device__ __forceinline__ int wqp_solve(const WView &s, const WDims &P, double 
     }
     __syncwarp();
     double lam_p = 0.0;
-    // (2) bring row p into the working set
+    // (2) bring row p into the working set (rows of the inverse are strided over the lanes)
     for (;;) {
       if (++steps > max_steps) {
         status = 3;
@@ -458,15 +469,21 @@ __device__ __forceinline__ int wqp_solve(const WView &s, const WDims &P, double 
         status = 4;
         break;
       }
-      double rw = 0.0, part = 0.0, t1 = INFINITY, aux = 0.0;
+      double part = 0.0, t1 = INFINITY, aux = 0.0;
       int l = -1;
-      if (lane < q) {
+#pragma unroll 1
+      for (int w = lane; w < q; w += 32) {
+        double rw = 0.0;
 #pragma unroll 4
-        for (int c = 0; c < q; ++c) rw += s.M[lane + WQ_QS * c] * s.g[c];
-        part = s.g[lane] * rw;
+        for (int c = 0; c < q; ++c) rw += Mp[w + (size_t)ldm * c] * s.g[c];
+        s.r[w] = rw;
+        part += s.g[w] * rw;
         if (rw > 0.0) {
-          t1 = s.lam[lane] / rw;
-          l = lane;
+          const double tt = s.lam[w] / rw;
+          if (l < 0 || tt < t1) {
+            t1 = tt;
+            l = w;
+          }
         }
       }
       const double delta = sigma - warp_sum(part);
@@ -496,28 +513,40 @@ __device__ __forceinline__ int wqp_solve(const WView &s, const WDims &P, double 
         status = 2;
         break;
       }
-      if (lane < q) s.lam[lane] -= t * rw;
+#pragma unroll 1
+      for (int w = lane; w < q; w += 32) s.lam[w] -= t * s.r[w];
       lam_p += t;
       __syncwarp();
       if (full) {
-        if (q + 1 > WQ_QS) {
+        if (q + 1 > WQ_QBIG) {
           status = 4;
           break;
         }
-        // bordered inverse [[M + r r'/d, -r/d], [-r'/d, 1/d]]: lane r owns row r
+        if (q + 1 > WQ_QS && Mp == s.M) {  // the inverse outgrows shared memory: move it to the slab
+#pragma unroll 1
+          for (int e = lane; e < q * q; e += 32) {
+            const int c = e / q, rr = e - c * q;
+            s.Mgl[rr + (size_t)WQ_QBIG * c] = s.M[rr + WQ_QS * c];
+          }
+          Mp = s.Mgl;
+          ldm = WQ_QBIG;
+          __syncwarp();
+        }
+        // bordered inverse [[M + r r'/d, -r/d], [-r'/d, 1/d]]
         const double id = 1.0 / delta;
 #pragma unroll 1
         for (int c = 0; c <= q; ++c) {
-          const double rc = __shfl_sync(FULLMASK, rw, c < q ? c : 0);  // every lane takes part in the shuffle
-          if (lane <= q) {
+          const double rc = c < q ? s.r[c] : 0.0;
+#pragma unroll 1
+          for (int rr = lane; rr <= q; rr += 32) {
             double val;
-            if (lane < q && c < q)
-              val = s.M[lane + WQ_QS * c] + rw * (rc * id);
-            else if (lane == q && c == q)
+            if (rr < q && c < q)
+              val = Mp[rr + (size_t)ldm * c] + s.r[rr] * (rc * id);
+            else if (rr == q && c == q)
               val = id;
             else
-              val = -(lane < q ? rw : rc) * id;
-            s.M[lane + WQ_QS * c] = val;
+              val = -(rr < q ? s.r[rr] : rc) * id;
+            Mp[rr + (size_t)ldm * c] = val;
           }
         }
         if (lane == 0) {
@@ -530,21 +559,26 @@ __device__ __forceinline__ int wqp_solve(const WView &s, const WDims &P, double 
         __syncwarp();
         break;
       }
-      // drop member l: M <- M - M(:,l) M(l,:)/M(l,l), then move the last member into slot l
+      // drop member l: M <- M - M(:,l) M(l,:)/M(l,l), then move the last member into slot l (s.r holds column l meanwhile)
       {
         const int last = q - 1;
-        const double col = lane < q ? s.M[lane + WQ_QS * l] : 0.0;
-        const double ip = 1.0 / __shfl_sync(FULLMASK, col, l);
+#pragma unroll 1
+        for (int w = lane; w < q; w += 32) s.r[w] = Mp[w + (size_t)ldm * l];
+        __syncwarp();
+        const double ip = 1.0 / s.r[l];
 #pragma unroll 1
         for (int c = 0; c < q; ++c) {
-          const double gc = __shfl_sync(FULLMASK, col, c) * ip;
-          if (lane < q) s.M[lane + WQ_QS * c] -= col * gc;
+          const double gc = s.r[c] * ip;
+#pragma unroll 1
+          for (int w = lane; w < q; w += 32) Mp[w + (size_t)ldm * c] -= s.r[w] * gc;
         }
         __syncwarp();
         if (l != last) {
-          if (lane < q) s.M[lane + WQ_QS * l] = s.M[lane + WQ_QS * last];
+#pragma unroll 1
+          for (int w = lane; w < q; w += 32) Mp[w + (size_t)ldm * l] = Mp[w + (size_t)ldm * last];
           __syncwarp();
-          if (lane < q) s.M[l + WQ_QS * lane] = s.M[last + WQ_QS * lane];
+#pragma unroll 1
+          for (int w = lane; w < q; w += 32) Mp[l + (size_t)ldm * w] = Mp[last + (size_t)ldm * w];
         }
         if (lane == 0) {
           s.inact[s.act[l]] = 0;

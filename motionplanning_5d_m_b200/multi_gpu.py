@@ -8,7 +8,8 @@ independent.  The only exchange is at the end:
   best_of         -- the GPU analogue of `[~,id] = min(routeL)` over parfor workers (Lib/functions/s_Parallel_rrt.m:27):
                      ranks hold alternative solutions of the SAME problems (different noise streams / seeds / routes);
                      all-gather of (cost, status) (16 B per problem), argmin over ranks, then one all-reduce in which only
-                     the winning rank contributes its trajectory (x + 0 is exact, so the winner's bits arrive unchanged).
+                     the winning rank contributes its trajectory (x + 0 is exact; the one value that does not survive is the
+                     sign of a zero: -0.0 + 0.0 = +0.0).  A candidate whose cost is NaN or infinite is never admissible.
 """
 import math
 
@@ -58,7 +59,7 @@ def best_of(cost, status, payload=None, group=None):
     low byte is 0 (converged) or 1 (MAX_ITER).  Returns (winner_rank (P,) long [-1: no admissible candidate], best_cost (P,),
     winner_payload dict or None); ties go to the lowest rank, like MATLAB's min()."""
     rank, G = world()
-    ok = (status.to(torch.int64) & 0xFF) < 2
+    ok = ((status.to(torch.int64) & 0xFF) < 2) & torch.isfinite(cost)
     c = torch.where(ok, cost, torch.full_like(cost, float("inf")))
     if G == 1:
         win = torch.where(ok, torch.zeros_like(status, dtype=torch.int64), torch.full_like(status, -1, dtype=torch.int64))

@@ -140,8 +140,9 @@ def test_main_2l_solve_parity(ctx, oracle):
 
 
 BULK_MODES = {"warp": dict(fused=1, warp=1, warp_cfg=0), "warp_3x3": dict(fused=1, warp=1, warp_cfg=1),
-              "warp_zs1": dict(fused=1, warp=1, warp_cfg=0, warp_zs=1), "cta": dict(fused=1, warp=0), "lockstep": dict(fused=0)}
-BULK_DEFAULT = dict(fused=1, warp=1, warp_cfg=0, warp_zs=0)
+              "warp_zs1": dict(fused=1, warp=1, warp_cfg=0, warp_zs=1), "warp_q31": dict(fused=1, warp=1, warp_qcap=31),
+              "warp_noscreen": dict(fused=1, warp=1, screen=0), "cta": dict(fused=1, warp=0), "lockstep": dict(fused=0)}
+BULK_DEFAULT = dict(fused=1, warp=1, warp_cfg=3, warp_zs=0, warp_qcap=15, screen=1)
 
 
 @pytest.mark.parametrize("mode", list(BULK_MODES))
@@ -165,7 +166,7 @@ def test_batch_m16ib_solve_parity(ctx, oracle, mode):
             ctx.set_option(k, v)
     assert ((ref["status"] & 0xFF) == 2).any() and ((ref["status"] & 0xFF) == 0).any()
     _compare_solve(out, ref)
-    assert ctx.stats()["launches"] == (44 if mode == "lockstep" else (6 if mode == "cta" else 8))
+    assert ctx.stats()["launches"] == (44 if mode == "lockstep" else (6 if mode in ("cta", "warp_noscreen") else 8))
 
 
 def test_psgcfs_main_fanuc_parity(ctx, oracle):

@@ -99,3 +99,12 @@ def test_final_cost_picks_last_iteration():
     it = torch.tensor([2, 0, 3], dtype=torch.int32)
     fc = multi_gpu.final_cost(ch, it)
     assert fc[0] == 2.0 and torch.isinf(fc[1]) and fc[2] == 1.0
+
+
+def test_best_of_ignores_non_finite_costs():
+    """a NaN / Inf cost with an admissible status is never a winner (single process: the same masking runs before the gather)"""
+    from motionplanning_5d_m_b200 import multi_gpu
+    cost = torch.tensor([float("nan"), 1.0, float("inf"), 2.0], dtype=torch.float64)
+    status = torch.tensor([0, 0, 1, 2], dtype=torch.int32)
+    win, best, _ = multi_gpu.best_of(cost, status)
+    assert win.tolist() == [-1, 0, -1, -1] and best[1] == 1.0 and torch.isinf(best[[0, 2, 3]]).all()
