@@ -376,6 +376,8 @@ def bench_solver(args, e):
         ctx.set_stream(st.cuda_stream)
         ctx.set_robot(robot, nj)
         ctx.set_obstacles(obs)
+        for kv in filter(None, os.environ.get("BENCH_OPTS", "").split(",")):  # development: library scheduling options
+            ctx.set_option(kv.split("=")[0], int(kv.split("=")[1]))
         ctxs.append(ctx)
         streams.append(st)
     feas = lambda cand: ctxs[0].nodes_feasible(cand)[0]

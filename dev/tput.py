@@ -53,3 +53,4 @@ for c in range(min(NC, 8)):
     torch.cuda.synchronize(); issue(c); ctxs[c].wait(); st = ctxs[c].stats()
     ps = ctxs[c].problem_steps(B)
     print("  single batch %d: total %.3f bulk %.3f heavy %.3f  qp_steps %d max_steps/problem %d max_active %d" % (c, st["ms_total"], st["ms_bulk"], st["ms_heavy"], st["qp_steps"], ps.max(), st["max_active"]))
+print("  grid launches:", ctxs[0].stats()["launches"])

@@ -94,6 +94,8 @@ struct cfs_ctx {
                           // 3 = 1 warp x 10 CTAs/SM (default: the finest granularity pipelines best across contexts), 4 = 2 x 5
   int warp_zs = 0;        // cfs_set_option("warp_zs"): direction slots in shared memory (0 = as many as fit, at most 4)
   int screen = 1;         // cfs_set_option("screen"): warp tier in two launches (iteration 1 | the rest), heavy tier starts after the first
+  long long warp_key = -1;  // cache of the warp tier's launch configuration
+  int warp_zs_pick = 0, warp_grid_pick = 0;
   int warp_qcap = 15;     // cfs_set_option("warp_qcap"): working-set rows the warp tier keeps (<= 31; inverse + directions spill to L2 beyond 16:
                           // measured, a single warp on a 16..31-row working set lengthens the tail more than the heavy tier costs)
   int heavy_cfg = 0;      // cfs_set_option("heavy_cfg"): 0 = 144 x 144 inverse on chip (whole SM), 1 = slim (64 x 64 on chip, 168 registers)
@@ -538,15 +540,36 @@ static int solve_device(cfs_ctx *ctx, int B, int solver, int grad, const double 
   // bulk tier of the fused solver: one warp per problem (k_warp.cu) when its shared-memory regions fit
   bool warp = false;
   a.warp_qcap = ctx->warp_qcap;
+  int warp_grid = 0;
   if (fused && ctx->use_warp) {
-    for (int zs = ctx->warp_zs > 0 ? ctx->warp_zs : 4; zs >= 1 && !warp; --zs) {
-      a.warp_zs = zs;
-      warp = warp_supported(a, ctx->warp_cfg);
-      if (ctx->warp_zs > 0) break;
+    // direction slots in shared memory: the count that keeps the most problems resident per SM (ties: more slots); cached per
+    // (n, obstacles, CTA shape)
+    const long long key = ((long long)n << 24) ^ ((long long)O << 16) ^ ((long long)ctx->warp_cfg << 8) ^ ctx->warp_zs;
+    if (key != ctx->warp_key) {
+      ctx->warp_key = key;
+      ctx->warp_zs_pick = 0;
+      ctx->warp_grid_pick = 0;
+      for (int zs = ctx->warp_zs > 0 ? ctx->warp_zs : 4; zs >= 1; --zs) {
+        a.warp_zs = zs;
+        if (warp_supported(a, ctx->warp_cfg)) {
+          const int g = warp_max_grid(a, ctx->device, ctx->warp_cfg);
+          if (g > ctx->warp_grid_pick) {
+            ctx->warp_grid_pick = g;
+            ctx->warp_zs_pick = zs;
+          }
+        }
+        if (ctx->warp_zs > 0) break;
+      }
+      if (ctx->warp_zs_pick > 0) {  // leave the kernel's dynamic shared-memory limit at the chosen configuration
+        a.warp_zs = ctx->warp_zs_pick;
+        warp_max_grid(a, ctx->device, ctx->warp_cfg);
+      }
     }
+    warp = ctx->warp_zs_pick > 0 && ctx->warp_grid_pick > 0;
+    a.warp_zs = ctx->warp_zs_pick;
+    warp_grid = ctx->warp_grid_pick;
   }
-  int grid = fused ? (warp ? warp_max_grid(a, ctx->device, ctx->warp_cfg) : fused_max_grid(a, ctx->device, 0))
-                   : qp_max_grid(a, ctx->device);
+  int grid = fused ? (warp ? warp_grid : fused_max_grid(a, ctx->device, 0)) : qp_max_grid(a, ctx->device);
   const int heavy_tier = ctx->heavy_cfg ? 2 : 1;
   int grid_heavy = fused ? fused_max_grid(a, ctx->device, heavy_tier) : 0;
   if (grid <= 0 || (fused && grid_heavy <= 0))
@@ -569,6 +592,7 @@ static int solve_device(cfs_ctx *ctx, int B, int solver, int grad, const double 
   if (fused && ctx->heavy_grid > 0 && grid_heavy > ctx->heavy_grid) grid_heavy = ctx->heavy_grid;
   const int grid_heavy2 = grid_heavy > 32 ? 32 : grid_heavy;  // second heavy launch of the screened pipeline: late escalations
   if (fused && ctx->bulk_grid > 0 && grid > ctx->bulk_grid) grid = ctx->bulk_grid;
+  if (getenv("CFS_DEBUG")) fprintf(stderr, "[cfs] solve: B=%d fused=%d warp=%d cfg=%d zs=%d grid=%d grid_heavy=%d\n", B, (int)fused, (int)warp, ctx->warp_cfg, a.warp_zs, grid, grid_heavy);
   if ((rc = ensure(ctx, ctx->slab, sizeof(double) * (size_t)n * n * (grid > grid_heavy ? grid : grid_heavy)))) return rc;
   a.slab = ptr<double>(ctx->slab);
 
@@ -704,7 +728,7 @@ static int solve_device(cfs_ctx *ctx, int B, int solver, int grad, const double 
 static int collect_stats(cfs_ctx *ctx, int B, int max_outer, const int *d_iters, const int *d_status) {
   cudaStream_t st = ctx->stream;
   long long steps[2] = {0, 0};
-  int cnt[8] = {0};
+  int cnt[16] = {0};
   std::vector<int> it(B), stt(B);
   CU(cudaMemcpyAsync(stt.data(), d_status, sizeof(int) * B, cudaMemcpyDeviceToHost, st));
   CU(cudaMemcpyAsync(steps, ctx->qpsteps.p, sizeof(steps), cudaMemcpyDeviceToHost, st));
@@ -716,6 +740,9 @@ static int collect_stats(cfs_ctx *ctx, int B, int max_outer, const int *d_iters,
   ctx->stats.ms_total = ms;
   ctx->stats.qp_steps = steps[0];
   ctx->stats.max_active = cnt[3];
+  if (getenv("CFS_DEBUG"))
+    fprintf(stderr, "[cfs] batch done: escalated after the screening pass %d, late escalations %d, continued past iteration 1: %d\n", cnt[5],
+            cnt[8], cnt[6]);
   long long pit = 0, gev = 0;
   for (int b = 0; b < B; ++b) {
     pit += it[b];

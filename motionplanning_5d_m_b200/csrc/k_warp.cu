@@ -380,8 +380,8 @@ static WarpKernel warp_kernel_nj(int cfg, bool two) {
     case 0: return two ? k_cfs_warp<NJ, 384, 168, 2> : k_cfs_warp<NJ, 384, 168, 1>;
     case 1: return two ? k_cfs_warp<NJ, 96, 224, 2> : k_cfs_warp<NJ, 96, 224, 1>;
     case 2: return two ? k_cfs_warp<NJ, 128, 168, 2> : k_cfs_warp<NJ, 128, 168, 1>;
-    case 3: return two ? k_cfs_warp<NJ, 32, 200, 2> : k_cfs_warp<NJ, 32, 200, 1>;
-    case 4: return two ? k_cfs_warp<NJ, 64, 200, 2> : k_cfs_warp<NJ, 64, 200, 1>;
+    case 3: return two ? k_cfs_warp<NJ, 32, 168, 2> : k_cfs_warp<NJ, 32, 168, 1>;
+    case 4: return two ? k_cfs_warp<NJ, 64, 168, 2> : k_cfs_warp<NJ, 64, 168, 1>;
   }
   return nullptr;
 }
@@ -397,7 +397,10 @@ int warp_max_grid(const SolveArgs &a, int device, int cfg) {
   if (!k) return 0;
   int sms = 0, per = 0;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-  if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 0;
+  // the opt-in maximum, not this configuration's size: the attribute is per function and shared by every context of the process
+  if (smem > 227 * 1024 || cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return 0;
+  // all of the SM's 228 KB as shared memory: the resident CTAs are limited by their shared-memory regions, not by L1
+  cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k, kWarpNT[cfg], smem);
   return sms * per;
 }
