@@ -93,6 +93,8 @@ struct cfs_ctx {
   int warp_cfg = 3;       // cfs_set_option("warp_cfg"): CTA shape of the warp tier (k_warp.cu): 0 = 12 warps x 1 CTA/SM, 1 = 3 x 3, 2 = 4 x 3,
                           // 3 = 1 warp x 10 CTAs/SM (default: the finest granularity pipelines best across contexts), 4 = 2 x 5
   int warp_zs = 0;        // cfs_set_option("warp_zs"): direction slots in shared memory (0 = as many as fit, at most 4)
+  int use_warp_lockstep = 0;  // cfs_set_option("warp_lockstep"): launch-per-iteration path solves its QPs with k_qp_warp (measured: no gain --
+                              // a lock-step iteration still waits for its slowest QP, and that one is slower on a single warp)
   int screen = 1;         // cfs_set_option("screen"): warp tier in two launches (iteration 1 | the rest), heavy tier starts after the first
   long long warp_key = -1;  // cache of the warp tier's launch configuration
   int warp_zs_pick = 0, warp_grid_pick = 0;
@@ -679,6 +681,26 @@ static int solve_device(cfs_ctx *ctx, int B, int solver, int grad, const double 
     return 0;
   }
   ctx->fused_last = false;
+  // launch-per-iteration path: QP by one warp per problem where its shared-memory regions fit (k_qp_warp)
+  bool qpw = false;
+  int grid_w = 0;
+  if (ctx->use_warp && ctx->use_warp_lockstep) {
+    for (int zs = 3; zs >= 1 && !qpw; --zs) {
+      a.warp_zs = zs;
+      qpw = qp_warp_supported(a);
+    }
+    if (qpw) {
+      grid_w = qp_warp_max_grid(a, ctx->device);
+      if (grid_w > (B + 3) / 4) grid_w = (B + 3) / 4;
+      qpw = grid_w > 0;
+    }
+    if (qpw) {
+      if ((rc = ensure(ctx, ctx->zslab, warp_slab_bytes_per_warp(a) * (size_t)grid_w * 4))) return rc;
+      a.zslab = ptr<double>(ctx->zslab);
+      a.esc_list = ptr<int>(ctx->cont);
+      a.esc_count = cnt + 5;
+    }
+  }
   CU(launch_solve_init(a, st)); ++launches;
   if (psg) {
     CU(cudaMemsetAsync(a.w, 0, sizeof(double) * (size_t)n * B, st));  // QQ*u at u = 0
@@ -707,7 +729,18 @@ static int solve_device(cfs_ctx *ctx, int B, int solver, int grad, const double 
     }
     if (detail) CU(cudaEventRecord(ctx->ev[3 * (it - 1) + 1], st));
     if (psg) { CU(launch_psg_point(a, st)); ++launches; }
-    CU(launch_qp(a, grid, st)); ++launches;
+    if (qpw) {
+      // warp-per-problem QP (k_qp_warp); the few problems whose working set outgrows it are redone by the CTA kernel
+      CU(cudaMemsetAsync(cnt + 4, 0, 2 * sizeof(int), st));
+      CU(launch_qp_warp(a, grid_w, st)); ++launches;
+      SolveArgs ae = a;
+      ae.list_cur = a.esc_list;
+      ae.count_cur = a.esc_count;
+      ae.work_counter = cnt + 4;
+      CU(launch_qp(ae, grid < 32 ? grid : 32, st)); ++launches;
+    } else {
+      CU(launch_qp(a, grid, st)); ++launches;
+    }
     if (psg) {  // w = QQ*u for EVAL.get_cost now and for the next PSG step
       CU(launch_dgemm(n, B, n, 1.0, ctx->dQQraw, n, false, a.u, n, a.w, n, st)); ++launches;
       CU(launch_psg_cost(a, st)); ++launches;
@@ -1468,6 +1501,7 @@ extern "C" int cfs_set_option(cfs_ctx *ctx, const char *name, int value) {
   if (strcmp(name, "lpt") == 0) { ctx->lpt = value; return 0; }
   if (strcmp(name, "warp") == 0) { ctx->use_warp = value; return 0; }
   if (strcmp(name, "screen") == 0) { ctx->screen = value; return 0; }
+  if (strcmp(name, "warp_lockstep") == 0) { ctx->use_warp_lockstep = value; return 0; }
   if (strcmp(name, "heavy_cfg") == 0) { ctx->heavy_cfg = value; return 0; }
   if (strcmp(name, "heavy_skip") == 0) { ctx->heavy_skip = value; return 0; }
   if (strcmp(name, "warp_cfg") == 0) { ctx->warp_cfg = value; return 0; }

@@ -162,6 +162,10 @@ size_t warp_smem_bytes(const SolveArgs &a, int cfg);
 int warp_max_grid(const SolveArgs &a, int device, int cfg);
 int warp_warps_per_cta(int cfg);
 size_t warp_slab_bytes_per_warp(const SolveArgs &a);
+// lock-step form of the warp QP (PSGCFS / DERIVEST paths): one outer iteration of list_cur; escalations go to esc_list
+bool qp_warp_supported(const SolveArgs &a);
+int qp_warp_max_grid(const SolveArgs &a, int device);
+cudaError_t launch_qp_warp(const SolveArgs &a, int grid, cudaStream_t s);
 cudaError_t launch_warp(const SolveArgs &a, int grid, int cfg, cudaStream_t s);
 
 // ---- dense get_con rows (one problem) -------------------------------------------------------------------------

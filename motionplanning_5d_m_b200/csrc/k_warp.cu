@@ -352,6 +352,150 @@ __global__ void __launch_bounds__(NT) __maxnreg__(MAXREG) k_cfs_warp(SolveArgs a
   }
 }
 
+// ---- lock-step form: one outer iteration of the problems in list_cur, one warp per problem ------------------------------------
+// The launch-per-iteration path (PSGCFS_FANUC.optimizer: the PSG point needs the batched QQ*u GEMM between two projections;
+// DERIVEST gradients come from their own kernel) keeps its structure -- gradient kernel | QP kernel per outer iteration -- but
+// the QP kernel (k_qp.cu: one CTA per problem) is replaced by this one: same prologue / epilogue, wqp_solve in the middle.
+// Problems whose working set outgrows the warp tier are appended to esc_list and taken by k_qp in the same iteration.
+template <int NJ, int NT>
+__global__ void __launch_bounds__(NT, 3) k_qp_warp(SolveArgs a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  constexpr int WPC = NT / 32;
+  const int n = a.n, H = a.H, O = a.nobs, OH = O * H, m = OH + 4 * n, N = 2 * n;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const WarpSmem L = warp_smem(n, NJ, OH, a.warp_zs, WPC, 0);
+  WView s = warp_view(smem_raw + L.regions + L.region_bytes * wid, n, NJ, OH, a.warp_zs);
+  s.zgl = a.zslab + (size_t)(blockIdx.x * WPC + wid) * warp_slab_doubles(n, a.warp_zs);
+  s.Mgl = s.zgl + (size_t)(WQ_QZ - a.warp_zs) * n;
+  s.qcap = a.warp_qcap < WQ_QBIG - 1 ? (a.warp_qcap > 1 ? a.warp_qcap : 1) : WQ_QBIG - 1;
+  const double dt = a.tab->dt, dt2 = dt * dt;
+  const bool psg = a.solver == 1;
+  const WDims P = {n, H, OH, O, m, 3 * n, a.has_lim, a.has_bounds, dt, a.G, a.gdiag, a.max_input, a.lim};
+  const int count = *a.count_cur;
+  const int it = a.outer_iter;
+  long long steps_total = 0;
+  int qmax_seen = 0;
+  for (;;) {
+    int slot = 0;
+    if (lane == 0) slot = atomicAdd(a.work_counter, 1);
+    slot = __shfl_sync(FULLMASK, slot, 0);
+    if (slot >= count) break;
+    const int b = a.list_cur[slot];
+    const double *x0 = a.x0 + (size_t)b * 2 * NJ;
+    double *ub = a.u + (size_t)b * n;
+    double *xb = a.x + (size_t)b * N;
+    __syncwarp();
+    // ---- prologue: rows from the gradient kernel's output (CFS_FANUC.m:117-121), u0 ----
+    if (lane < 2 * NJ) s.x0s[lane] = x0[lane];
+#pragma unroll 2
+    for (int c = lane; c < n; c += 32) s.u0s[c] = a.u0[(size_t)b * n + c];
+#pragma unroll 1
+    for (int e = lane * 4; e < m; e += 128) *reinterpret_cast<unsigned int *>(s.inact + e) = 0u;
+    __syncwarp();
+#pragma unroll 1
+    for (int cid = lane; cid < OH; cid += 32) {
+      const int j = cid / H, i = cid - j * H;
+      const double *gr = a.grad + ((size_t)b * OH + cid) * NJ;
+      const double margin = a.margin_is_D ? a.tab->obs[j].D : a.tab->obs[j].eps;
+      double gu = 0.0, sg = 0.0;
+#pragma unroll
+      for (int k = 0; k < NJ; ++k) {
+        const double gk = gr[k];
+        s.ocoef[(size_t)cid * NJ + k] = -gk;
+        // B_theta u = theta_i - (theta_0 + i dt w_0) once x_ is the roll-out of u (not in the first iteration: CFS_FANUC.m:55-56)
+        if (it > 1) gu += gk * (xb[(size_t)i * 2 * NJ + k] - (s.x0s[k] + ((i + 1) * dt) * s.x0s[NJ + k]));
+        const double gd = __ldg(a.gdiag + i * NJ + k);
+        sg += (gk * gk) * (gd * gd);
+      }
+      s.orhs[cid] = (a.dist[(size_t)b * OH + cid] - margin) - gu;
+      s.onrm[cid] = sg;
+    }
+    __syncwarp();
+    // ---- the QP (CFS_FANUC.m:85) / the projection (PSGCFS_FANUC.m:120) ----
+    int q = 0, steps = 0, status = 0;
+    const bool skip_solve = psg && a.skip[b];  // stop_inner() already true: u stays, no projection (PSGCFS_FANUC.m:88)
+    if (skip_solve) {
+#pragma unroll 2
+      for (int c = lane; c < n; c += 32) s.uq[c] = ub[c];
+      __syncwarp();
+    } else {
+      const int masked = w_mask_antiparallel<NJ>(s, P);
+      status = wqp_solve<NJ>(s, P, a.cost0[b], (a.has_bounds && a.fupper) ? a.fupper[b] : INFINITY, 0x7fffffff, masked, q, steps,
+                             qmax_seen);
+    }
+    steps_total += steps;
+    if (status == 4) {  // the working set outgrew the warp tier: k_qp redoes this problem's iteration
+      if (lane == 0) a.esc_list[atomicAdd(a.esc_count, 1)] = b;
+      continue;
+    }
+    if (lane == 0 && a.prob_steps) a.prob_steps[b] += steps;
+    if (status != 0) {  // 2 infeasible / 3 numerical: u, x keep the previous iterate
+      if (lane == 0) a.status[b] = status;
+      continue;
+    }
+    // ---- epilogue: e_u, cost by duality, roll-out, stop rule (EVAL.m:51-73, CFS_FANUC.m:88-94) ----
+    double cost = 0.0;
+    if (!psg) {
+      double pc = 0.0;
+#pragma unroll 1
+      for (int w = 0; w < q; ++w) {
+        const int cw = s.act[w];
+        pc += s.lam[w] * (W_ROW_DOT(cw, s.u0s) - w_row_rhs<NJ>(cw, s, P));
+      }
+      cost = a.cost0[b] + 0.5 * pc;
+    }
+    double pe = 0.0;
+#pragma unroll 2
+    for (int c = lane; c < n; c += 32) {
+      const double un = s.uq[c];
+      const double dlt = ub[c] - un;
+      pe += dlt * dlt;
+      ub[c] = un;
+    }
+    const double e_u = sqrt(warp_sum(pe));
+    double px = 0.0;
+    {
+      const int i0 = 2 * lane, i1 = i0 + 1;
+      const bool v0 = i0 < H, v1 = i1 < H;
+#pragma unroll 1
+      for (int k = 0; k < NJ; ++k) {
+        const double a0 = v0 ? s.uq[i0 * NJ + k] : 0.0, a1 = v1 ? s.uq[i1 * NJ + k] : 0.0;
+        double s0, s1, t0, t1;
+        w_prefix2(a0, a1, s0, s1, t0, t1);
+        const double w0 = s.x0s[NJ + k], th00 = s.x0s[k];
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) {
+          if (!(h ? v1 : v0)) continue;
+          const int i = h ? i1 : i0;
+          const double S1 = h ? s1 : s0, T = h ? t1 : t0;
+          const double thn = (th00 + ((i + 1) * dt) * w0) + dt2 * (0.5 * S1 + T), omn = w0 + dt * S1;
+          // CFS: x_old = previous x_ (CFS_FANUC.m:88); PSGCFS never updates eval.x_old, it stays ones (EVAL.m:47)
+          const double d1 = thn - (psg ? 1.0 : xb[(size_t)i * 2 * NJ + k]), d2 = omn - (psg ? 1.0 : xb[(size_t)i * 2 * NJ + NJ + k]);
+          px += d1 * d1 + d2 * d2;
+          xb[(size_t)i * 2 * NJ + k] = thn;
+          xb[(size_t)i * 2 * NJ + NJ + k] = omn;
+        }
+      }
+    }
+    const double dx = sqrt(warp_sum(px));
+    if (lane == 0) {
+      if (!psg) a.cost_hist[(size_t)b * a.max_outer + (it - 1)] = cost;
+      if (a.e_u_hist) a.e_u_hist[(size_t)b * a.max_outer + (it - 1)] = e_u;
+      a.iters[b] = it;
+      if (dx < a.eps_outer)
+        a.status[b] = 0;
+      else if (it + 1 > a.max_outer)
+        a.status[b] = 1;
+      else
+        a.list_next[atomicAdd(a.count_next, 1)] = b;
+    }
+  }
+  if (lane == 0) {
+    if (steps_total) atomicAdd(reinterpret_cast<unsigned long long *>(a.qp_steps), (unsigned long long)steps_total);
+    if (qmax_seen) atomicMax(a.max_active, qmax_seen);
+  }
+}
+
 // ---- host side ------------------------------------------------------------------------------------------------------------
 // CTA shapes (warps of one CTA share nothing but the staged tables; small CTAs let another context's launch move into an SM
 // as soon as a few warps have drained):  cfg 0: 12 warps x 1 CTA/SM, 1: 3 warps x 3, 2: 4 warps x 3, 3: 1 warp x 10, 4: 2 warps x 5
@@ -409,6 +553,32 @@ cudaError_t launch_warp(const SolveArgs &a, int grid, int cfg, cudaStream_t st) 
   WarpKernel k = warp_kernel(a.nj, cfg, a.nobs);
   if (!k) return cudaErrorInvalidValue;
   k<<<grid, kWarpNT[cfg], warp_smem_bytes(a, cfg), st>>>(a);
+  return cudaGetLastError();
+}
+
+// lock-step warp QP (PSGCFS / DERIVEST paths): 4 warps per CTA
+bool qp_warp_supported(const SolveArgs &a) {
+  if (a.nj != 2 && a.nj != 5) return false;
+  if (a.H > 64 || a.n > 32 * W_NC || a.warp_zs < 1 || a.warp_zs > 8) return false;
+  return warp_smem(a.n, a.nj, a.nobs * a.H, a.warp_zs, 4, 0).total <= 227 * 1024;
+}
+
+int qp_warp_max_grid(const SolveArgs &a, int device) {
+  const size_t smem = warp_smem(a.n, a.nj, a.nobs * a.H, a.warp_zs, 4, 0).total;
+  WarpKernel k = a.nj == 2 ? k_qp_warp<2, 128> : k_qp_warp<5, 128>;
+  int sms = 0, per = 0;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return 0;
+  cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k, 128, smem);
+  return sms * per;
+}
+
+cudaError_t launch_qp_warp(const SolveArgs &a, int grid, cudaStream_t st) {
+  const size_t smem = warp_smem(a.n, a.nj, a.nobs * a.H, a.warp_zs, 4, 0).total;
+  if (a.nj == 2) k_qp_warp<2, 128><<<grid, 128, smem, st>>>(a);
+  else if (a.nj == 5) k_qp_warp<5, 128><<<grid, 128, smem, st>>>(a);
+  else return cudaErrorInvalidValue;
   return cudaGetLastError();
 }
 
