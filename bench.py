@@ -554,8 +554,9 @@ def bench_solver(args, e):
         "roofline": {"bound": "fp64", "kernel": dom_name,
                      "achieved": ach_tf, "peak": fp64_tf, "unit": "TFLOP/s", "frac": ach_tf / fp64_tf if fp64_tf else None,
                      "traffic": DRAM_BYTES_PER_LAUNCH.get(args.config) if (B == 4096 and H == 50) else None,
-                     "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of the bulk launches, ncu --set full "
-                                       "(profiles/dram_traffic.json, profiles/README.md)",
+                     "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum summed over one step's four solver launches "
+                                       "(screen, heavy#1, bulk, heavy#2), single-pass ncu run without replay save/restore "
+                                       "(profiles/r02_dram_single_pass.csv; the --set full capture inflates writes, profiles/README.md)",
                      "peak_source": "measured here by cfs_measure_fp64_peak (DFMA micro-benchmark; MEASURED_PEAKS.json "
                                     "has no FP64 entry), implied SM clock %.0f MHz" % fp64_mhz,
                      "algorithmic_flops_per_launch": flops_per_launch, "avg_launch_ms": amort_ms,

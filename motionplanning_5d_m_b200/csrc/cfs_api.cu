@@ -95,6 +95,7 @@ struct cfs_ctx {
   int warp_zs = 0;        // cfs_set_option("warp_zs"): direction slots in shared memory (0 = as many as fit, at most 4)
   int use_warp_lockstep = 0;  // cfs_set_option("warp_lockstep"): launch-per-iteration path solves its QPs with k_qp_warp (measured: no gain --
                               // a lock-step iteration still waits for its slowest QP, and that one is slower on a single warp)
+  int one_shot = 0;       // cfs_set_option("one_shot"): warp tier without a work queue, one problem per warp
   int screen = 1;         // cfs_set_option("screen"): warp tier in two launches (iteration 1 | the rest), heavy tier starts after the first
   long long warp_key = -1;  // cache of the warp tier's launch configuration
   int warp_zs_pick = 0, warp_grid_pick = 0;
@@ -583,7 +584,8 @@ static int solve_device(cfs_ctx *ctx, int B, int solver, int grad, const double 
   }
   if (warp) {
     const int wpc = warp_warps_per_cta(ctx->warp_cfg);
-    if (grid > (B + wpc - 1) / wpc) grid = (B + wpc - 1) / wpc;
+    a.one_shot = ctx->one_shot;
+    if (grid > (B + wpc - 1) / wpc || ctx->one_shot) grid = (B + wpc - 1) / wpc;
     if (grid < 1) grid = 1;
     if ((rc = ensure(ctx, ctx->zslab, warp_slab_bytes_per_warp(a) * (size_t)grid * wpc))) return rc;
     a.zslab = ptr<double>(ctx->zslab);
@@ -1501,6 +1503,7 @@ extern "C" int cfs_set_option(cfs_ctx *ctx, const char *name, int value) {
   if (strcmp(name, "lpt") == 0) { ctx->lpt = value; return 0; }
   if (strcmp(name, "warp") == 0) { ctx->use_warp = value; return 0; }
   if (strcmp(name, "screen") == 0) { ctx->screen = value; return 0; }
+  if (strcmp(name, "one_shot") == 0) { ctx->one_shot = value; return 0; }
   if (strcmp(name, "warp_lockstep") == 0) { ctx->use_warp_lockstep = value; return 0; }
   if (strcmp(name, "heavy_cfg") == 0) { ctx->heavy_cfg = value; return 0; }
   if (strcmp(name, "heavy_skip") == 0) { ctx->heavy_skip = value; return 0; }

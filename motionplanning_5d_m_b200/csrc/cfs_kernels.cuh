@@ -138,6 +138,7 @@ struct SolveArgs {
   // phase 0: every problem start to finish.  phase 1 ("screen"): outer iteration 1 only; problems that are not finished go
   // to cont_list.  phase 2: resume the problems of cont_list from outer iteration 2 (state in x / u / iters / touch).
   int phase;
+  int one_shot;               // warp tier: grid = one warp per problem, no work queue (CTAs leave the SM after one problem)
   int *cont_list, *cont_count;
   int *touch;                 // B: CFS_FLAG_TOUCH of the problems in cont_list
 };

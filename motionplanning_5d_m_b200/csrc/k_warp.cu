@@ -157,10 +157,15 @@ __global__ void __launch_bounds__(NT) __maxnreg__(MAXREG) k_cfs_warp(SolveArgs a
 
   const bool resume = a.phase == 2;
   const int count = resume ? *a.cont_count : a.B;
-  for (;;) {
+  for (int round = 0;; ++round) {
     int slot = 0;
-    if (lane == 0) slot = atomicAdd(a.work_counter, 1);
-    slot = __shfl_sync(FULLMASK, slot, 0);
+    if (a.one_shot) {  // one problem per warp, then the CTA leaves the SM (see cfs_set_option "one_shot")
+      if (round > 0) break;
+      slot = blockIdx.x * WPC + wid;
+    } else {
+      if (lane == 0) slot = atomicAdd(a.work_counter, 1);
+      slot = __shfl_sync(FULLMASK, slot, 0);
+    }
     if (slot >= count) break;
     const int b = resume ? a.cont_list[slot] : (a.order ? a.order[slot] : slot);
     const double *x0 = a.x0 + (size_t)b * 2 * NJ;
