@@ -292,7 +292,7 @@ def make_env(args):
         raise SystemExit("bench.py: no CUDA device; this framework has no CPU fallback")
     torch.cuda.set_device(e.local_rank)
     e.dev = torch.device("cuda", e.local_rank)
-    e.numa = bind_to_gpu_numa(e.local_rank) if e.world > 1 else None  # N = 1 keeps every core for the CPU baseline leg
+    e.numa = bind_to_gpu_numa(e.local_rank) if (e.world > 1 and not os.environ.get("BENCH_NO_NUMA")) else None  # N = 1 keeps every core for the CPU baseline leg
     if e.world > 1:
         dist.init_process_group("nccl", device_id=e.dev)
     e.main_stream = torch.cuda.Stream(device=e.dev)
@@ -322,12 +322,14 @@ def run_steps(e, ctxs, streams, steps, issue, host, after=None):
     t_begin.record(e.main_stream)
     for st in streams:
         st.wait_event(t_begin)
+    t_host = time.perf_counter()
     for k in range(steps):
         c = k % NC
         if host and k >= NC:
             ctxs[c].wait()  # the host buffers of this context are about to be reused
         issue(c)
         e.launches += ctxs[c].stats()["launches"]
+    e.host_issue_ms = (time.perf_counter() - t_host) * 1e3
     if after is not None:
         after((steps - 1) % NC)
     for st in streams:
@@ -383,7 +385,8 @@ def bench_solver(args, e):
     feas = lambda cand: ctxs[0].nodes_feasible(cand)[0]
     mkcfg = (lambda sd: synthetic.batch_config_m200i_psgcfs(B, feas, horizon=H, seed=sd)) if psg else \
         (lambda sd: synthetic.batch_config_m16ib(B, feas, horizon=H, seed=sd))
-    cfgs = [mkcfg(synthetic.SEED + 1000 * e.rank + c) for c in range(NC)]
+    seed0 = synthetic.SEED + 1000 * int(os.environ.get("BENCH_SEED_RANK", e.rank))  # development: another rank's batches
+    cfgs = [mkcfg(seed0 + c) for c in range(NC)]
     s = cfgs[0]["sys_info"]
     eps_o, K, alpha = float(s["epsilon_O"]), int(s["MAX_O_ITER"]), float(s.get("alpha", 0.0))
     for ctx in ctxs:
@@ -433,8 +436,29 @@ def bench_solver(args, e):
     barrier(e)
     sampler.mark()
     e.launches = 0
-    ms_dev = run_steps(e, ctxs, streams, args.steps, lambda c: issue(c, False), False, after=final_gather)
+    ms_dev = run_steps(e, ctxs, streams, args.steps, lambda c: issue(c, False), False,
+                       after=None if os.environ.get("BENCH_NO_GATHER") else final_gather)
     barrier(e)
+    rank_ms = [ms_dev]
+    if e.world > 1:  # every rank's own device time (diagnostic: the value uses the max)
+        t_all = torch.zeros(e.world, dtype=torch.float64, device=e.dev)
+        e.dist.all_gather_into_tensor(t_all, torch.tensor([ms_dev], dtype=torch.float64, device=e.dev))
+        rank_ms = [float(v) for v in t_all]
+    if os.environ.get("BENCH_QUICK"):  # development: resident leg only
+        clk = sampler.stop()
+        info = [None] * e.world
+        mine = {"rank": e.rank, "issue_ms": round(e.host_issue_ms, 2), "sm_mhz": clk.get("sm_mhz"), "numa": e.numa,
+                "cores": cpu_count(), "seed0": seed0}
+        if e.world > 1:
+            e.dist.all_gather_object(info, mine)
+        else:
+            info = [mine]
+        if e.rank == 0:
+            print(json.dumps({"quick_ranks": info}), flush=True)
+        if e.rank == 0:
+            print(json.dumps({"quick": True, "n_gpus": e.world, "ms_per_step": max(rank_ms) / args.steps,
+                              "rank_ms_per_step": [v / args.steps for v in rank_ms], "clocks": clk}), flush=True)
+        return
     wp_ctx = [ctxs[c].stats()["grad_waypoints"] for c in range(min(NC, args.steps))]
     wp_timed = sum(wp_ctx[k % NC] for k in range(args.steps))
     conv_ctx = [float(((d_out[c]["status"] & 0xFF) == 0).double().mean()) for c in range(min(NC, args.steps))]
@@ -535,10 +559,11 @@ def bench_solver(args, e):
                    "contexts": NC, "seed": synthetic.SEED, "numa_binding": e.numa,
                    "parallelism": "independent problems sharded over %d GPU(s), no data-path collective; one NCCL all-gather "
                                   "of (cost,status) at the end of the timed region" % e.world},
-        "e2e": {"value": e.world * B * args.steps / (ms_e2e * 1e-3), "unit": unit,
-                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps,
-                "api": "cfs_solve_batch_async + cfs_wait (host pointers, pinned): H2D + solve + D2H of every step "
-                       "inside the timed events, %d contexts in rotation" % NC},
+        "e2e_arrays": {"value": e.world * B * args.steps / (ms_e2e * 1e-3), "unit": unit,
+                       "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps,
+                       "api": "cfs_solve_batch_async + cfs_wait (host pointers, pinned): every array of the class contract in "
+                              "(x0, ff, caug, x_) and out (u, x_, cost_all, e_u_all, iters, status), H2D + solve + D2H of every "
+                              "step inside the timed events, %d contexts in rotation" % NC},
         "e2e_pageable": {"value": e.world * B * steps_p / (ms_page * 1e-3), "unit": unit, "steps": steps_p,
                          "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_page / steps_p,
                          "api": "the same entry with pageable (numpy / mxGetPr-like) caller buffers: the library stages them "
@@ -547,6 +572,7 @@ def bench_solver(args, e):
         "gpu_launches_note": "kernels launched by libcfs_b200 inside the two timed regions (device-resident + e2e), counted by "
                              "the library per solve (cfs_stats.launches: %d per step)" % int(stt["launches"]),
         "clocks": clocks,
+        "rank_ms_per_step": [v / args.steps for v in rank_ms],
         "converged_trajectories_per_sec": e.world * B * args.steps / (ms_dev * 1e-3) * conv_frac,
         "latency_ms_single_batch": float(min(lat1)),
         "ms_per_cfs_iter": float(min(lat1)) / max(int(iters.max()), 1),
@@ -581,13 +607,17 @@ def bench_solver(args, e):
                         "mean_iters": float(iters.mean()), "max_iters": int(iters.max()),
                         "qp_steps": int(stt["qp_steps"]), "max_working_set": int(stt["max_active"])},
     })
-    if ms_sg is not None:
-        line["e2e_start_goal"] = {"value": e.world * B * args.steps / (ms_sg * 1e-3), "unit": unit,
-                                  "h2d_bytes_per_step": int(2 * B * nj * 8), "d2h_bytes_per_step": int(B * (n + K) * 8 + 2 * B * 4),
-                                  "ms_per_step": ms_sg / args.steps, "status_equal_to_array_path": sg_status_equal,
-                                  "api": "cfs_set_cost_blocks + cfs_solve_start_goal_async: start/goal pairs in, the mains' set-up "
-                                         "(straight-line reference, ff, caug: main_FANUC.m:38-103) built on the device, "
-                                         "u + cost history + iters + status out (the recommended batch entry)"}
+    if ms_sg is None:
+        line["e2e"] = line["e2e_arrays"]
+    else:
+        line["e2e"] = {"value": e.world * B * args.steps / (ms_sg * 1e-3), "unit": unit,
+                       "h2d_bytes_per_step": int(2 * B * nj * 8), "d2h_bytes_per_step": int(B * (n + K) * 8 + 2 * B * 4),
+                       "ms_per_step": ms_sg / args.steps, "status_equal_to_array_path": sg_status_equal,
+                       "api": "cfs_set_cost_blocks + cfs_solve_start_goal_async + cfs_wait, the documented batch entry (INTEGRATION.md): "
+                              "start/goal pairs in from pinned host memory, the mains' set-up (straight-line reference, ff, caug: "
+                              "main_FANUC.m:38-103) built on the device, u + cost history + iters + status back to the host "
+                              "(x_ is the roll-out of u and is copied only on request); e2e_arrays is the array entry with "
+                              "every input and output of the class contract copied"}
     if e.world == 1:
         # bounded CPU sample of the same workload: the oracle port on all host cores and on one, plus a parity check
         import oracle as O

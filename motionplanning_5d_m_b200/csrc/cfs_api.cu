@@ -597,7 +597,10 @@ static int solve_device(cfs_ctx *ctx, int B, int solver, int grad, const double 
   const int grid_heavy2 = grid_heavy > 32 ? 32 : grid_heavy;  // second heavy launch of the screened pipeline: late escalations
   if (fused && ctx->bulk_grid > 0 && grid > ctx->bulk_grid) grid = ctx->bulk_grid;
   if (getenv("CFS_DEBUG")) fprintf(stderr, "[cfs] solve: B=%d fused=%d warp=%d cfg=%d zs=%d grid=%d grid_heavy=%d\n", B, (int)fused, (int)warp, ctx->warp_cfg, a.warp_zs, grid, grid_heavy);
-  if ((rc = ensure(ctx, ctx->slab, sizeof(double) * (size_t)n * n * (grid > grid_heavy ? grid : grid_heavy)))) return rc;
+  // spill slabs of the working-set inverse: the warp tier has its own (zslab); the CTA tiers need n x n per CTA, and the two
+  // heavy launches of the screened pipeline can overlap, so they get disjoint halves
+  const int slab_ctas = fused ? ((warp ? 0 : grid) > 2 * grid_heavy ? grid : 2 * grid_heavy) : grid;
+  if ((rc = ensure(ctx, ctx->slab, sizeof(double) * (size_t)n * n * slab_ctas))) return rc;
   a.slab = ptr<double>(ctx->slab);
 
   const bool detail = ctx->timing_level >= 2;
@@ -648,6 +651,7 @@ static int solve_device(cfs_ctx *ctx, int B, int solver, int grad, const double 
       a2.esc_list = ext + 2 * (size_t)B;  // late escalations (working sets that outgrow the warp tier in later iterations)
       a2.esc_count = cnt + 8;
       a2.work_counter2 = cnt + 9;
+      a2.slab = a.slab + (size_t)n * n * grid_heavy;
       if (side) {
         CU(cudaEventRecord(ctx->ev_bulk, st));
         CU(cudaStreamWaitEvent(ctx->heavy_stream, ctx->ev_bulk, 0));
