@@ -156,6 +156,20 @@ int cfs_solve_routes_device(cfs_ctx *ctx, int B, int W, const int *route_len, in
                             double *cost_hist, double *e_u_hist, int *iters, int *status, int sync);
 /* The resampling step alone: sampled (nj x (H+1) x B) = cubicpolytraj(route, (0:W-1)*dt, linspace(0,(W-1)*dt,H+1)). */
 int cfs_resample_routes(cfs_ctx *ctx, int B, int W, int H, const double *routes /*nj x W x B*/, double *sampled);
+/* CHOMP_FANUC(obs, sys_info, uu, ROBOT).optimizer()  (Lib/CHOMP_FANUC.m:54-165), the gradient-descent baseline planner of the
+ * reference, for B problems that share robot, obstacles and cost:
+ *   u_init = uu (n x B), xref = sys_info.x_, alpha = sys_info.alpha; obs{j}.D / obs{j}.epsilon from cfs_set_obstacles.
+ *   Every outer iteration: dm_f per link (:115-134), derivest gradient of dist_link_*(linkid) (:151,:156), the update
+ *   u <- u - alpha*3*(QQ*u + ff + 2000*dcostObs) (:75), roll-out, cost_all(k) = get_cost(u) + fobs_m() (:63).
+ *   The reference's stop rule never fires before MAX_O_ITER (eval.x_ / eval.x_old are never updated by this class), so
+ *   iters = max_outer and status = CFS_STATUS_MAX_ITER for every problem (| CFS_FLAG_TOUCH).  x and e_u_hist may be NULL.
+ *   Two quirks of the reference are reproduced as written and documented in DESIGN.md: dm_f has no joint-2 offset on the
+ *   200i, and the gradient of waypoint i is chained through Baug((i-1)*njoint+1 : i*njoint, :) (row stride njoint). */
+int cfs_chomp_batch(cfs_ctx *ctx, int B, const double *x0 /*2nj x B*/, const double *ff /*n x B*/, const double *caug /*B*/,
+                    const double *xref /*2njH x B*/, const double *u_init /*n x B*/, double alpha, int max_outer,
+                    double *u /*n x B*/, double *x /*2njH x B or NULL*/, double *cost_hist /*max_outer x B*/,
+                    double *e_u_hist /*max_outer x B or NULL*/, int *iters /*B*/, int *status /*B*/);
+
 /* Blocks until the context's stream is idle and collects the statistics of the batch in flight (if any). */
 int cfs_wait(cfs_ctx *ctx);
 /* Same, every pointer is a DEVICE pointer on ctx's device (inputs already resident in HBM); asynchronous on the

@@ -169,9 +169,11 @@ static void out_int(mxArray *&dst, const std::vector<int> &v) {
 
 // ---- 'solve' ------------------------------------------------------------------------------------------------------------------
 static void cmd_solve(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]) {
-  if (nrhs < 5) mexErrMsgIdAndTxt("cfs:arg", "usage: cfs_mex('solve', solver, grad, ROBOT, obs, sys_info [, noise])");
+  if (nrhs < 5) mexErrMsgIdAndTxt("cfs:arg", "usage: cfs_mex('solve', solver, grad, ROBOT, obs, sys_info [, noise | uu])");
   const std::string solver = str(prhs[0]), grad = str(prhs[1]), robot_name = str(prhs[2]);
-  if (solver != "CFS" && solver != "PSGCFS") mexErrMsgIdAndTxt("cfs:arg", "solver '%s' (CFS | PSGCFS)", solver.c_str());
+  if (solver != "CFS" && solver != "PSGCFS" && solver != "CHOMP")
+    mexErrMsgIdAndTxt("cfs:arg", "solver '%s' (CFS | PSGCFS | CHOMP)", solver.c_str());
+  const bool chomp = solver == "CHOMP";
   if (grad != "num_jac" && grad != "derivest") mexErrMsgIdAndTxt("cfs:arg", "grad '%s' (num_jac | derivest)", grad.c_str());
   const mxArray *obs = prhs[3], *si = prhs[4];
   const int H = (int)scalar(field(si, "H"), "sys_info.H"), nj = (int)scalar(field(si, "njoint"), "sys_info.njoint");
@@ -211,7 +213,12 @@ static void cmd_solve(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]
   const size_t ldxr = xr_rows * (xr_cols / B);  // sys_info.xR may carry later roll-out columns (B = 1)
   for (size_t b = 0; b < B; ++b) std::memcpy(&x0[(size_t)2 * nj * b], mxGetPr(xR) + ldxr * b, 2 * nj * sizeof(double));
   const double *noise = nullptr;
-  if (nrhs > 5 && prhs[5] && !mxIsEmpty(prhs[5])) noise = dbl(prhs[5], n * (size_t)K * B, "noise (n x MAX_O_ITER x B)");
+  if (chomp) {  // CHOMP_FANUC(obs, sys_info, uu, ROBOT): the initial controls (Lib/CHOMP_FANUC.m:34,48)
+    if (nrhs < 6 || !prhs[5] || mxIsEmpty(prhs[5])) mexErrMsgIdAndTxt("cfs:arg", "CHOMP needs the initial controls uu (n x B)");
+    noise = dbl(prhs[5], n * B, "uu (n x B)");
+  } else if (nrhs > 5 && prhs[5] && !mxIsEmpty(prhs[5])) {
+    noise = dbl(prhs[5], n * (size_t)K * B, "noise (n x MAX_O_ITER x B)");
+  }
   if (psg && !noise && K > 0)
     mexErrMsgIdAndTxt("cfs:arg", "PSGCFS needs the normrnd(0,0.1,[nn,1]) draws of every outer iteration (PSGCFS_FANUC.m:109) as "
                                  "noise (n x MAX_O_ITER x B); matlab/PSGCFS_FANUC.m draws them");
@@ -220,6 +227,12 @@ static void cmd_solve(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]
   mxArray *x = mxCreateDoubleMatrix(2 * n, B, mxREAL), *cost = mxCreateDoubleMatrix(K > 0 ? K : 1, B, mxREAL),
           *eu = mxCreateDoubleMatrix(K > 0 ? K : 1, B, mxREAL);
   mxArray *it = mxCreateNumericMatrix(1, B, mxINT32_CLASS, mxREAL), *st = mxCreateNumericMatrix(1, B, mxINT32_CLASS, mxREAL);
+  if (chomp) {
+    if (!alpha) mexErrMsgIdAndTxt("cfs:arg", "CHOMP needs sys_info.alpha");
+    check(cfs_chomp_batch(g_ctx, (int)B, x0.data(), mxGetPr(ff), mxGetPr(caug), mxGetPr(xref), noise, scalar(alpha, "sys_info.alpha"), K,
+                          mxGetPr(plhs[0]), mxGetPr(x), mxGetPr(cost), mxGetPr(eu), (int *)mxGetData(it), (int *)mxGetData(st)),
+          "cfs_chomp_batch");
+  } else
   check(cfs_solve_batch(g_ctx, (int)B, psg ? CFS_SOLVER_PSGCFS : CFS_SOLVER_CFS, grad == "derivest" ? CFS_GRAD_DERIVEST : CFS_GRAD_NUMJAC,
                         x0.data(), mxGetPr(ff), mxGetPr(caug), mxGetPr(xref), noise, scalar(field(si, "epsilon_O"), "sys_info.epsilon_O"), K,
                         alpha ? scalar(alpha, "sys_info.alpha") : 0.0, mxGetPr(plhs[0]), mxGetPr(x), mxGetPr(cost), mxGetPr(eu),
@@ -349,6 +362,6 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]) {
   if (cmd == "solve") return cmd_solve(nlhs, plhs, nrhs - 1, prhs + 1);
   if (cmd == "rrt") return cmd_rrt(nlhs, plhs, nrhs - 1, prhs + 1);
   if (cmd == "routes") return cmd_routes(nlhs, plhs, nrhs - 1, prhs + 1);
-  if (cmd == "CFS" || cmd == "PSGCFS") return cmd_solve(nlhs, plhs, nrhs, prhs);  // round-1 calling form
+  if (cmd == "CFS" || cmd == "PSGCFS" || cmd == "CHOMP") return cmd_solve(nlhs, plhs, nrhs, prhs);  // short calling form
   mexErrMsgIdAndTxt("cfs:arg", "unknown command '%s' (solve | rrt | routes | device)", cmd.c_str());
 }

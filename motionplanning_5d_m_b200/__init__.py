@@ -5,7 +5,7 @@ reference's MATLAB interface for that path (CFS_FANUC, PSGCFS_FANUC, EVAL, robot
 """
 from ._lib import (CfsError, Context, FLAG_TOUCH, GRAD_DERIVEST, GRAD_NUMJAC, SOLVER_CFS, SOLVER_PSGCFS,  # noqa: F401
                    STATUS_CONVERGED, STATUS_INFEASIBLE, STATUS_MAX_ITER, STATUS_NO_ROUTE, STATUS_NUMERICAL)
-from .cfs import CFS_FANUC, PSGCFS_FANUC, BatchCFS, EVAL  # noqa: F401
+from .cfs import CFS_FANUC, PSGCFS_FANUC, CHOMP_FANUC, BatchCFS, EVAL  # noqa: F401
 from .problem import (build_cost_matrices, build_linear_term, make_sys_info, straight_line_reference)  # noqa: F401
 from .robot import robotproperty2  # noqa: F401
 from .rrt import RRT_FANUC, s_Parallel_rrt, rrtstar_cfs  # noqa: F401

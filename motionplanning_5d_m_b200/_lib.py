@@ -19,7 +19,7 @@ FLAG_TOUCH = 0x100
 
 # every symbol include/cfs_b200.h declares (tests check that the library exports all of them)
 SYMBOLS = ["cfs_create", "cfs_destroy", "cfs_last_error", "cfs_version", "cfs_set_stream", "cfs_set_option", "cfs_set_robot", "cfs_set_obstacles", "cfs_set_obstacles_ex",
-           "cfs_set_cost", "cfs_set_cost_blocks", "cfs_solve_start_goal", "cfs_solve_start_goal_async", "cfs_solve_routes", "cfs_solve_routes_async", "cfs_solve_routes_var", "cfs_solve_routes_var_async", "cfs_solve_routes_device", "cfs_resample_routes", "cfs_solve_batch", "cfs_solve_batch_async", "cfs_wait", "cfs_solve_batch_device", "cfs_dist_grad", "cfs_time_dist_grad", "cfs_get_con",
+           "cfs_set_cost", "cfs_set_cost_blocks", "cfs_solve_start_goal", "cfs_solve_start_goal_async", "cfs_solve_routes", "cfs_solve_routes_async", "cfs_solve_routes_var", "cfs_solve_routes_var_async", "cfs_solve_routes_device", "cfs_resample_routes", "cfs_solve_batch", "cfs_solve_batch_async", "cfs_chomp_batch", "cfs_wait", "cfs_solve_batch_device", "cfs_dist_grad", "cfs_time_dist_grad", "cfs_get_con",
            "cfs_nodes_feasible", "cfs_nearest_steer", "cfs_rrt_find_routes", "cfs_rrt_find_routes_device", "cfs_get_stats", "cfs_set_timing", "cfs_get_iter_times", "cfs_get_problem_steps", "cfs_get_qp_profile", "cfs_measure_fp64_peak"]
 
 
@@ -259,6 +259,24 @@ class Context:
                                        _dp(out["u"]), _dp(out["x"]), _dp(out["cost_hist"]), _dp(out["e_u_hist"]),
                                        _dp(out["iters"]), _dp(out["status"]))
         self._check(rc, "cfs_solve_batch")
+        return out
+
+    def chomp_batch(self, x0, ff, caug, xref, u_init, alpha, max_outer):
+        """CHOMP_FANUC.optimizer (Lib/CHOMP_FANUC.m:54-165) for B problems: x0 (B,2nj), ff (B,n), caug (B,), xref (B,2njH),
+        u_init (B,n) = the constructor's uu.  Exactly max_outer gradient steps per problem (cfs_chomp_batch)."""
+        x0, ff, caug, xref, u_init = _f64(x0), _f64(ff), _f64(caug), _f64(xref), _f64(u_init)
+        B = x0.shape[0]
+        if not getattr(self, "n", 0):
+            raise CfsError("cost not set (cfs_set_cost)")
+        n, N = self.n, 2 * self.n
+        assert x0.shape == (B, 2 * self.nj) and ff.shape == (B, n) and xref.shape == (B, N) and caug.shape == (B,)
+        assert u_init.shape == (B, n)
+        out = dict(u=np.empty((B, n)), x=np.empty((B, N)), cost_hist=np.empty((B, max_outer)),
+                   e_u_hist=np.empty((B, max_outer)), iters=np.empty(B, dtype=np.int32), status=np.empty(B, dtype=np.int32))
+        rc = self._lib.cfs_chomp_batch(self._h, C.c_int(B), _dp(x0), _dp(ff), _dp(caug), _dp(xref), _dp(u_init),
+                                       C.c_double(alpha), C.c_int(max_outer), _dp(out["u"]), _dp(out["x"]),
+                                       _dp(out["cost_hist"]), _dp(out["e_u_hist"]), _dp(out["iters"]), _dp(out["status"]))
+        self._check(rc, "cfs_chomp_batch")
         return out
 
     def solve_batch_ptr(self, B, x0, ff, caug, xref, eps_outer, max_outer, u, x, cost_hist, e_u_hist, iters, status,

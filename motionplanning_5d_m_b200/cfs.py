@@ -99,6 +99,33 @@ class PSGCFS_FANUC(_SolverBase):
     SOLVER = _lib.SOLVER_PSGCFS
 
 
+class CHOMP_FANUC(_SolverBase):
+    """Lib/CHOMP_FANUC.m: self = CHOMP_FANUC(obs, sys_info, uu, ROBOT); self = self.optimizer()  -- the gradient-descent
+    baseline planner: exactly MAX_O_ITER steps u <- u - alpha*3*(QQ*u + ff + 2000*dcostObs) (CHOMP_FANUC.m:54-83)."""
+
+    def __init__(self, obs, sys_info, uu, ROBOT="M16iB", ctx=None, device=0):
+        super().__init__(obs, sys_info, ROBOT, ctx=ctx, device=device)
+        self.u = np.array(uu, dtype=np.float64).reshape(-1)  # CHOMP_FANUC.m:48
+
+    def optimizer(self):
+        s = self.sys_info
+        ctx = self._context()
+        K = int(s["MAX_O_ITER"])
+        out = ctx.chomp_batch(np.asarray(s["xR"], dtype=np.float64)[:, 0][None], np.asarray(s["ff"])[None],
+                              np.array([s["caug"]], dtype=np.float64), self.x_[None], self.u[None], float(s["alpha"]), K)
+        cost0 = self.eval.get_cost(self.u)  # CHOMP_FANUC.m:55
+        self.u = out["u"][0].copy()
+        self.x_ = out["x"][0].copy()
+        self.status = int(out["status"][0])
+        self.iter_O = K + 1
+        self.eval.cost_all = out["cost_hist"][0].copy()
+        self.eval.e_u_all = out["e_u_hist"][0].copy()
+        self.eval.e_cost_all = np.abs(np.concatenate([[cost0], self.eval.cost_all[:-1]]) - self.eval.cost_all)  # EVAL.m:57
+        if K:
+            self.eval.cost_new = float(self.eval.cost_all[-1])
+        return self
+
+
 class BatchCFS:
     """B independent problems sharing robot / obstacles / horizon / weights: the batched form of CFS_FANUC.optimizer."""
 

@@ -1207,6 +1207,82 @@ extern "C" int cfs_solve_batch(cfs_ctx *ctx, int B, int solver, int grad, const 
   return cfs_wait(ctx);
 }
 
+// ---- CHOMP_FANUC (Lib/CHOMP_FANUC.m), k_chomp.cu ----------------------------------------------------------------------
+extern "C" int cfs_chomp_batch(cfs_ctx *ctx, int B, const double *x0, const double *ff, const double *caug, const double *xref,
+                               const double *u_init, double alpha, int max_outer, double *u, double *x, double *cost_hist,
+                               double *e_u_hist, int *iters, int *status) {
+  if (!ctx) return CFS_E_ARG;
+  int rc = check_ready(ctx, true);
+  if (rc) return rc;
+  if (B < 0 || max_outer < 0) return fail(ctx, CFS_E_ARG, "cfs_chomp_batch: bad argument");
+  if (B == 0) return 0;
+  if (!x0 || !ff || !caug || !xref || !u_init || !u || !cost_hist || !iters || !status)
+    return fail(ctx, CFS_E_ARG, "cfs_chomp_batch: NULL buffer");
+  if ((rc = finish_pending(ctx))) return rc;
+  CU(cudaSetDevice(ctx->device));
+  const int nj = ctx->nj, H = ctx->H, n = ctx->n, N = 2 * n, O = ctx->nobs, OH = O * H, K = max_outer;
+  cudaStream_t st = ctx->stream;
+  NvtxRange nvtx("cfs:chomp");
+  // one device buffer: x0 | ff | caug | u | x | w | cost | e_u | dist | grad | linkdist | flags
+  size_t o_x0 = 0, o_ff = o_x0 + (size_t)2 * nj * B, o_caug = o_ff + (size_t)n * B, o_u = o_caug + B, o_x = o_u + (size_t)n * B,
+         o_w = o_x + (size_t)N * B, o_cost = o_w + (size_t)n * B, o_eu = o_cost + (size_t)K * B + 1,
+         o_dist = o_eu + (size_t)K * B + 1, o_grad = o_dist + (size_t)OH * B + 1, o_ld = o_grad + (size_t)OH * B * nj + 1,
+         o_fl = o_ld + (size_t)OH * B * nj + 1, total = o_fl + (size_t)(B + 1) / 2 + 1;
+  if ((rc = ensure(ctx, ctx->scratch_out, sizeof(double) * total))) return rc;
+  double *d = ptr<double>(ctx->scratch_out);
+  int *d_flags = reinterpret_cast<int *>(d + o_fl);
+  CU(cudaMemcpyAsync(d + o_x0, x0, sizeof(double) * (size_t)2 * nj * B, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(d + o_ff, ff, sizeof(double) * (size_t)n * B, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(d + o_caug, caug, sizeof(double) * B, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(d + o_u, u_init, sizeof(double) * (size_t)n * B, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(d + o_x, xref, sizeof(double) * (size_t)N * B, cudaMemcpyHostToDevice, st));
+  CU(cudaMemsetAsync(d_flags, 0, sizeof(int) * B, st));
+  GradArgs g;
+  memset(&g, 0, sizeof(g));
+  g.tab = ctx->dtab; g.dv = ctx->ddv;
+  g.x = d + o_x; g.ld_prob = N; g.ld_i = 2 * nj;
+  g.nslots = B; g.H = H; g.nj = nj; g.nobs = O;
+  g.o_prob = OH; g.o_obs = H; g.o_i = 1;
+  g.dist = d + o_dist; g.grad = d + o_grad; g.linkdist = d + o_ld; g.flags = d_flags;
+  g.no_off = 1;
+  ChompArgs a;
+  memset(&a, 0, sizeof(a));
+  a.B = B; a.n = n; a.nj = nj; a.H = H; a.nobs = O; a.max_outer = K; a.alpha = alpha; a.tab = ctx->dtab;
+  a.x0 = d + o_x0; a.ff = d + o_ff; a.caug = d + o_caug; a.u = d + o_u; a.x = d + o_x; a.w = d + o_w;
+  a.dist = g.dist; a.grad = g.grad; a.linkdist = g.linkdist;
+  a.cost_hist = d + o_cost; a.e_u_hist = d + o_eu;
+  int launches = 0;
+  CU(cudaEventRecord(ctx->ev_a, st));
+  if (O > 0) { CU(launch_grad_derivest(g, st)); ++launches; }
+  CU(launch_dgemm(n, B, n, 1.0, ctx->dQQraw, n, false, a.u, n, d + o_w, n, st)); ++launches;
+  for (int it = 1; it <= K; ++it) {
+    a.it = it;
+    CU(launch_chomp_step(a, st)); ++launches;
+    if (O > 0) { CU(launch_grad_derivest(g, st)); ++launches; }
+    CU(launch_dgemm(n, B, n, 1.0, ctx->dQQraw, n, false, a.u, n, d + o_w, n, st)); ++launches;
+    CU(launch_chomp_cost(a, st)); ++launches;
+  }
+  CU(cudaEventRecord(ctx->ev_b, st));
+  CU(cudaMemcpyAsync(u, d + o_u, sizeof(double) * (size_t)n * B, cudaMemcpyDeviceToHost, st));
+  if (x) CU(cudaMemcpyAsync(x, d + o_x, sizeof(double) * (size_t)N * B, cudaMemcpyDeviceToHost, st));
+  if (K > 0) {
+    CU(cudaMemcpyAsync(cost_hist, d + o_cost, sizeof(double) * (size_t)K * B, cudaMemcpyDeviceToHost, st));
+    if (e_u_hist) CU(cudaMemcpyAsync(e_u_hist, d + o_eu, sizeof(double) * (size_t)K * B, cudaMemcpyDeviceToHost, st));
+  }
+  std::vector<int> fl(B);
+  CU(cudaMemcpyAsync(fl.data(), d_flags, sizeof(int) * B, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  for (int b = 0; b < B; ++b) {
+    iters[b] = K;
+    status[b] = CFS_STATUS_MAX_ITER | (fl[b] & 0x100);  // stop_outer only ends at iter_O > MAX_O_ITER (CHOMP_FANUC.m:56)
+  }
+  float ms = 0;
+  cudaEventElapsedTime(&ms, ctx->ev_a, ctx->ev_b);
+  ctx->stats.ms_total = ms;
+  ctx->stats.launches = launches;
+  return 0;
+}
+
 // ---- direct kernels -------------------------------------------------------------------------------------------------
 extern "C" int cfs_dist_grad(cfs_ctx *ctx, int N, int grad_mode, const double *theta, double *dist, int *linkid,
                              double *grad, int *flags) {

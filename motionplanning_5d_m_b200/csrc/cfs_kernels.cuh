@@ -24,6 +24,11 @@ struct GradArgs {
   int *linkid;
   double *grad;
   int *flags;                // per problem: OR of CFS_FLAG_TOUCH (atomicOr)
+  // K1d, CHOMP_FANUC.dm_f mode (Lib/CHOMP_FANUC.m:115-134): the base evaluation (distance per link, linkid) ignores the joint
+  // offsets of the table (dm_f sets DH(i,1) = theta(i) and nothing else, also on the 200i), the derivest evaluations of
+  // dist_link_* keep them; linkdist (or nullptr) receives the nj per-link distances of every (waypoint, obstacle) pair
+  int no_off;
+  double *linkdist;
 };
 cudaError_t launch_grad_numjac(const GradArgs &a, cudaStream_t s);
 cudaError_t launch_grad_derivest(const GradArgs &a, cudaStream_t s);
@@ -144,6 +149,20 @@ struct SolveArgs {
 };
 cudaError_t launch_solve_init(const SolveArgs &a, cudaStream_t s);
 cudaError_t launch_v0(const SolveArgs &a, cudaStream_t s);
+// ---- CHOMP_FANUC (k_chomp.cu) ------------------------------------------------------------------------------
+struct ChompArgs {
+  int B, n, nj, H, nobs, max_outer, it;
+  double alpha;
+  const DevTables *tab;
+  const double *x0, *ff, *caug;  // 2nj x B, n x B, B
+  double *u, *x;                 // n x B, 2n x B: the iterate, updated in place
+  const double *w;               // QQ * u of the current u (n x B)
+  const double *dist, *grad, *linkdist;  // K1d (dm_f mode) at the current x: [b][obstacle][waypoint] (, [joint] / [link])
+  double *cost_hist, *e_u_hist;  // max_outer x B
+};
+cudaError_t launch_chomp_step(const ChompArgs &a, cudaStream_t s);
+cudaError_t launch_chomp_cost(const ChompArgs &a, cudaStream_t s);
+
 cudaError_t launch_psg_point(const SolveArgs &a, cudaStream_t s);  // K5: PSG_update_arm point + v0 = P*point
 cudaError_t launch_psg_cost(const SolveArgs &a, cudaStream_t s);   // EVAL.get_cost of the projected iterate
 cudaError_t launch_qp(const SolveArgs &a, int grid, cudaStream_t s);

@@ -164,6 +164,7 @@ __global__ void __launch_bounds__(GRAD_THREADS, K1D_MINB) k_grad_derivest(GradAr
         xf_first(tab.link[0], cs, sn, M);
       else
         xf_step_inplace(M, tab.link[l], cs, sn);
+      if (a.no_off) continue;
       link_endpoints(M, tab.link[l], tab.base, p);
       const double d = link_obs_dist(p, tab.obs[j], touched);
       if (d < dbase) {
@@ -172,6 +173,24 @@ __global__ void __launch_bounds__(GRAD_THREADS, K1D_MINB) k_grad_derivest(GradAr
       }
     }
     const long long o = prob * a.o_prob + (long long)j * a.o_obs + i * a.o_i;
+    if (a.no_off) {  // CHOMP_FANUC.dm_f: the same chain without the joint offsets; every link's distance is kept
+#pragma unroll 1
+      for (int l = 0; l < NJ; ++l) {
+        double sn, cs;
+        sincos(thp[l], &sn, &cs);
+        if (l == 0)
+          xf_first(tab.link[0], cs, sn, M);
+        else
+          xf_step_inplace(M, tab.link[l], cs, sn);
+        link_endpoints(M, tab.link[l], tab.base, p);
+        const double d = link_obs_dist(p, tab.obs[j], touched);
+        if (a.linkdist) a.linkdist[o * NJ + l] = d;
+        if (d < dbase) {
+          dbase = d;
+          lid = l + 1;
+        }
+      }
+    }
     o_s[tid] = o;
     a.dist[o] = dbase;
     if (a.linkid) a.linkid[o] = lid;

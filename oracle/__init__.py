@@ -209,6 +209,23 @@ class Problem:
         return dict(u=u, x=x, cost_hist=cost, e_u_hist=e_u, iters=iters, status=status, qp_iters=qp[:, 0],
                     qp_max_active=qp[:, 1])
 
+    def chomp_batch(self, D, eps, x0, ff, caug, xref, u_init, nthreads=0, use_twin=False):
+        """CHOMP_FANUC.optimizer for B problems: D / eps = obs{j}.D / obs{j}.epsilon, u_init (B,n) = the constructor's uu."""
+        x0, ff, caug, xref, u_init = map(_f64, (x0, ff, caug, xref, u_init))
+        D, eps = _f64(np.atleast_1d(D)), _f64(np.atleast_1d(eps))
+        B = x0.shape[0]
+        K = self.cfg.max_outer
+        u = np.zeros((B, self.n))
+        x = np.zeros((B, self.N))
+        cost = np.zeros((B, K))
+        e_u = np.zeros((B, K))
+        iters = np.zeros(B, dtype=np.int32)
+        status = np.zeros(B, dtype=np.int32)
+        (twin() if use_twin else lib()).orc_chomp_solve_batch(C.byref(self.r), C.byref(self.cfg), _p(D), _p(eps), C.c_int(B),
+                                                               C.c_int(nthreads), _p(x0), _p(ff), _p(caug), _p(xref), _p(u_init),
+                                                               _p(u), _p(x), _p(cost), _p(e_u), _p(iters), _p(status))
+        return dict(u=u, x=x, cost_hist=cost, e_u_hist=e_u, iters=iters, status=status)
+
 
 def chol_J0(G):
     n = G.shape[0]

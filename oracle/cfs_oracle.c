@@ -1077,6 +1077,125 @@ void orc_cfs_solve_batch2(const orc_robot *r, const orc_cfg *c, int B, int nthre
 }
 
 /* ------------------------------------------------------------------------------------------
+ * CHOMP_FANUC (Lib/CHOMP_FANUC.m), the gradient-descent baseline planner.
+ *   dm_f (:115-134): per-link distance minus obs.D with DH(i,1)=theta(i) and NO joint-2 offset, also for
+ *     the 200i (unlike dist_link_200i.m:8) -- restated as written; touch rule as everywhere else.
+ *   dcostObs_f (:137-165): per waypoint i and obstacle j: linkid = argmin dm_f, gradient of
+ *     dist_link_*(linkid) by derivest per joint (:151,:156), chained through
+ *     Baug((i-1)*njoint+1 : i*njoint, :)  (:153,:158).  NOTE (faithful quirk): the row stride is njoint,
+ *     not nstate = 2*njoint, so waypoint i (1-based) picks the THETA rows of step (i+1)/2 when i is odd and
+ *     the OMEGA rows of step i/2 when i is even.
+ *   CHOMP_update_arm (:73-83): u <- u - alpha*3*(QQ*u + ff + 2000*dcostObs), then the roll-out.
+ *   fobs_m (:91-112): sum over waypoints, obstacles and ALL links of the CHOMP potential of dm_f.
+ *   optimizer (:54-69): eval.x_ / eval.x_old are never updated, so stop_outer only ends at iter_O >
+ *     MAX_O_ITER: exactly max_outer updates.  cost_all(k) = get_cost(u_k) + fobs_m(x_k) (:63).
+ * ---------------------------------------------------------------------------------------- */
+static void chomp_dm(const orc_robot *r, const double *theta, const double *obs6, double D, double *d /* nj */,
+                     int *touched) {
+  double pos[ORC_MAXL * 6];
+  if (r->kind == ORC_2L) {
+    cap_pos_2l(r, theta, pos);
+  } else {
+    double DH[ORC_MAXL][4];
+    memcpy(DH, r->DH, sizeof(DH));
+    for (int i = 0; i < r->nj; ++i) DH[i][0] = theta[i]; /* :119-121, no offset */
+    cap_pos_dh(DH, r->nj, r->base, r->cap, pos);
+  }
+  for (int i = 0; i < r->nj; ++i) d[i] = link_dist(pos + 6 * i, obs6, touched) - D; /* :127-133 */
+}
+
+static double chomp_potential(double d, double eps) { /* :100-106 */
+  if (d < 0) return -d + 0.5 * eps;
+  if (d <= eps) return (1.0 / (2.0 * eps)) * (d - eps) * (d - eps);
+  return 0.0;
+}
+
+int orc_chomp_solve(const orc_robot *r, const orc_cfg *c, const double *D, const double *eps, const double *x0,
+                    const double *ff, double caug, const double *xref, const double *u_init, double *u, double *x,
+                    double *cost_hist, double *e_u_hist, int *iters, int *touched) {
+  const int nj = r->nj, H = c->H, n = nj * H, N = 2 * nj * H;
+  const double dt = r->dt;
+  double *g = (double *)malloc(sizeof(double) * 2 * n), *uo = g + n;
+  for (int k = 0; k < n; ++k) u[k] = u_init[k];
+  for (int k = 0; k < N; ++k) x[k] = xref[k];
+  int it = 0;
+  for (it = 1; it <= c->max_outer; ++it) {
+    for (int k = 0; k < n; ++k) uo[k] = u[k];
+    /* dcostObs_f at the current x_ */
+    for (int k = 0; k < n; ++k) g[k] = 0.0;
+    for (int i = 1; i <= H; ++i) {
+      const double *theta = x + (size_t)(i - 1) * 2 * nj;
+      for (int j = 0; j < c->nobs; ++j) {
+        const double *o6 = c->obs + (size_t)ORC_OBS_STRIDE * j;
+        double d[ORC_MAXL];
+        chomp_dm(r, theta, o6, D[j], d, touched);
+        int lid = 1;
+        for (int s = 1; s < nj; ++s)
+          if (d[s] < d[lid - 1]) lid = s + 1; /* [dis, linkid] = min(Dfx): first minimum */
+        const double dv = d[lid - 1];
+        double w;
+        if (dv < 0) w = -1.0;
+        else if (dv <= eps[j]) w = (1.0 / eps[j]) * (dv - eps[j]);
+        else continue;
+        double dD[ORC_MAXL];
+        orc_derivest_grad(r, theta, o6, lid, dD, touched);
+        /* rows (i-1)*nj+1 .. i*nj of Baug: theta rows of step (i+1)/2 (i odd) or omega rows of step i/2 (i even) */
+        const int step = (i + 1) / 2, odd = i & 1;
+        for (int jj = 1; jj <= step; ++jj)
+          for (int k = 0; k < nj; ++k) {
+            const double bcoef = odd ? (0.5 * dt * dt + ((step - jj) * dt) * dt) : dt;
+            g[(jj - 1) * nj + k] += w * dD[k] * bcoef;
+          }
+      }
+    }
+    /* u <- u - alpha*3*(QQ*u + ff + 2000*dcostObs)   (:75) */
+    for (int cidx = 0; cidx < n; ++cidx) {
+      double qu = 0;
+      for (int k = 0; k < n; ++k) qu += c->QQ[cidx + (size_t)n * k] * uo[k];
+      u[cidx] = uo[cidx] - (c->alpha * 3) * ((qu + ff[cidx]) + 2000 * g[cidx]);
+    }
+    rollout(nj, H, dt, x0, u, x);
+    /* cost_new = get_cost(u) + fobs_m()   (:63) */
+    double fobs = 0;
+    for (int i = 1; i <= H; ++i)
+      for (int j = 0; j < c->nobs; ++j) {
+        double d[ORC_MAXL];
+        chomp_dm(r, x + (size_t)(i - 1) * 2 * nj, c->obs + (size_t)ORC_OBS_STRIDE * j, D[j], d, touched);
+        for (int s = 0; s < nj; ++s) fobs += chomp_potential(d[s], eps[j]);
+      }
+    cost_hist[it - 1] = get_cost(n, c->QQ, ff, caug, u) + fobs;
+    if (e_u_hist) {
+      double e2 = 0;
+      for (int k = 0; k < n; ++k) e2 += (uo[k] - u[k]) * (uo[k] - u[k]);
+      e_u_hist[it - 1] = sqrt(e2);
+    }
+  }
+  *iters = c->max_outer;
+  free(g);
+  return ORC_MAX_ITER;
+}
+
+void orc_chomp_solve_batch(const orc_robot *r, const orc_cfg *c, const double *D, const double *eps, int B, int nthreads,
+                           const double *x0, const double *ff, const double *caug, const double *xref,
+                           const double *u_init, double *u, double *x, double *cost_hist, double *e_u_hist, int *iters,
+                           int *status) {
+  const int nj = r->nj, n = nj * c->H, N = 2 * n;
+#ifdef _OPENMP
+  if (nthreads > 0) omp_set_num_threads(nthreads);
+#endif
+  (void)nthreads;
+#pragma omp parallel for schedule(dynamic, 1)
+  for (int b = 0; b < B; ++b) {
+    int touched = 0;
+    status[b] = orc_chomp_solve(r, c, D, eps, x0 + (size_t)b * 2 * nj, ff + (size_t)b * n, caug[b], xref + (size_t)b * N,
+                                u_init + (size_t)b * n, u + (size_t)b * n, x + (size_t)b * N,
+                                cost_hist + (size_t)b * c->max_outer,
+                                e_u_hist ? e_u_hist + (size_t)b * c->max_outer : NULL, &iters[b], &touched);
+    if (touched) status[b] |= 0x100;
+  }
+}
+
+/* ------------------------------------------------------------------------------------------
  * RRT_FANUC.feasible (Lib/RRT_FANUC.m:146-181): infeasible if any link distance < obs{j}.D (:172).
  * Returns 1 feasible / 0 not; *dmin = min over all (obstacle, link) distances (no early break, so that
  * the value is order-independent; the reference breaks out of the link loop, which only saves work).

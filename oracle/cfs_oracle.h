@@ -124,6 +124,16 @@ void orc_cfs_solve_batch2(const orc_robot *r, const orc_cfg *c, int B, int nthre
                           double *u, double *x, double *cost_hist, double *e_u_hist, int *iters, int *status,
                           int *qp_stats /* 2*B or NULL */);
 
+/* CHOMP_FANUC.optimizer (Lib/CHOMP_FANUC.m:54-165): exactly c->max_outer gradient steps from u_init / xref.
+ * D, eps: obs{j}.D and obs{j}.epsilon (c->margin is not used).  Returns ORC_MAX_ITER. */
+int orc_chomp_solve(const orc_robot *r, const orc_cfg *c, const double *D, const double *eps, const double *x0,
+                    const double *ff, double caug, const double *xref, const double *u_init, double *u, double *x,
+                    double *cost_hist, double *e_u_hist, int *iters, int *touched);
+void orc_chomp_solve_batch(const orc_robot *r, const orc_cfg *c, const double *D, const double *eps, int B, int nthreads,
+                           const double *x0, const double *ff, const double *caug, const double *xref,
+                           const double *u_init, double *u, double *x, double *cost_hist, double *e_u_hist, int *iters,
+                           int *status);
+
 /* RRT_FANUC.feasible (RRT_FANUC.m:146-181) and nearest/steer (RRT_FANUC.m:116-129) */
 int  orc_rrt_feasible(const orc_robot *r, const double *theta, int nobs, const double *obs, const double *D,
                       double *dmin, int *touched);

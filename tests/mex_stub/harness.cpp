@@ -248,7 +248,7 @@ extern "C" int mexh_cfs(const char *solver, const char *grad, const char *robot_
   si->fields["epsilon_O"] = dbl(1, 1, &eps_outer);
   si->fields["MAX_O_ITER"] = dbl(1, 1, &Kd);
   si->fields["alpha"] = dbl(1, 1, &alpha);
-  const mxArray *prhs[6] = {chr(solver), chr(grad), chr(robot_name), obs, si, noise ? dbl(n * max_outer, B, noise) : nullptr};
+  const mxArray *prhs[6] = {chr(solver), chr(grad), chr(robot_name), obs, si, noise ? (std::strcmp(solver, "CHOMP") == 0 ? dbl(n, B, noise) /* uu */ : dbl(n * max_outer, B, noise)) : nullptr};
   mxArray *plhs[7] = {nullptr};
   int rc = 0;
   try {

@@ -289,3 +289,81 @@ def cfs_optimizer(s, robot, obs_list, kind, psg=False, noise=None):
         cost_all.append(cost_new)
         iter_O += 1
     return u, x_, np.array(cost_all), iter_O - 1
+
+
+def dist_link(theta, robot, obs, kind, linkid):
+    """dist_link_Heu.m:1-26 / dist_link_200i.m:1-25 (the 200i variant subtracts pi/2 from joint 2, :8)"""
+    n = len(theta)
+    DH = robot["DH"][:n].copy()
+    DH[:, 0] = theta
+    if kind == "M200i":
+        DH[1, 0] = DH[1, 0] - np.pi / 2
+    pos = cap_pos(robot["base"], DH, [c["p"] for c in robot["cap"]])
+    i = linkid - 1
+    dis, pts = dist_lin_seg(pos[i][:, 0], pos[i][:, 1], obs[:, 0], obs[:, 1])
+    if abs(dis) < 0.0001:
+        dis = -np.linalg.norm(pts[:3] - pos[i][:, 1])
+    return dis
+
+
+def chomp_dm(theta, robot, ob):
+    """CHOMP_FANUC.dm_f (Lib/CHOMP_FANUC.m:115-134): DH(i,1) = theta(i) and nothing else, per-link distance minus obs.D"""
+    n = len(theta)
+    DH = robot["DH"][:n].copy()
+    DH[:, 0] = theta
+    pos = cap_pos(robot["base"], DH, [c["p"] for c in robot["cap"]])
+    d = np.zeros(n)
+    for i in range(n):
+        dis, pts = dist_lin_seg(pos[i][:, 0], pos[i][:, 1], ob["l"][:, 0], ob["l"][:, 1])
+        if abs(dis) < 0.0001:
+            dis = -np.linalg.norm(pts[:3] - pos[i][:, 1])
+        d[i] = dis - ob["D"]
+    return d
+
+
+def chomp_optimizer(s, robot, obs_list, kind, uu):
+    """CHOMP_FANUC.optimizer (Lib/CHOMP_FANUC.m:54-165) with the literal Baug row slices of :153/:158.  eval.x_ / eval.x_old are
+    never touched by the class, so the loop runs MAX_O_ITER times.  Returns u, x_, cost_all, e_u_all."""
+    H, nj, ns = s["H"], s["njoint"], 2 * s["njoint"]
+    n = H * nj
+    A, Bm = s["Aaug"], s["Baug"]
+    QQ, ff, caug = s["QQ"], s["ff"], s["caug"]
+    x0 = s["xR"][:, 0]
+    x_ = np.array(s["x_"], dtype=np.float64)
+    u = np.array(uu, dtype=np.float64)
+    cost_all, e_u_all = [], []
+    for _ in range(int(s["MAX_O_ITER"])):
+        u_old = u.copy()
+        dc_all = np.zeros(n)                                     # dcostObs_f, :137-165
+        for i in range(1, H + 1):
+            theta = x_[ns * (i - 1): ns * (i - 1) + nj]
+            for ob in obs_list:
+                Dfx = chomp_dm(theta, robot, ob)
+                lid = int(np.argmin(Dfx)) + 1
+                rows = Bm[(i - 1) * nj: i * nj, :]                # Baug((i-1)*njoint+1:i*njoint,:)  -- as written
+                if Dfx[lid - 1] < 0 or Dfx[lid - 1] <= ob["epsilon"]:
+                    dD = np.zeros(nj)
+                    for sj in range(nj):
+                        def f(xv, sj=sj):
+                            th = theta.copy()
+                            th[sj] = xv
+                            return dist_link(th, robot, ob["l"], kind, lid)
+                        dD[sj] = derivest(f, theta[sj])[0]
+                    if Dfx[lid - 1] < 0:
+                        dc_all += -(dD @ rows)
+                    else:
+                        dc_all += (1.0 / ob["epsilon"]) * (Dfx[lid - 1] - ob["epsilon"]) * (dD @ rows)
+        u = u_old - s["alpha"] * 3 * ((QQ @ u_old + ff) + 2000 * dc_all)          # :75
+        x_ = A @ x0 + Bm @ u                                                       # :77-82
+        fobs = 0.0                                                                 # fobs_m, :91-112
+        for i in range(1, H + 1):
+            theta = x_[ns * (i - 1): ns * (i - 1) + nj]
+            for ob in obs_list:
+                for dv in chomp_dm(theta, robot, ob):
+                    if dv < 0:
+                        fobs += -dv + 0.5 * ob["epsilon"]
+                    elif dv <= ob["epsilon"]:
+                        fobs += (1.0 / (2 * ob["epsilon"])) * (dv - ob["epsilon"]) ** 2
+        cost_all.append(0.5 * u @ QQ @ u + ff @ u + caug + fobs)
+        e_u_all.append(np.linalg.norm(u_old - u))
+    return u, x_, np.array(cost_all), np.array(e_u_all)

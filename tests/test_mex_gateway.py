@@ -115,6 +115,29 @@ def test_gateway_matches_the_ctypes_path(harness, ctx, oracle):
     assert np.array_equal(out["u"], ref["u"]) and np.array_equal(out["status"], ref["status"])
 
 
+@pytest.mark.gpu
+def test_chomp_through_the_gateway(harness, oracle):
+    """cfs_mex('solve', 'CHOMP', 'derivest', ROBOT, obs, sys_info, uu) -- the call matlab/CHOMP_FANUC.m makes -- returns what the
+    ctypes path (cfs_chomp_batch) returns"""
+    H, K, B = 20, 6, 5
+    cfg = common.batch_m16ib(oracle, B, horizon=H, seed=3)
+    s = dict(cfg["sys_info"], MAX_O_ITER=K)
+    uu = 0.02 * np.random.default_rng(1).standard_normal((B, H * 5))
+    c = M.Context(0)
+    rb = dict(cfg["robot"])
+    rb["name"] = "M16iB"
+    c.set_robot(rb, 5)
+    c.set_obstacles(cfg["obs"])
+    c.set_cost(H, s["QQ"], s["lim"], s["MAX_input"])
+    ref = c.chomp_batch(cfg["x0"], cfg["ff"], cfg["caug"], cfg["xref"], uu, float(s["alpha"]), K)
+    out = call_mex(harness, "CHOMP", "derivest", "M16iB", cfg["robot"], cfg["obs"], s, cfg["x0"], cfg["ff"], cfg["caug"],
+                   cfg["xref"], noise=uu)
+    for k in ("u", "x", "cost_hist", "iters", "status"):
+        assert np.array_equal(out[k], ref[k]), k
+    with pytest.raises(RuntimeError, match="uu"):
+        call_mex(harness, "CHOMP", "derivest", "M16iB", cfg["robot"], cfg["obs"], s, cfg["x0"], cfg["ff"], cfg["caug"], cfg["xref"])
+
+
 def _robot_args(robot, nj):
     DH = np.asfortranarray(robot["DH"], dtype=np.float64)
     cap = np.asfortranarray(np.stack([np.asarray(robot["cap"][i]["p"], dtype=np.float64)[:, :2] for i in range(nj)], axis=2))
@@ -174,7 +197,7 @@ def test_gateway_validates_its_inputs(harness):
     ROBOT, robot, obs, s = common.main_fanuc_config()
     args = (s["xR"][:, 0][None], s["ff"][None], np.array([s["caug"]]), s["x_"][None])
     with pytest.raises(RuntimeError, match="cfs:arg.*unknown command"):
-        call_mex(harness, "CHOMP", "num_jac", ROBOT, robot, obs, s, *args)
+        call_mex(harness, "STOMP", "num_jac", ROBOT, robot, obs, s, *args)
     with pytest.raises(RuntimeError, match="cfs:arg.*grad"):
         call_mex(harness, "CFS", "hessian", ROBOT, robot, obs, s, *args)
     bad = dict(s)
