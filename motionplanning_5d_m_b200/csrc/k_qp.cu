@@ -123,7 +123,21 @@ __global__ void __launch_bounds__(QP_THREADS, 3) k_qp(SolveArgs a) {
       __syncthreads();
     }
     const int masked = skip_solve ? 0 : qp_mask_antiparallel<QP_THREADS>(s, dims);
-    const int status = qp_solve<QP_THREADS, QP_QS, true, 0>(s, dims, a.cost0[b], (has_bnd && a.fupper) ? a.fupper[b] : INFINITY, skip_solve, q, steps,
+    double fup = (has_bnd && a.fupper) ? a.fupper[b] : INFINITY;
+    if (psg && has_vel && !skip_solve) {
+      // Weak-duality bound for the projection (PSGCFS_FANUC.m:115-128 has no control bounds): the velocity rows alone confine
+      // every feasible u to |u_(i,k)| <= max(2 lim_k, lim_k + |w0_k|) / dt =: U_k (two consecutive velocities inside
+      // [-lim, lim]), so 1/2 ||u - u_||^2 <= 1/2 sum (U_k + |u__(i,k)|)^2 on the feasible set.  A dual value above it proves
+      // infeasibility -- long before the nearly dependent working set of an infeasible projection ruins the inverse.
+      double part = 0.0;
+      for (int c = tid; c < n; c += QP_THREADS) {
+        const int k = c % nj;
+        const double U = fmax(2.0 * s.lim[k], s.lim[k] + fabs(s.w0[k])) / dt + fabs(s.v0s[2 * n + c]);
+        part += U * U;
+      }
+      fup = a.cost0[b] + 0.5 * block_sum<QP_THREADS>(part, s.red) * (1.0 + 1e-9);
+    }
+    const int status = qp_solve<QP_THREADS, QP_QS, true, 0>(s, dims, a.cost0[b], fup, skip_solve, q, steps,
                                 qmax_seen, pf, tck, prof, 0x7fffffff, masked);
     steps_total += steps;
     if (tid == 0 && a.prob_steps) a.prob_steps[b] += steps;

@@ -694,6 +694,27 @@ __device__ __forceinline__ int qp_solve(const QpView &s, const QpDims &P, double
     }
     if (bidx < 0) {
       if (q == 0 || polished || (steps <= 6 && q <= 6)) {  // few updates: M is still accurate to ~1e-13
+        if (q > 6) {
+          // Safety net: every member of the working set must hold with equality at the recovered point.  On a nearly
+          // dependent working set (an infeasible QP on which neither the dependence test nor weak duality has fired yet)
+          // the rank-1 updated inverse can lose all accuracy; the scan above only looks at inactive rows and would
+          // accept the point.  Such a state is reported as numerical breakdown instead of a wrong "optimal".
+          double worst = 0.0;
+#pragma unroll 1
+          for (int w = tid; w < q; w += NT) {
+            const int cw = s.act[w];
+            const double rhs = cw < OH ? s.orhs[cw] : prim_rhs<NJ>((cw - OH) >> 1, (cw - OH) & 1, P, s);
+            const double res = fabs(slack_at<NJ>(cw, P, s, s.v)) / (1.0 + fabs(rhs));
+            worst = fmax(worst, res);
+          }
+          int wi = 0;
+          worst = -worst;
+          block_argmin<NT>(worst, wi, s.red);
+          if (-worst > 1e-6) {
+            status = 3;
+            break;
+          }
+        }
         status = 0;
         break;
       }
