@@ -502,7 +502,7 @@ def bench_solver(args, e):
         lat1.append(ctx0.stats()["ms_total"])
     iters = d_out[0]["iters"].cpu().numpy()
     status = d_out[0]["status"].cpu().numpy()
-    fused = stt["launches"] <= 8
+    fused = stt["launches"] <= 12
     fp64_tf, fp64_mhz = ctx0.measure_fp64_peak()
     f_wp = F_WAYPOINT_DERIVEST if args.grad == "derivest" else F_WAYPOINT_NUMJAC
     grad_flops = f_wp * stt["grad_waypoints"]

@@ -41,6 +41,9 @@ struct cfs_ctx {
   cudaStream_t own_stream = nullptr;  // created by cfs_create
   cudaStream_t heavy_stream = nullptr;  // highest priority: the heavy tier must not queue behind other contexts' bulk tiers
   cudaEvent_t ev_bulk = nullptr, ev_heavy = nullptr;
+#define CFS_MAX_SCREEN 3
+  cudaStream_t heavy_streams[CFS_MAX_SCREEN] = {nullptr, nullptr, nullptr};  // the heavy launches of the screening passes (= heavy_stream)
+  cudaEvent_t ev_pass[CFS_MAX_SCREEN] = {nullptr, nullptr, nullptr}, ev_hdone[CFS_MAX_SCREEN] = {nullptr, nullptr, nullptr};
   std::string err;
   // tables
   DevTables htab;
@@ -96,7 +99,7 @@ struct cfs_ctx {
   int use_warp_lockstep = 0;  // cfs_set_option("warp_lockstep"): launch-per-iteration path solves its QPs with k_qp_warp (measured: no gain --
                               // a lock-step iteration still waits for its slowest QP, and that one is slower on a single warp)
   int one_shot = 0;       // cfs_set_option("one_shot"): warp tier without a work queue, one problem per warp
-  int screen = 1;         // cfs_set_option("screen"): warp tier in two launches (iteration 1 | the rest), heavy tier starts after the first
+  int screen = 2;         // cfs_set_option("screen"): number of screening passes (0..3): outer iterations 1..screen of the warp tier in launches of their own, each followed by a heavy launch
   long long warp_key = -1;  // cache of the warp tier's launch configuration
   int warp_zs_pick = 0, warp_grid_pick = 0;
   int warp_qcap = 15;     // cfs_set_option("warp_qcap"): working-set rows the warp tier keeps (<= 31; inverse + directions spill to L2 beyond 16:
@@ -230,8 +233,15 @@ extern "C" int cfs_create(cfs_ctx **out, int device_id) {
     int lo = 0, hi = 0;
     cudaDeviceGetStreamPriorityRange(&lo, &hi);  // hi is the numerically lowest = highest priority
     if (cudaStreamCreateWithPriority(&ctx->heavy_stream, cudaStreamNonBlocking, hi) != cudaSuccess) ctx->heavy_stream = nullptr;
-    cudaEventCreateWithFlags(&ctx->ev_bulk, cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&ctx->ev_heavy, cudaEventDisableTiming);
+    cudaEventCreate(&ctx->ev_bulk);   // timing enabled: cfs_dev_timeline
+    cudaEventCreate(&ctx->ev_heavy);
+    ctx->heavy_streams[0] = ctx->heavy_stream;
+    for (int p = 0; p < CFS_MAX_SCREEN; ++p) {
+      ctx->heavy_streams[p] = ctx->heavy_stream;  // one heavy stream per context: streams beyond the device's hardware queues
+                                                  // (CUDA_DEVICE_MAX_CONNECTIONS <= 32) only buy false dependencies
+      cudaEventCreate(&ctx->ev_pass[p]);
+      cudaEventCreate(&ctx->ev_hdone[p]);
+    }
   }
   *out = ctx;
   return 0;
@@ -279,6 +289,10 @@ extern "C" void cfs_destroy(cfs_ctx *ctx) {
   if (ctx->heavy_stream) cudaStreamDestroy(ctx->heavy_stream);
   if (ctx->ev_bulk) cudaEventDestroy(ctx->ev_bulk);
   if (ctx->ev_heavy) cudaEventDestroy(ctx->ev_heavy);
+  for (int p = 0; p < CFS_MAX_SCREEN; ++p) {
+    if (ctx->ev_pass[p]) cudaEventDestroy(ctx->ev_pass[p]);
+    if (ctx->ev_hdone[p]) cudaEventDestroy(ctx->ev_hdone[p]);
+  }
   delete ctx;
 }
 
@@ -497,8 +511,8 @@ static int solve_device(cfs_ctx *ctx, int B, int solver, int grad, const double 
   if ((rc = ensure(ctx, ctx->flags, sizeof(int) * B))) return rc;
   if ((rc = ensure(ctx, ctx->listA, sizeof(int) * B))) return rc;
   if ((rc = ensure(ctx, ctx->listB, sizeof(int) * B))) return rc;
-  if ((rc = ensure(ctx, ctx->counters, sizeof(int) * 16))) return rc;
-  if ((rc = ensure(ctx, ctx->cont, sizeof(int) * 3 * (size_t)B))) return rc;
+  if ((rc = ensure(ctx, ctx->counters, sizeof(int) * 64))) return rc;
+  if ((rc = ensure(ctx, ctx->cont, sizeof(int) * 8 * (size_t)B))) return rc;
   if ((rc = ensure(ctx, ctx->qpsteps, sizeof(long long) * 32))) return rc;
 
   SolveArgs a;
@@ -599,7 +613,7 @@ static int solve_device(cfs_ctx *ctx, int B, int solver, int grad, const double 
   if (getenv("CFS_DEBUG")) fprintf(stderr, "[cfs] solve: B=%d fused=%d warp=%d cfg=%d zs=%d grid=%d grid_heavy=%d\n", B, (int)fused, (int)warp, ctx->warp_cfg, a.warp_zs, grid, grid_heavy);
   // spill slabs of the working-set inverse: the warp tier has its own (zslab); the CTA tiers need n x n per CTA, and the two
   // heavy launches of the screened pipeline can overlap, so they get disjoint halves
-  const int slab_ctas = fused ? ((warp ? 0 : grid) > 2 * grid_heavy ? grid : 2 * grid_heavy) : grid;
+  const int slab_ctas = fused ? ((warp ? 0 : grid) > (1 + CFS_MAX_SCREEN) * grid_heavy ? grid : (1 + CFS_MAX_SCREEN) * grid_heavy) : grid;
   if ((rc = ensure(ctx, ctx->slab, sizeof(double) * (size_t)n * n * slab_ctas))) return rc;
   a.slab = ptr<double>(ctx->slab);
 
@@ -612,13 +626,16 @@ static int solve_device(cfs_ctx *ctx, int B, int solver, int grad, const double 
   }
   int launches = 0;
   CU(cudaEventRecord(ctx->ev_a, st));
-  CU(cudaMemsetAsync(cnt, 0, sizeof(int) * 16, st));
+  CU(cudaMemsetAsync(cnt, 0, sizeof(int) * 64, st));
   CU(cudaMemsetAsync(ctx->qpsteps.p, 0, sizeof(long long) * 32, st));
   CU(cudaMemsetAsync(ctx->probsteps.p, 0, sizeof(int) * B, st));
   a.list_cur = ptr<int>(ctx->listA); a.count_cur = cnt + 0;
   a.list_next = ptr<int>(ctx->listB); a.count_next = cnt + 1;
   a.work_counter = cnt + 2;
   if (fused) {
+    NvtxRange nvtx_solve("cfs:fused solve (screen | bulk | heavy)");
+    const bool screen = warp && ctx->screen && !ctx->heavy_skip;
+    const bool side = ctx->heavy_stream && ctx->heavy_prio && !detail;  // heavy tier on its own highest-priority stream
     // one persistent kernel: every CTA carries a problem through all its outer iterations (k_fused.cu)
     CU(launch_dgemm(n, B, n, -1.0, ctx->dG + (size_t)2 * n * np + 2 * n, np, false, ff, n, a.u0, n, st)); ++launches;
     CU(launch_v0(a, st)); ++launches;
@@ -631,38 +648,52 @@ static int solve_device(cfs_ctx *ctx, int B, int solver, int grad, const double 
       launches += 2;
       a.order = ptr<int>(ctx->listB);
     }
-    NvtxRange nvtx_solve("cfs:fused solve (screen | bulk | heavy)");
-    const bool screen = warp && ctx->screen && !ctx->heavy_skip;
-    const bool side = ctx->heavy_stream && ctx->heavy_prio && !detail;  // heavy tier on its own highest-priority stream
     if (detail) CU(cudaEventRecord(ctx->ev[0], st));
     if (screen) {
-      // Screening pass: outer iteration 1 of every problem.  The long dual chains (almost all of them infeasibility
-      // certificates of the FIRST linearisation) reach the heavy tier ~0.3 ms into the batch and run concurrently with the
-      // rest of the bulk tier instead of after it; everything unfinished continues from iteration 2 in the second launch.
-      SolveArgs a1 = a, a2 = a;
+      // Screening passes: outer iteration 1 (then 2, ... for ctx->screen > 1) of every problem in a launch of its own.  The long
+      // dual chains (almost all of them infeasibility certificates of an early linearisation) reach the heavy tier a fraction
+      // of a millisecond into the batch and run -- each pass's escalations on their own highest-priority stream -- concurrently
+      // with the rest of the work instead of after it; everything unfinished continues in the next launch.
+      //   lists in ctx->cont (B ints each): [0] cont A, [1] cont B, [2] touch flags, [3 + p] escalations of pass p
+      //   counters: cnt[16 + 4 p + {0,1,2,3}] = cont count, work queue, escalation count, heavy work queue of pass p
       int *ext = ptr<int>(ctx->cont);
-      a1.phase = 1;
-      a1.cont_list = a2.cont_list = ext;
-      a1.touch = a2.touch = ext + B;
-      a1.cont_count = a2.cont_count = cnt + 6;
-      CU(launch_warp(a1, grid, ctx->warp_cfg, st)); ++launches;
-      a2.phase = 2;
-      a2.work_counter = cnt + 7;
-      a2.esc_list = ext + 2 * (size_t)B;  // late escalations (working sets that outgrow the warp tier in later iterations)
-      a2.esc_count = cnt + 8;
-      a2.work_counter2 = cnt + 9;
-      a2.slab = a.slab + (size_t)n * n * grid_heavy;
-      if (side) {
-        CU(cudaEventRecord(ctx->ev_bulk, st));
-        CU(cudaStreamWaitEvent(ctx->heavy_stream, ctx->ev_bulk, 0));
-        CU(launch_fused(a1, grid_heavy, heavy_tier, ctx->heavy_stream)); ++launches;
-        CU(cudaEventRecord(ctx->ev_heavy, ctx->heavy_stream));
+      const int npass = ctx->screen > CFS_MAX_SCREEN ? CFS_MAX_SCREEN : ctx->screen;
+      const size_t slab_h = (size_t)n * n;
+      SolveArgs ap = a;
+      ap.touch = ext + 2 * (size_t)B;
+      int heavy_launches = 0;
+      SolveArgs heavy_args[CFS_MAX_SCREEN + 1];
+      bool on_side[CFS_MAX_SCREEN + 1] = {false, false, false, false};
+      for (int p = 0; p <= npass; ++p) {  // p < npass: screening pass of iteration p + 1; p == npass: the rest
+        int *c4 = cnt + 16 + 4 * p;
+        ap.phase = p == 0 ? 1 : 2;
+        ap.it_stop = p < npass ? p + 1 : 0;
+        ap.cont_list = ext + (size_t)((p + 1) & 1) * B;   // written by the previous pass
+        ap.cont_count = p ? cnt + 16 + 4 * (p - 1) : nullptr;
+        ap.cont_out = ext + (size_t)(p & 1) * B;
+        ap.cont_out_count = c4;
+        ap.work_counter = c4 + 1;
+        ap.esc_list = ext + (3 + (size_t)p) * B;
+        ap.esc_count = c4 + 2;
+        ap.work_counter2 = c4 + 3;
+        CU(launch_warp(ap, grid, ctx->warp_cfg, st)); ++launches;
+        if (detail && p == npass) CU(cudaEventRecord(ctx->ev[1], st));
+        heavy_args[p] = ap;  // heavy tier over this pass's escalation list; disjoint spill slabs (the launches can overlap)
+        heavy_args[p].slab = a.slab + slab_h * (size_t)(p == 0 ? 0 : grid_heavy + (p - 1) * grid_heavy2);
+        cudaStream_t hs = (side && p < npass) ? ctx->heavy_streams[p] : nullptr;
+        if (hs) {
+          CU(cudaEventRecord(ctx->ev_pass[p], st));
+          CU(cudaStreamWaitEvent(hs, ctx->ev_pass[p], 0));
+          CU(launch_fused(heavy_args[p], p == 0 ? grid_heavy : grid_heavy2, heavy_tier, hs)); ++launches;
+          CU(cudaEventRecord(ctx->ev_hdone[p], hs));
+          on_side[p] = true;
+          ++heavy_launches;
+        }
       }
-      CU(launch_warp(a2, grid, ctx->warp_cfg, st)); ++launches;
-      if (detail) CU(cudaEventRecord(ctx->ev[1], st));
-      if (!side) { CU(launch_fused(a1, grid_heavy, heavy_tier, st)); ++launches; }
-      CU(launch_fused(a2, grid_heavy2, heavy_tier, st)); ++launches;
-      if (side) CU(cudaStreamWaitEvent(st, ctx->ev_heavy, 0));
+      for (int p = 0; p <= npass; ++p)  // the last pass's escalations (and, without side streams, all of them) follow the warp tier
+        if (!on_side[p]) { CU(launch_fused(heavy_args[p], p == 0 ? grid_heavy : grid_heavy2, heavy_tier, st)); ++launches; }
+      for (int p = 0; p < npass; ++p)
+        if (on_side[p]) CU(cudaStreamWaitEvent(st, ctx->ev_hdone[p], 0));
     } else {
       CU(warp ? launch_warp(a, grid, ctx->warp_cfg, st) : launch_fused(a, grid, 0, st)); ++launches;  // bulk tier: every problem
       if (detail) CU(cudaEventRecord(ctx->ev[1], st));
@@ -767,7 +798,7 @@ static int solve_device(cfs_ctx *ctx, int B, int solver, int grad, const double 
 static int collect_stats(cfs_ctx *ctx, int B, int max_outer, const int *d_iters, const int *d_status) {
   cudaStream_t st = ctx->stream;
   long long steps[2] = {0, 0};
-  int cnt[16] = {0};
+  int cnt[64] = {0};
   std::vector<int> it(B), stt(B);
   CU(cudaMemcpyAsync(stt.data(), d_status, sizeof(int) * B, cudaMemcpyDeviceToHost, st));
   CU(cudaMemcpyAsync(steps, ctx->qpsteps.p, sizeof(steps), cudaMemcpyDeviceToHost, st));
@@ -780,8 +811,8 @@ static int collect_stats(cfs_ctx *ctx, int B, int max_outer, const int *d_iters,
   ctx->stats.qp_steps = steps[0];
   ctx->stats.max_active = cnt[3];
   if (getenv("CFS_DEBUG"))
-    fprintf(stderr, "[cfs] batch done: escalated after the screening pass %d, late escalations %d, continued past iteration 1: %d\n", cnt[5],
-            cnt[8], cnt[6]);
+    fprintf(stderr, "[cfs] batch done: escalations per launch %d %d %d %d, continued after each screening pass %d %d %d\n", cnt[18], cnt[22],
+            cnt[26], cnt[30], cnt[16], cnt[20], cnt[24]);
   long long pit = 0, gev = 0;
   for (int b = 0; b < B; ++b) {
     pit += it[b];
@@ -1280,6 +1311,20 @@ extern "C" int cfs_chomp_batch(cfs_ctx *ctx, int B, const double *x0, const doub
   cudaEventElapsedTime(&ms, ctx->ev_a, ctx->ev_b);
   ctx->stats.ms_total = ms;
   ctx->stats.launches = launches;
+  return 0;
+}
+
+// Development aid (dev/timeline.py; not part of include/cfs_b200.h): where the stages of the last fused solve of `ctx` fell on the
+// device's time axis, in ms after the START of the last solve of `ref` (another context of the same device):
+// out = {solve enqueued work starts, screening launch done, heavy launch #1 done, everything done}.  Call after cfs_wait.
+extern "C" int cfs_dev_timeline(cfs_ctx *ctx, cfs_ctx *ref, double *out4) {
+  if (!ctx || !ref || !out4) return CFS_E_ARG;
+  cudaEvent_t ev[4] = {ctx->ev_a, ctx->ev_pass[0], ctx->ev_hdone[0], ctx->ev_b};
+  for (int k = 0; k < 4; ++k) {
+    float ms = 0;
+    out4[k] = (ev[k] && cudaEventElapsedTime(&ms, ref->ev_a, ev[k]) == cudaSuccess) ? ms : -1.0;
+  }
+  cudaGetLastError();
   return 0;
 }
 

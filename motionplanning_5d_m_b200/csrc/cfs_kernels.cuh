@@ -146,6 +146,11 @@ struct SolveArgs {
   int one_shot;               // warp tier: grid = one warp per problem, no work queue (CTAs leave the SM after one problem)
   int *cont_list, *cont_count;
   int *touch;                 // B: CFS_FLAG_TOUCH of the problems in cont_list
+  // a launch with it_stop > 0 stops every problem after outer iteration it_stop and appends the unfinished ones to cont_out
+  // (screening passes: the long dual chains of the early iterations reach the heavy tier while the bulk of the work is
+  // still ahead); it_stop = 0: run to the stop rule
+  int it_stop;
+  int *cont_out, *cont_out_count;
 };
 cudaError_t launch_solve_init(const SolveArgs &a, cudaStream_t s);
 cudaError_t launch_v0(const SolveArgs &a, cudaStream_t s);

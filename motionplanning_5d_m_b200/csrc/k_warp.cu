@@ -334,7 +334,7 @@ __global__ void __launch_bounds__(NT) __maxnreg__(MAXREG) k_cfs_warp(SolveArgs a
       else if (it + 1 > a.max_outer)
         status = 1;  // MAX_ITER (EVAL.m:69-72)
       __syncwarp();
-      if (a.phase == 1) break;  // screening pass: one outer iteration
+      if (a.it_stop && it >= a.it_stop) break;  // screening pass: the problem continues in a later launch
     }
 
     // ---- results: u and x_ of the last completed iteration are already in global memory ----
@@ -342,9 +342,9 @@ __global__ void __launch_bounds__(NT) __maxnreg__(MAXREG) k_cfs_warp(SolveArgs a
     if (lane == 0) {
       a.iters[b] = iters;
       if (a.prob_steps) a.prob_steps[b] = steps_prob;
-      if (status < 0) {  // screening pass: the problem continues in phase 2
+      if (status < 0) {  // screening pass: the problem continues in the next launch
         a.touch[b] = any_touch ? 0x100 : 0;
-        a.cont_list[atomicAdd(a.cont_count, 1)] = b;
+        a.cont_out[atomicAdd(a.cont_out_count, 1)] = b;
       } else {
         a.status[b] = status | (any_touch ? 0x100 : 0);
         if (status == 4) a.esc_list[atomicAdd(a.esc_count, 1)] = b;

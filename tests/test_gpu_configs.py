@@ -206,7 +206,10 @@ def test_headline_batch_full_size_against_oracle(ctx, oracle):
     it = ref["iters"]
     sel = well & (it > 0)
     cg, cr = out["cost_hist"][sel, it[sel] - 1], ref["cost_hist"][sel, it[sel] - 1]
-    assert np.all(np.abs(cg - cr) <= 1e-6 * np.abs(cr))@pytest.mark.gpu
+    assert np.all(np.abs(cg - cr) <= 1e-6 * np.abs(cr))
+
+
+@pytest.mark.gpu
 def test_psgcfs_bench_batch_status_and_iterations_equal(ctx, oracle):
     """The 2048-problem PSGCFS batch bench.py --config psgcfs times (M200i, H = 30): status and iteration count of EVERY problem
     equal to the oracle's.  Regression test: 158 of these projections are infeasible (confirmed with an LP on the oracle's dense
