@@ -591,6 +591,142 @@ static __device__ __noinline__ void qp_polish(const QpView &s, const QpDims &P, 
   __syncthreads();
 }
 
+// Re-factorisation of the working set (G-based tiers): the inverse M of S_W = C_W QQ^-1 C_W' is rebuilt from the Gram operator
+// instead of trusted after many rank-1 updates.  Rows that depend on the rows before them (remaining pivot below QP_DEP_TOL of
+// their own norm) and rows whose multiplier comes out non-positive leave the set, and the factorisation is repeated on the
+// smaller set: what remains has independent rows, positive multipliers lambda = S_W^-1 b (b = violation at the unconstrained
+// minimiser) and u(lambda) stationary on it -- a valid state of the dual method, from which qp_solve continues.  Called when
+// the working-set residual check finds the updated inverse broken (typically a nearly dependent set on an infeasible QP).
+// Returns the new size of the working set, or -1 if no consistent set was reached.
+template <int NT, int QS, int NJ>
+static __device__ __noinline__ int qp_refactor(const QpView &s, const QpDims &P, int q0, double cost0, bool &in_smem,
+                                               double *fval_new) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int NW = NT / 32;
+  if (q0 > NT || q0 > P.ldg) return -1;  // the column scratch (pscr) holds NT entries
+  int qc = q0;
+  double *A = nullptr;
+  int ld = 0;
+  for (int pass = 0;; ++pass) {
+    A = qc <= QS ? s.Msm : P.Mgl;
+    ld = qc <= QS ? QS : P.ldg;
+#pragma unroll 1
+    for (int idx = tid; idx < qc * qc; idx += NT) {  // S_W, lower triangle
+      const int j = idx / qc, i = idx - j * qc;
+      if (i >= j) A[i + (size_t)ld * j] = gram(s.act[i], s.act[j], P, s.ocoef);
+    }
+#pragma unroll 1
+    for (int i = tid; i < qc; i += NT) s.g[i] = -slack_at<NJ>(s.act[i], P, s, s.v0s);
+    __syncthreads();
+#pragma unroll 1
+    for (int i = tid; i < qc; i += NT) {
+      s.r[i] = A[i + (size_t)ld * i];
+      s.toff[i] = 0;  // "left the set" flags (the term lists are rebuilt below)
+    }
+    __syncthreads();
+    // in-place inverse of the symmetric positive definite matrix by sweeping every row (lower triangle only): afterwards
+    // A = -(S^-1) on the swept rows; a dependent row is taken out (zero row and column)
+#pragma unroll 1
+    for (int k = 0; k < qc; ++k) {
+      const double pv = A[k + (size_t)ld * k];
+      const bool dep = !(pv > QP_DEP_TOL * s.r[k]);
+#pragma unroll 1
+      for (int i = tid; i < qc; i += NT) s.pscr[i] = dep ? 0.0 : (i >= k ? A[i + (size_t)ld * k] : A[k + (size_t)ld * i]);
+      __syncthreads();
+      if (dep) {
+#pragma unroll 1
+        for (int i = tid; i < qc; i += NT) {
+          if (i >= k) A[i + (size_t)ld * k] = 0.0;
+          else A[k + (size_t)ld * i] = 0.0;
+        }
+        if (tid == 0) s.toff[k] = 1;
+        __syncthreads();
+        continue;
+      }
+      const double ip = 1.0 / pv;
+#pragma unroll 1
+      for (int j = warp; j < qc; j += NW) {
+        if (j == k) continue;
+        const double cj = s.pscr[j] * ip;
+#pragma unroll 4
+        for (int i = j + lane; i < qc; i += 32)
+          if (i != k) A[i + (size_t)ld * j] -= s.pscr[i] * cj;
+      }
+#pragma unroll 1
+      for (int i = tid; i < qc; i += NT) {
+        if (i > k) A[i + (size_t)ld * k] = s.pscr[i] * ip;
+        else if (i < k) A[k + (size_t)ld * i] = s.pscr[i] * ip;
+        else A[k + (size_t)ld * k] = -ip;
+      }
+      __syncthreads();
+    }
+    int bad = 0;
+#pragma unroll 1
+    for (int i = tid; i < qc; i += NT) {  // lambda = S^-1 b
+      double acc = 0.0;
+#pragma unroll 4
+      for (int j = 0; j < qc; ++j) acc += (i >= j ? A[i + (size_t)ld * j] : A[j + (size_t)ld * i]) * s.g[j];
+      s.lam[i] = -acc;
+      if (s.toff[i] || !(-acc > 0.0)) ++bad;
+    }
+    __syncthreads();
+    const int nbad = (int)(block_sum<NT>((double)bad, s.red) + 0.5);
+    if (nbad == 0) break;
+    if (pass >= 5) return -1;
+    if (tid == 0) {  // take the rows out (a few hundred entries at most: one thread, fixed order)
+      int o = 0;
+      for (int i = 0; i < qc; ++i) {
+        if (s.toff[i] || !(s.lam[i] > 0.0)) {
+          s.inact[s.act[i]] = 0;
+        } else {
+          s.act[o++] = s.act[i];
+        }
+      }
+    }
+    qc -= nbad;
+    __syncthreads();
+    if (qc <= 0) {
+      qc = 0;
+      break;
+    }
+  }
+  // M = S^-1, both triangles
+#pragma unroll 1
+  for (int j = warp; j < qc; j += NW)
+#pragma unroll 1
+    for (int i = j + lane; i < qc; i += 32) {
+      const double val = -A[i + (size_t)ld * j];
+      A[i + (size_t)ld * j] = val;
+      A[j + (size_t)ld * i] = val;
+    }
+  if (tid == 0) {
+    int o = 0;
+    for (int w = 0; w < qc; ++w) {
+      s.toff[w] = o;
+      o += (s.act[w] < P.OH) ? P.nj : 1;
+    }
+    s.toff[qc] = o;
+  }
+  __syncthreads();
+#pragma unroll 1
+  for (int w = tid; w < qc; w += NT) {
+    const Desc d = decode(s.act[w], P, s.ocoef);
+    const int t0 = s.toff[w];
+    for (int k = 0; k < d.nterm; ++k) {
+      s.trow[t0 + k] = d.row0 + k;
+      s.tcoef[t0 + k] = d.cv ? d.cv[k] : d.coef;
+      s.towner[t0 + k] = w;
+    }
+  }
+  double part = 0.0;
+#pragma unroll 1
+  for (int w = tid; w < qc; w += NT) part += s.g[w] * s.lam[w];
+  *fval_new = cost0 + 0.5 * block_sum<NT>(part, s.red);  // (also orders the writes above)
+  in_smem = qc <= QS;
+  __syncthreads();
+  return qc;
+}
+
 // Solves   min 1/2 u'QQ u + ff'u  s.t. the rows described by (s.ocoef, s.orhs, lim, umax)   starting from the
 // unconstrained minimiser whose primitives are in s.v0s / s.v.  On return (status 0) s.v holds the primitives of the
 // optimum (controls in s.v[2n..3n)), s.lam / s.act / q the multipliers and the working set.
@@ -607,6 +743,7 @@ __device__ __forceinline__ int qp_solve(const QpView &s, const QpDims &P, double
   constexpr bool CACHED = QZ > 0;
   int q = 0, status = skip_solve ? 0 : -1, steps = 0;
   bool in_smem = true, polished = false;
+  int refactors = 0;
   if (CACHED) {
     if (tid <= QZ) s.zslot[tid] = tid;
     __syncthreads();
@@ -711,8 +848,27 @@ __device__ __forceinline__ int qp_solve(const QpView &s, const QpDims &P, double
           worst = -worst;
           block_argmin<NT>(worst, wi, s.red);
           if (-worst > 1e-6) {
-            status = 3;
-            break;
+            // broken inverse: rebuild it from the Gram operator (twice at most per QP), drop what does not belong to a valid
+            // working set, and continue; the cached tiers (small working sets, no term lists) report the breakdown
+            int q1 = -1;
+            double fnew = fval;
+            if (!CACHED && refactors < 2) {
+              ++refactors;
+              q1 = qp_refactor<NT, QS, NJ>(s, P, q, cost0, in_smem, &fnew);
+              ++steps;
+            }
+            if (q1 < 0) {
+              status = 3;
+              break;
+            }
+            q = q1;
+            fval = fnew;
+            polished = false;
+            if (fval > fupper) {
+              status = 2;
+              break;
+            }
+            continue;
           }
         }
         status = 0;
@@ -754,10 +910,33 @@ __device__ __forceinline__ int qp_solve(const QpView &s, const QpDims &P, double
         status = 4;
         break;
       }
-      // g_w = c_w QQ^-1 c_p'
+      // g_w = c_w QQ^-1 c_p' = sum over the member's terms of coef_t * (G[row_t, :] . c_p): one thread per TERM (<= nj
+      // independent L2 loads each) instead of one per member (up to nj x nj dependent ones), then a fixed-order sum per member.
+      // twgt is free between two refreshes.
       if (!CACHED) {
+        const Desc dp = decode(p, P, s.ocoef);
+        const int T = s.toff[q];
 #pragma unroll 1
-        for (int w = tid; w < q; w += NT) s.g[w] = gram(s.act[w], p, P, s.ocoef);
+        for (int t = tid; t < T; t += NT) {
+          const double *__restrict__ Gr = P.G + (size_t)s.trow[t] * P.np + dp.row0;
+          double acc;
+          if (dp.nterm == 1) {
+            acc = dp.coef * Gr[0];
+          } else {
+            acc = 0.0;
+#pragma unroll 6
+            for (int l2 = 0; l2 < dp.nterm; ++l2) acc += dp.cv[l2] * Gr[l2];
+          }
+          s.twgt[t] = s.tcoef[t] * acc;
+        }
+        __syncthreads();
+#pragma unroll 1
+        for (int w = tid; w < q; w += NT) {
+          double acc = 0.0;
+#pragma unroll 1
+          for (int t = s.toff[w]; t < s.toff[w + 1]; ++t) acc += s.twgt[t];
+          s.g[w] = acc;
+        }
         __syncthreads();
       }
       // r = Minv g ;  delta = sigma - g'r  (z'n+ in Goldfarb-Idnani's notation) ; t1 = largest dual step keeping lambda >= 0
