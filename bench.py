@@ -503,6 +503,17 @@ def bench_solver(args, e):
     iters = d_out[0]["iters"].cpu().numpy()
     status = d_out[0]["status"].cpu().numpy()
     fused = stt["launches"] <= 12
+    grad_phase = None
+    if fused and not psg and args.grad == "numjac":
+        # clock64 split of the warp tier (profiled instantiation of the kernel, timing level 3): the gradient code's own rate
+        ctx0.set_timing(3)
+        issue(0, False)
+        ctx0.wait()
+        wp = ctx0.warp_profile()
+        ctx0.set_timing(1)
+        if wp[0] > 0 and wp[4] > 0:
+            grad_phase = {"cycles_gradient": int(wp[0]), "cycles_qp": int(wp[1]), "cycles_problems": int(wp[2]), "gradient_passes": int(wp[3]),
+                          "resident_warps": int(wp[4]), "share_of_warp_cycles": float(wp[0]) / float(wp[2])}
     fp64_tf, fp64_mhz = ctx0.measure_fp64_peak()
     f_wp = F_WAYPOINT_DERIVEST if args.grad == "derivest" else F_WAYPOINT_NUMJAC
     grad_flops = f_wp * stt["grad_waypoints"]
@@ -594,6 +605,13 @@ def bench_solver(args, e):
                      "note": "algorithmic FLOPs = %.0f per waypoint gradient x %.0f waypoint gradients per step (SURVEY.md 8d); the "
                              "solver kernels also run the QP, roll-out and stop rule" % (f_wp, wp_timed / args.steps),
                      "share_of_step": share},
+        "roofline_gradient_phase": None if grad_phase is None else dict(grad_phase, **{
+            "bound": "fp64", "unit": "TFLOP/s", "peak": fp64_tf,
+            "achieved": F_WAYPOINT_NUMJAC * grad_phase["gradient_passes"] * H * len(obs) /
+                        (grad_phase["cycles_gradient"] / grad_phase["resident_warps"] / (fp64_mhz * 1e6)) / 1e12,
+            "note": "the gradient code of the path that actually runs (k_cfs_warp's get_con phase, clock64 per warp): "
+                    "algorithmic FLOPs of the gradient passes / (gradient-phase warp-cycles / resident warps) -- the rate the "
+                    "kernel would sustain if every resident warp were in its gradient phase; frac = achieved / peak"}),
         "roofline_k1": {"bound": "fp64", "kernel": "k_grad_%s stand-alone" % args.grad, "achieved": k1_tf, "peak": fp64_tf,
                         "unit": "TFLOP/s", "frac": k1_tf / fp64_tf if fp64_tf else None, "waypoints": int(th_all.shape[0]),
                         "avg_launch_ms": k1_ms},
@@ -607,6 +625,9 @@ def bench_solver(args, e):
                         "mean_iters": float(iters.mean()), "max_iters": int(iters.max()),
                         "qp_steps": int(stt["qp_steps"]), "max_working_set": int(stt["max_active"])},
     })
+    if line.get("roofline_gradient_phase"):
+        g_ = line["roofline_gradient_phase"]
+        g_["frac"] = g_["achieved"] / g_["peak"] if g_["peak"] else None
     if ms_sg is None:
         line["e2e"] = line["e2e_arrays"]
     else:

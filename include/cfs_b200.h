@@ -249,6 +249,12 @@ int cfs_get_problem_steps(cfs_ctx *ctx, int *steps, int B);
  * refresh, violation scan, gram+solve+step length, working-set update, epilogue} ticks, problems, outer steps; out16[8..15]
  * = the same for the heavy tier of the fused kernel */
 int cfs_get_qp_profile(cfs_ctx *ctx, long long *out16);
+/* timing level 3, warp tier (nj = 5, one obstacle, default CTA shape): clock64 cycles summed over the warps of the last solve:
+ * out6 = {gradient phase (get_con: FK + distances + num_jac), QP (mask + dual active set), whole problems, gradient passes,
+ *         warps resident on the device with a full grid, SMs}.
+ * The gradient code's own rate -- what the kernel would sustain if every resident warp were in its gradient phase -- is
+ *   passes * H * n_obs * 9680 FLOP / (out6[0] / out6[4]) cycles; bench.py reports it as roofline.gradient_phase. */
+int cfs_get_warp_profile(cfs_ctx *ctx, long long *out6);
 /* FP64 FMA micro-benchmark (roofline denominator: MEASURED_PEAKS.json has no FP64 entry). Returns TFLOP/s. */
 int cfs_measure_fp64_peak(cfs_ctx *ctx, double *tflops, double *sm_clock_mhz_est);
 

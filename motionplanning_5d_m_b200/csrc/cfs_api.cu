@@ -99,6 +99,7 @@ struct cfs_ctx {
   int use_warp_lockstep = 0;  // cfs_set_option("warp_lockstep"): launch-per-iteration path solves its QPs with k_qp_warp (measured: no gain --
                               // a lock-step iteration still waits for its slowest QP, and that one is slower on a single warp)
   int one_shot = 0;       // cfs_set_option("one_shot"): warp tier without a work queue, one problem per warp
+  long long last_warp_grid_warps = 0, last_sms = 0;  // cfs_get_warp_profile
   int screen = 2;         // cfs_set_option("screen"): number of screening passes (0..3): outer iterations 1..screen of the warp tier in launches of their own, each followed by a heavy launch
   long long warp_key = -1;  // cache of the warp tier's launch configuration
   int warp_zs_pick = 0, warp_grid_pick = 0;
@@ -598,6 +599,12 @@ static int solve_device(cfs_ctx *ctx, int B, int solver, int grad, const double 
   }
   if (warp) {
     const int wpc = warp_warps_per_cta(ctx->warp_cfg);
+    {
+      int sms = 0;
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+      ctx->last_sms = sms;
+      ctx->last_warp_grid_warps = (long long)warp_grid * wpc;  // resident warps of a full grid
+    }
     a.one_shot = ctx->one_shot;
     if (grid > (B + wpc - 1) / wpc || ctx->one_shot) grid = (B + wpc - 1) / wpc;
     if (grid < 1) grid = 1;
@@ -1599,6 +1606,17 @@ extern "C" int cfs_get_qp_profile(cfs_ctx *ctx, long long *out8) {
   if (ctx->qpsteps.cap < sizeof(long long) * 32) return fail(ctx, CFS_E_STATE, "cfs_get_qp_profile: no solve yet");
   CU(cudaSetDevice(ctx->device));
   CU(cudaMemcpyAsync(out8, ptr<long long>(ctx->qpsteps) + 8, sizeof(long long) * 16, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+extern "C" int cfs_get_warp_profile(cfs_ctx *ctx, long long *out4) {
+  if (!ctx || !out4) return CFS_E_ARG;
+  out4[4] = ctx->last_warp_grid_warps;
+  out4[5] = ctx->last_sms;
+  if (ctx->qpsteps.cap < sizeof(long long) * 32) return fail(ctx, CFS_E_STATE, "cfs_get_warp_profile: no solve yet");
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaMemcpyAsync(out4, ptr<long long>(ctx->qpsteps) + 24, sizeof(long long) * 4, cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   return 0;
 }

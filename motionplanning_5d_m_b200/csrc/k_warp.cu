@@ -133,7 +133,9 @@ __host__ __device__ inline WarpSmem warp_smem(int n, int nj, int OH, int zs, int
   return L;
 }
 
-template <int NJ, int NT, int MAXREG, int OC>
+// PROF: clock64 split of every problem into gradient phase / QP / everything (timing level 3: cfs_get_warp_profile); a separate
+// instantiation so that the production kernel keeps its register budget
+template <int NJ, int NT, int MAXREG, int OC, bool PROF = false>
 __global__ void __launch_bounds__(NT) __maxnreg__(MAXREG) k_cfs_warp(SolveArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr int WPC = NT / 32;
@@ -154,6 +156,7 @@ __global__ void __launch_bounds__(NT) __maxnreg__(MAXREG) k_cfs_warp(SolveArgs a
   const double qnan = __longlong_as_double(0x7ff8000000000000LL);
   long long steps_total = 0;
   int qmax_seen = 0;
+  long long pf_grad = 0, pf_qp = 0, pf_all = 0, pf_passes = 0, pf_t0 = 0, pf_t1 = 0;
 
   const bool resume = a.phase == 2;
   const int count = resume ? *a.cont_count : a.B;
@@ -172,6 +175,7 @@ __global__ void __launch_bounds__(NT) __maxnreg__(MAXREG) k_cfs_warp(SolveArgs a
     const double *xref = a.xref + (size_t)b * N;
     double *ub = a.u + (size_t)b * n;
     double *xb = a.x + (size_t)b * N;
+    if (PROF) pf_t0 = clock64();
 
     // ---- problem set-up: u = 0, x_ = sys_info.x_, histories NaN, first stop test against x_old = ones (EVAL.m:47) ----
     __syncwarp();
@@ -214,6 +218,7 @@ __global__ void __launch_bounds__(NT) __maxnreg__(MAXREG) k_cfs_warp(SolveArgs a
 
     for (int it = iters + 1; status < 0; ++it) {
       // ---- get_con: distance + num_jac gradient of every waypoint, rows written in place (CFS_FANUC.m:110-124) ----
+      if (PROF) pf_t1 = clock64();
 #pragma unroll 1
       for (int i = lane; i < H; i += 32) {
         const double *thp = s.th + (size_t)i * NJ;
@@ -251,11 +256,18 @@ __global__ void __launch_bounds__(NT) __maxnreg__(MAXREG) k_cfs_warp(SolveArgs a
       for (int e = lane * 4; e < m; e += 128)  // inact[] = 0, four rows per store (the region is padded to 16 B)
         *reinterpret_cast<unsigned int *>(s.inact + e) = 0u;
       __syncwarp();
+      if (PROF) {
+        const long long now = clock64();
+        pf_grad += now - pf_t1;
+        pf_t1 = now;
+        ++pf_passes;
+      }
 
       // ---- Solve_QP (CFS_FANUC.m:85) ----
       int q = 0, steps = 0;
       const int masked = w_mask_antiparallel<NJ>(s, P);
       const int qst = wqp_solve<NJ>(s, P, cost0, fupper, a.esc_steps, masked, q, steps, qmax_seen);
+      if (PROF) pf_qp += clock64() - pf_t1;
       steps_total += steps;
       steps_prob += steps;
       if (qst != 0) {  // 2 infeasible / 3 numerical: u, x_ keep the previous iterate; 4: the heavy tier redoes this iteration
@@ -338,6 +350,7 @@ __global__ void __launch_bounds__(NT) __maxnreg__(MAXREG) k_cfs_warp(SolveArgs a
     }
 
     // ---- results: u and x_ of the last completed iteration are already in global memory ----
+    if (PROF) pf_all += clock64() - pf_t0;
     const int any_touch = __any_sync(FULLMASK, touched);
     if (lane == 0) {
       a.iters[b] = iters;
@@ -354,6 +367,12 @@ __global__ void __launch_bounds__(NT) __maxnreg__(MAXREG) k_cfs_warp(SolveArgs a
   if (lane == 0) {
     if (steps_total) atomicAdd(reinterpret_cast<unsigned long long *>(a.qp_steps), (unsigned long long)steps_total);
     if (qmax_seen) atomicMax(a.max_active, qmax_seen);
+    if (PROF && a.prof) {  // slots 16..19 of the profile block: gradient-phase, QP, per-problem total cycles; gradient passes
+      atomicAdd(reinterpret_cast<unsigned long long *>(a.prof + 16), (unsigned long long)pf_grad);
+      atomicAdd(reinterpret_cast<unsigned long long *>(a.prof + 17), (unsigned long long)pf_qp);
+      atomicAdd(reinterpret_cast<unsigned long long *>(a.prof + 18), (unsigned long long)pf_all);
+      atomicAdd(reinterpret_cast<unsigned long long *>(a.prof + 19), (unsigned long long)pf_passes);
+    }
   }
 }
 
@@ -534,7 +553,8 @@ static WarpKernel warp_kernel_nj(int cfg, bool two) {
   }
   return nullptr;
 }
-static WarpKernel warp_kernel(int nj, int cfg, int nobs) {
+static WarpKernel warp_kernel(int nj, int cfg, int nobs, bool prof = false) {
+  if (prof && nj == 5 && cfg == 3 && nobs <= 1) return k_cfs_warp<5, 32, 168, 1, true>;
   if (nj == 2) return warp_kernel_nj<2>(cfg, nobs > 1);
   if (nj == 5) return warp_kernel_nj<5>(cfg, nobs > 1);
   return nullptr;
@@ -555,8 +575,12 @@ int warp_max_grid(const SolveArgs &a, int device, int cfg) {
 }
 
 cudaError_t launch_warp(const SolveArgs &a, int grid, int cfg, cudaStream_t st) {
-  WarpKernel k = warp_kernel(a.nj, cfg, a.nobs);
+  WarpKernel k = warp_kernel(a.nj, cfg, a.nobs, a.prof != nullptr);
   if (!k) return cudaErrorInvalidValue;
+  if (a.prof) {  // the profiled instantiation is a function of its own: same opt-in limits as warp_max_grid sets
+    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  }
   k<<<grid, kWarpNT[cfg], warp_smem_bytes(a, cfg), st>>>(a);
   return cudaGetLastError();
 }
