@@ -369,3 +369,31 @@ def test_scheduling_options_never_change_results(ctx, oracle):
             assert np.array_equal(out[k], ref[k]), (name, k)
     with pytest.raises(M.CfsError, match="unknown option"):
         ctx.set_option("no_such_option", 1)
+
+
+def test_profiled_instantiation_returns_the_same_results(ctx, oracle):
+    """Timing level 3 runs the profiled instantiations (clock64 split of the warp tier: cfs_get_warp_profile, and of the QP core:
+    cfs_get_qp_profile).  Same results bit for bit, plausible counters: gradient + QP cycles inside the per-problem total, one
+    gradient pass per problem-iteration (a failed QP consumed its gradient pass too)."""
+    cfg = common.batch_m16ib(oracle, 96)
+    s = cfg["sys_info"]
+    r = dict(cfg["robot"])
+    r["name"] = "M16iB"
+    ctx.set_robot(r, 5)
+    ctx.set_obstacles(cfg["obs"])
+    ctx.set_cost(s["H"], s["QQ"], s["lim"], s["MAX_input"])
+    args = (cfg["x0"], cfg["ff"], cfg["caug"], cfg["xref"], s["epsilon_O"], s["MAX_O_ITER"])
+    ref = ctx.solve_batch(*args)
+    ctx.set_timing(3)
+    try:
+        out = ctx.solve_batch(*args)
+        wp = ctx.warp_profile()
+    finally:
+        ctx.set_timing(1)
+    for k in ("u", "x", "iters", "status"):
+        assert np.array_equal(out[k], ref[k]), k
+    grad, qp, total, passes, resident, sms = (int(v) for v in wp)
+    assert grad > 0 and qp > 0 and grad + qp < total and resident >= sms > 0
+    st = out["status"] & 0xFF
+    expect = int(out["iters"].sum() + (st >= 2).sum())   # problem-iterations incl. the failed last QP of a problem
+    assert 0.5 * expect <= passes <= expect + 96          # (iterations the heavy tier ran are not the warp tier's passes)
