@@ -72,9 +72,12 @@ int cfs_set_stream(cfs_ctx *ctx, void *cuda_stream);
  * every resident slot / 48 CTAs): caps of the two tiers' grids; "heavy_prio" (default 1): heavy tier on a
  * highest-priority stream; "warp" (default 1): bulk tier with one WARP per problem (k_warp.cu; 0 = one CTA per problem);
  * "warp_cfg" (default 3): its CTA shape (0: 12 warps x 1 CTA/SM, 1: 3 x 3, 2: 4 x 3, 3: 1 x 10, 4: 2 x 5); "warp_zs"
- * (default 0 = as many as fit): cached directions per warp kept in shared memory; "screen" (default 1): the warp tier runs in
- * two launches (outer iteration 1 | the rest) so that the heavy tier starts after the first; "heavy_cfg" (default 0): 1 =
- * slim heavy tier (64 x 64 inverse on chip, 168 registers). */
+ * (default 0 = as many as fit): cached directions per warp kept in shared memory; "screen" (default 2, 0..3): number of screening
+ * passes -- outer iterations 1..screen of the warp tier run in launches of their own, each followed by a heavy-tier launch for
+ * the long dual chains it found (on the high-priority stream, concurrent with the rest of the work); "heavy_cfg" (default 0):
+ * 1 = slim heavy tier (64 x 64 inverse on chip, 168 registers); "warp_qcap" (default 15): rows a working set may reach in
+ * the warp tier before the problem goes to the heavy tier; "one_shot", "warp_lockstep", "heavy_skip": measurement switches
+ * (DESIGN.md section 4b). */
 int cfs_set_option(cfs_ctx *ctx, const char *name, int value);
 
 /* ---- problem data ------------------------------------------------------------------------------------- */

@@ -140,8 +140,8 @@ struct SolveArgs {
   double *zslab;              // per-warp overflow of the direction cache: (WQ_QZ - warp_zs) * n doubles per resident warp
   int warp_zs;                // direction slots kept in shared memory
   int warp_qcap;              // working-set capacity of the warp tier (rows), <= 31; beyond it -> heavy tier
-  // phase 0: every problem start to finish.  phase 1 ("screen"): outer iteration 1 only; problems that are not finished go
-  // to cont_list.  phase 2: resume the problems of cont_list from outer iteration 2 (state in x / u / iters / touch).
+  // phase 0 / 1: fresh problems (all B).  phase 2: resume the problems of cont_list (state in x / u / iters / touch) from their
+  // next outer iteration.  How far a launch goes is set by it_stop below.
   int phase;
   int one_shot;               // warp tier: grid = one warp per problem, no work queue (CTAs leave the SM after one problem)
   int *cont_list, *cont_count;
