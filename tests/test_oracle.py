@@ -279,3 +279,37 @@ def test_solver_loop_against_an_independent_restatement(oracle, case):
     assert np.abs(x_ - g[case + ".x"]).max() < 1e-7 and np.abs(u - g[case + ".u"]).max() < 1e-7
     ref = g[case + ".cost_hist"][:iters]
     assert np.all(np.abs(cost_all - ref) <= 1e-7 * np.abs(ref))
+
+
+def test_oracle_infeasibility_verdicts_against_an_lp(oracle):
+    """The oracle's "QP infeasible" verdicts on the PSGCFS bench batch (M200i, H = 30, 2048 problems), checked by a phase-1 LP
+    (scipy / HiGHS) on the oracle's dense rows: min t s.t. A u - t <= b.  Includes the 8 problems on which the CUDA projection
+    used to return a point ("a parity bug this rule exposed"): the LP confirms the oracle on all of them."""
+    scipy_opt = pytest.importorskip("scipy.optimize")
+    import bench
+    from motionplanning_5d_m_b200 import synthetic
+    O = oracle
+    B, H = 2048, 30
+    c0 = synthetic.batch_config_m200i_psgcfs(B, bench.oracle_feasible(O, "M200i", [synthetic.OBS_M200I]), horizon=H, seed=synthetic.SEED)
+    s = c0["sys_info"]
+    n = H * 5
+    P = bench.make_oracle_problem(O, c0, 0, solver=1)
+    ref = P.solve_batch(c0["x0"], c0["ff"], c0["caug"], c0["xref"], noise=c0["noise"])
+    st = ref["status"] & 0xFF
+    first_infeasible = np.where((st == 2) & (ref["iters"] == 0))[0]
+    assert len(first_infeasible) > 100
+    disputed = [646, 652, 1325, 1376, 1521, 1651, 1706, 2021]
+    assert all(b in first_infeasible for b in disputed)
+    feasible = np.where(st == 1)[0][:6]
+    for b in list(disputed) + list(first_infeasible[:6]) + list(feasible):
+        A_, b_, _, _, _, _ = P.get_con(c0["x0"][b], c0["xref"][b], np.zeros(n))
+        m = A_.shape[0]
+        cvec = np.zeros(n + 1)
+        cvec[-1] = 1.0
+        res = scipy_opt.linprog(cvec, A_ub=np.hstack([A_, -np.ones((m, 1))]), b_ub=b_, bounds=[(None, None)] * n + [(-1.0, None)],
+                                method="highs")
+        assert res.status == 0
+        if st[b] == 2:
+            assert res.fun > 1e-6, (b, res.fun)      # no u satisfies every row: the smallest maximal violation is positive
+        else:
+            assert res.fun < -1e-6, (b, res.fun)
