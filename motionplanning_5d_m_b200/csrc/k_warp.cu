@@ -18,6 +18,9 @@
 // The robot/obstacle tables are staged once per CTA by one TMA bulk copy (UBLKCP) and shared by its warps.
 // Problems whose working set outgrows 15 rows, or that need more than esc_steps dual steps in one QP, are handed to the heavy
 // tier (k_fused.cu, tier 1), which resumes them from their last completed outer iteration.
+// One solve is several launches of this kernel (cfs_api.cu, "screening passes"): a launch with it_stop = k stops every problem
+// after outer iteration k and appends the unfinished ones to a continuation list that the next launch resumes (phase 2), so
+// that the heavy tier can start on the long dual chains of the early iterations while most of the work is still ahead.
 #include "cfs_geom.cuh"
 #include "qp_warp.cuh"
 
