@@ -60,12 +60,12 @@ def parse_args():
     ap.add_argument("--batch", type=int, default=0, help="problems (cfs 4096, psgcfs 2048) / RRT seeds (rrtstar 1024) per GPU and step")
     ap.add_argument("--horizon", type=int, default=0, help="cfs 50, psgcfs 30, rrtstar 40")
     ap.add_argument("--grad", default="numjac", choices=["numjac", "derivest"])
-    ap.add_argument("--contexts", type=int, default=0, help="library contexts (streams + buffer sets) the steps rotate over (cfs 24, else 8)")
+    ap.add_argument("--contexts", type=int, default=0, help="library contexts (streams + buffer sets) the steps rotate over (cfs and psgcfs 24, rrtstar 8)")
     ap.add_argument("--cpu-reps", type=int, default=3, help="CPU baseline: passes of the oracle over the same batch")
     a = ap.parse_args()
     a.batch = a.batch or {"cfs": 4096, "psgcfs": 2048, "rrtstar": 1024}[a.config]
     a.horizon = a.horizon or {"cfs": 50, "psgcfs": 30, "rrtstar": 40}[a.config]
-    a.contexts = a.contexts or {"cfs": 24, "psgcfs": 8, "rrtstar": 8}[a.config]
+    a.contexts = a.contexts or {"cfs": 24, "psgcfs": 24, "rrtstar": 8}[a.config]
     return a
 
 
