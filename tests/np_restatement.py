@@ -367,3 +367,80 @@ def chomp_optimizer(s, robot, obs_list, kind, uu):
         cost_all.append(0.5 * u @ QQ @ u + ff @ u + caug + fobs)
         e_u_all.append(np.linalg.norm(u_old - u))
     return u, x_, np.array(cost_all), np.array(e_u_all)
+
+
+def rrt_find_route(robot, kind, obs_list, x0, goal, goal_th, region_g, region_s, sample_off, ratial, rnd, bi=0.5, max_iter=400,
+                   star=False):
+    """RRT_FANUC.find_route (Lib/RRT_FANUC.m:63-207) with MATLAB's rand replaced by the stream `rnd`, consumed in the reference's
+    order (pp = rand; rand(nstate,1) when pp < bi -- :108,111).  1-based parents as in all_nodes(1,:); -1 for the root.
+    Returns route (nj, len), all_nodes (1+nj, node_num), total_dis, fail, numbers of the stream consumed."""
+    nj = len(x0)
+    it = iter(np.asarray(rnd, dtype=np.float64))
+    used = [0]
+
+    def rand():
+        used[0] += 1
+        return next(it)
+
+    def feasible(theta):                                         # :146-181
+        for ob in obs_list:
+            DH = robot["DH"][:nj].copy()
+            DH[:, 0] = theta
+            if kind == "M200i":
+                DH[1, 0] = DH[1, 0] - np.pi / 2
+            pos = cap_pos(robot["base"], DH, [c["p"] for c in robot["cap"]])
+            for i in range(nj):
+                dis, pts = dist_lin_seg(pos[i][:, 0], pos[i][:, 1], ob["l"][:, 0], ob["l"][:, 1])
+                if abs(dis) < 0.0001:
+                    dis = -np.linalg.norm(pts[:3] - pos[i][:, 1])
+                if dis < ob["D"]:
+                    return False
+        return True
+
+    new = np.array(x0, dtype=np.float64)
+    all_nodes = np.concatenate([[-1.0], new])[:, None]
+    total_dis = [0.0]
+    node_num, fail, parent = 1, False, 1
+    to_dis = []
+
+    def reached():                                               # :193-207
+        nonlocal fail
+        ok = bool(np.all(goal - region_g < new) and np.all(new < goal + region_g))
+        if node_num > max_iter:
+            fail = True
+            ok = True
+        return ok
+
+    done = reached()
+    while not done:
+        while True:                                              # getNode, :97-104
+            pp = rand()
+            if pp < bi:
+                sample = (np.array([rand() for _ in range(nj)]) - 0.5) * region_s * 2 + sample_off
+            else:
+                sample = np.array(goal_th, dtype=np.float64)
+            to_dis = [np.linalg.norm((all_nodes[1:, i] - sample) * ratial) for i in range(node_num)]
+            parent = int(np.argmin(to_dis)) + 1                  # strict <: the first minimum (:120-127)
+            pn = all_nodes[1:, parent - 1]
+            new = pn + (sample - pn) * 0.1 / np.linalg.norm(pn - sample)
+            if feasible(new):
+                break
+        all_nodes = np.hstack([all_nodes, np.concatenate([[parent], new])[:, None]])   # addNode, :184-190
+        total_dis.append(total_dis[parent - 1] + to_dis[parent - 1])
+        node_num += 1
+        if star:                                                 # arrangeNode, :134-142
+            for i in range(len(to_dis)):
+                if to_dis[i] < 0.2 and total_dis[i] > total_dis[-1] + to_dis[i]:
+                    all_nodes[0, i] = node_num
+                    total_dis[i] = total_dis[-1] + to_dis[i]
+        done = reached()
+    route = new[:, None]
+    p = parent if node_num > 1 else -1
+    if node_num == 1:
+        p = -1
+    guard = 0
+    while p != -1 and guard <= node_num:
+        route = np.hstack([all_nodes[1:, int(p) - 1][:, None], route])
+        p = all_nodes[0, int(p) - 1]
+        guard += 1
+    return route, all_nodes, np.array(total_dis), fail, used[0]

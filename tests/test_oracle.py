@@ -313,3 +313,32 @@ def test_oracle_infeasibility_verdicts_against_an_lp(oracle):
             assert res.fun > 1e-6, (b, res.fun)      # no u satisfies every row: the smallest maximal violation is positive
         else:
             assert res.fun < -1e-6, (b, res.fun)
+
+
+@pytest.mark.parametrize("star", [False, True])
+def test_rrt_find_route_against_an_independent_restatement(oracle, star):
+    """orc_rrt_find_route against tests/np_restatement.py's own RRT_FANUC.find_route (own FK / distLinSeg / feasibility, python
+    lists for the tree) on the scene of RRTstar_CFS.m, same uniform stream: same parents, node counts, numbers consumed and
+    failure flags; nodes, accumulated distances and the route to 1e-12."""
+    from motionplanning_5d_m_b200 import rrt
+    O = oracle
+    sc = rrt.SCENE_RRTSTAR
+    robot = M.robotproperty2("M200i")
+    rb = dict(robot)
+    rb["cap"] = [{"p": np.asarray(c["p"], dtype=np.float64)[:, :2]} for c in robot["cap"]]
+    r = O.robot("M200i")
+    found = 0
+    for seed, max_iter in ((1, 400), (0, 120), (2, 120), (3, 120)):   # seed 1 reaches the goal box after 186 nodes, the others hit MAX_ITER
+        rnd = np.random.default_rng(900 + seed).random(4096)
+        a = O.rrt_find_route(r, sc["obs"], [o["D"] for o in sc["obs"]], sc["x0"], sc["goal"], sc["region_g"], sc["region_s"],
+                             sc["sample_off"], sc["goal"], sc["ratial"], rnd, max_iter=max_iter, star=star)
+        route, nodes, tot, fail, used = NP.rrt_find_route(rb, "M200i", sc["obs"], sc["x0"], sc["goal"], sc["goal"], sc["region_g"],
+                                                          sc["region_s"], sc["sample_off"], sc["ratial"], rnd, max_iter=max_iter,
+                                                          star=star)
+        assert a is not None
+        assert a["n_nodes"] == nodes.shape[1] and a["fail"] == fail and a["rnd_used"] == used
+        assert np.array_equal(a["parent"], nodes[0].astype(np.int32))
+        assert np.abs(a["nodes"] - nodes[1:].T).max() < 1e-12 and np.abs(a["total_dis"] - tot).max() < 1e-12
+        assert a["route"].shape == route.T.shape and np.abs(a["route"] - route.T).max() < 1e-12
+        found += 0 if fail else 1
+    assert found >= 1 and found < 4   # both exits of find_route are exercised: goal box reached, MAX_ITER
