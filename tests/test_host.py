@@ -4,6 +4,7 @@ import os
 import re
 
 import numpy as np
+import pytest
 
 import motionplanning_5d_m_b200 as M
 from motionplanning_5d_m_b200 import _lib, problem
@@ -146,3 +147,19 @@ def test_flat_fixture_round_trip(oracle, tmp_path):
     # column-major on disk: the first 8 values of QQ in the file are its first COLUMN
     off = raw.index(b"QQ".ljust(32, b"\0")) + 32 + 4 + 16
     assert np.array_equal(np.frombuffer(raw[off:off + 64], dtype="<f8"), cfg["sys_info"]["QQ"][:8, 0])
+
+
+def test_cubicpolytraj_against_a_hermite_spline():
+    """problem.cubicpolytraj (the toolbox default RRTstar_CFS.m:100 relies on: zero velocity at every waypoint) against scipy's
+    cubic Hermite interpolant with zero end slopes on every segment -- an independent construction of the same piecewise cubic."""
+    interp = pytest.importorskip("scipy.interpolate")
+    from motionplanning_5d_m_b200 import problem
+    rng = np.random.default_rng(5)
+    for W, T in ((2, 41), (7, 41), (23, 31)):
+        wp = rng.standard_normal((5, W))
+        tw = np.linspace(0.0, 3.7, W)
+        tt = np.linspace(0.0, 3.7, T)
+        ours = problem.cubicpolytraj(wp, tw, tt)
+        ref = interp.CubicHermiteSpline(tw, wp, np.zeros_like(wp), axis=1)(tt)
+        np.testing.assert_allclose(ours, ref, rtol=0, atol=1e-12)
+        assert np.array_equal(ours[:, 0], wp[:, 0]) and np.abs(ours[:, -1] - wp[:, -1]).max() < 1e-15
